@@ -1,0 +1,171 @@
+/*
+ * smap.h -- C ABI of the B200 (sm_100a) semantic-mapping hot path.
+ *
+ * The reference (AutonomousVehicleLaboratory/vision_semantic_segmentation) is pure
+ * Python/numpy and has no FFI of its own; the boundary it offers is
+ * the Python mapping API.  This header is the C ABI that sits directly under that
+ * API: every entry point names the reference statements it replaces (paths relative
+ * to the reference root).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *   - return value: 0 = SMAP_OK, negative = error; smap_last_error() gives the text
+ *     (thread-local).  Nothing throws across this boundary.
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers
+ *     are host memory.  `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream).  Calls only ENQUEUE work unless documented as synchronising.
+ *   - one handle per GPU; a handle is not thread-safe.
+ *   - the BEV grid is (map_height, map_width, num_classes) float64, C-contiguous,
+ *     axis 0 <- world x, axis 1 <- world y (src/mapping_replay.py:80,181).
+ */
+#ifndef SMAP_B200_H_
+#define SMAP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SMAP_API __attribute__((visibility("default")))
+#else
+#define SMAP_API
+#endif
+
+#define SMAP_ABI_VERSION 1
+#define SMAP_MAX_CLASSES 31 /* class bits 0..30 + 1 intensity-boost bit in a 32-bit cell mask */
+#define SMAP_MAX_CAMERAS 8
+
+enum {
+    SMAP_OK = 0,
+    SMAP_ERR_INVALID = -1,  /* bad argument */
+    SMAP_ERR_CUDA = -2,     /* a CUDA runtime call failed */
+    SMAP_ERR_NOMEM = -3,    /* allocation failed */
+    SMAP_ERR_STATE = -4,    /* call order: classes / camera not set */
+    SMAP_ERR_NO_DEVICE = -5 /* no usable sm_100 device */
+};
+
+/* point-cloud layouts accepted by the kernels */
+enum {
+    SMAP_PTS_F32X4 = 0,  /* N x {x, y, z, intensity} float32, 16-byte aligned (PointCloud2 / float4) */
+    SMAP_PTS_F64_SOA = 1 /* (4, N) float64 rows x, y, z, intensity with row stride `ld` (the reference's pcd) */
+};
+
+typedef struct smap_handle smap_handle;
+
+/* Replaces the constructor arithmetic of SemanticMapping.__init__ (src/mapping_replay.py:86-94). */
+typedef struct smap_config {
+    int32_t map_height;      /* int((B[0][1]-B[0][0]) / res) */
+    int32_t map_width;       /* int((B[1][1]-B[1][0]) / res) */
+    int32_t num_classes;     /* len(cfg.LABELS), 1..31 */
+    int32_t use_intensity;   /* cfg.MAPPING.PCD.USE_INTENSITY */
+    int32_t lane_index;      /* index of the class named "lane", -1 if none (src/mapping_replay.py:288) */
+    int32_t device;          /* CUDA device ordinal */
+    double boundary_x_min;   /* cfg.MAPPING.BOUNDARY[0][0] */
+    double boundary_y_min;   /* cfg.MAPPING.BOUNDARY[1][0] */
+    double resolution;       /* cfg.MAPPING.RESOLUTION */
+    double origin_offset_x;  /* 1369.0496826171875  (src/mapping_replay.py:261) */
+    double origin_offset_y;  /* 562.84814453125 */
+    double range_max;        /* cfg.MAPPING.PCD.RANGE_MAX */
+    void *map_dev;           /* caller-owned grid (MH*MW*C doubles) or NULL: the handle allocates it */
+} smap_config;
+
+/* One frame of the batched fused path. */
+typedef struct smap_frame {
+    const void *points_dev;   /* cloud, layout below */
+    int64_t n_points;
+    int64_t ld;               /* row stride for SMAP_PTS_F64_SOA, ignored for F32X4 */
+    int32_t layout;           /* SMAP_PTS_* */
+    int32_t camera;           /* slot set with smap_set_camera */
+    const uint8_t *image_dev; /* (H, W, 3) uint8 RGB colour-coded label image */
+    int32_t image_width;
+    int32_t image_height;
+    int32_t has_transform;    /* 0: cloud already in the velodyne frame (pcd_frame_id == "velodyne") */
+    int32_t reserved;
+    double world_to_velodyne[16]; /* row-major 4x4 = inv(T_base_to_origin(pose) @ T_velodyne_to_baselink) */
+} smap_frame;
+
+/* counters of the most recent frame(s); see smap_get_stats */
+typedef struct smap_stats {
+    int64_t frames;          /* frames integrated since create / clear */
+    int64_t points;          /* points read */
+    int64_t touched_cells;   /* K of the last deterministic frame (distinct cells updated) */
+    int64_t kernel_launches; /* kernels launched by this handle */
+} smap_stats;
+
+SMAP_API int smap_abi_version(void);
+SMAP_API const char *smap_last_error(void);
+
+/* Number of visible CUDA devices (<0 on error) and name / SM count / compute capability of one. */
+SMAP_API int smap_device_count(void);
+SMAP_API int smap_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
+
+SMAP_API int smap_create(const smap_config *cfg, smap_handle **out);
+SMAP_API int smap_destroy(smap_handle *h);
+
+/* Camera projection matrix P = K [R t] (3x4 row-major, src/camera.py:28) for a slot. */
+SMAP_API int smap_set_camera(smap_handle *h, int camera, const double P_host[12]);
+
+/* cfg.LABEL_COLORS (C x 3 uint8) and the update matrix (C x C float64 row-major): np.eye(C) for the
+ * count update or ConfusionMatrix.get_submatrix(LABELS, True, True) (src/mapping_replay.py:104-109).
+ * Column i is added to a cell when class i is observed there (src/mapping_replay.py:281). */
+SMAP_API int smap_set_classes(smap_handle *h, const uint8_t *colors_host, const double *cm_host);
+
+/* ---- parity API: SemanticMapping.project_pcd (src/mapping_replay.py:214-246) -------------------
+ * Transform, project, cull (range + frustum), stable compaction, label gather.
+ * Outputs have room for n points with row stride out_ld (>= n):
+ *   out_pcd   (4, out_ld) float64  masked_pcd = pcd[:, mask]       (original coordinates + intensity)
+ *   out_label (3, out_ld) uint8    label = image[v, u].T
+ *   out_uv    (2, out_ld) int32    image_idx = IXY[:, mask]        (may be NULL)
+ *   out_keep  (n) uint8            the mask itself                 (may be NULL)
+ * SYNCHRONISES the stream to return M in *m_host. */
+SMAP_API int smap_project(smap_handle *h, const smap_frame *frame, double *out_pcd_dev, uint8_t *out_label_dev,
+                 int32_t *out_uv_dev, uint8_t *out_keep_dev, int64_t out_ld, int64_t *m_host, void *stream);
+
+/* ---- parity API: SemanticMapping.update_map (src/mapping_replay.py:248-301) --------------------
+ * pcd (4, M) float64 row stride ld, label (3, M) uint8 row stride ldl; updates `map_dev` (NULL = the
+ * handle's own grid) in place, de-duplicated per (cell, class) within the call, classes applied in
+ * ascending order -> bit-exact with the reference, log-likelihood mode included. */
+SMAP_API int smap_update(smap_handle *h, double *map_dev, const double *pcd_dev, int64_t ld, const uint8_t *label_dev,
+                int64_t ldl, int64_t m, void *stream);
+
+/* ---- fused path: project_pcd + update_map of ONE frame, nothing materialised -------------------
+ * (src/mapping_replay.py:184-192 loop body).  Deterministic: bit-exact in both update modes. */
+SMAP_API int smap_integrate(smap_handle *h, const smap_frame *frame, void *stream);
+
+/* Batched fused path: all frames in one launch.  Frames are de-duplicated independently (frame-slotted
+ * cell masks) and their increments added with atomics: exact for the count update (integer-valued
+ * doubles), order-dependent rounding (<= 1e-12 relative) for log-likelihood matrices. */
+SMAP_API int smap_integrate_batch(smap_handle *h, const smap_frame *frames_host, int n_frames, void *stream);
+
+/* Same as smap_integrate with HOST buffers: points (layout as in frame) and image are copied to the
+ * device through the handle's staging ring inside the call (async on `stream`; pass pinned memory
+ * for overlap).  frame->points_dev / image_dev hold HOST pointers here. */
+SMAP_API int smap_integrate_host(smap_handle *h, const smap_frame *frame_with_host_ptrs, void *stream);
+
+/* ---- rendering: free functions of src/renderer.py, any grid ------------------------------------ */
+/* apply_filter: cv2.filter2D 3x3 box, BORDER_REFLECT_101 (src/renderer.py:175-189). src != dst. */
+SMAP_API int smap_apply_filter(const double *src_dev, int mh, int mw, int c, double *dst_dev, int device, void *stream);
+/* render_bev_map: argmax colour, zero-sum cells black (src/renderer.py:32-59). */
+SMAP_API int smap_render(const double *map_dev, int mh, int mw, int c, const uint8_t *colors_host, uint8_t *rgb_dev,
+                int device, void *stream);
+/* apply_filter + render_bev_map in one pass (src/mapping_replay.py:198-200); filtered_dev may be NULL. */
+SMAP_API int smap_filter_render(const double *map_dev, int mh, int mw, int c, const uint8_t *colors_host,
+                       uint8_t *rgb_dev, double *filtered_dev, int device, void *stream);
+/* render_bev_map_with_thresholds (src/renderer.py:131-172): priority (C ints, low -> high),
+ * thresholds (C doubles, indexed by paint step as in the reference). */
+SMAP_API int smap_render_thresholds(const double *map_dev, int mh, int mw, int c, const uint8_t *colors_host,
+                           const int32_t *priority_host, const double *thresholds_host, uint8_t *rgb_dev,
+                           int device, void *stream);
+
+/* ---- grid access ------------------------------------------------------------------------------- */
+SMAP_API int smap_map_ptr(smap_handle *h, double **map_dev, int64_t *n_elements);
+SMAP_API int smap_clear(smap_handle *h, void *stream);            /* self.map = np.zeros(...)  src/mapping_replay.py:181 */
+SMAP_API int smap_download(smap_handle *h, double *map_host);     /* synchronises */
+SMAP_API int smap_upload(smap_handle *h, const double *map_host); /* synchronises */
+SMAP_API int smap_get_stats(smap_handle *h, smap_stats *out);     /* synchronises the handle's last stream */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMAP_B200_H_ */

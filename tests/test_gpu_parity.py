@@ -1,0 +1,177 @@
+"""GPU: the CUDA path (through the C ABI) against the golden vectors of the real reference and
+against the C oracle on the same seeded inputs.  Bit-exact everywhere (integer indices, labels,
+count grids, log-likelihood grids in the deterministic path, rendered images)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import c_oracle  # noqa: E402
+from tests.common import Case, GOLDEN_CASES, sha  # noqa: E402
+from vision_semantic_segmentation_b200 import synthetic as syn  # noqa: E402
+from vision_semantic_segmentation_b200.device_mapper import DeviceMapper  # noqa: E402
+from vision_semantic_segmentation_b200 import renderer  # noqa: E402
+from vision_semantic_segmentation_b200.utils import transforms as tr  # noqa: E402
+
+
+def make_mapper(case):
+    return DeviceMapper(case.mh, case.mw, case.colors, case.cm, case.boundary, case.resolution, case.range_max,
+                        case.use_intensity, case.lane, cameras=[case.cam], device=0)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("layout", ["f32x4", "f64soa"])
+def test_fused_path_matches_reference_golden(name, layout):
+    case = Case(name)
+    dm = make_mapper(case)
+    for f, out in enumerate(case.spec["frames_out"]):
+        pcd, points, image, T = case.frame(f)
+        cloud = dev(points) if layout == "f32x4" else dev(pcd)
+        dm.integrate(dm.make_frame(cloud, dev(image), T, 0))
+        assert sha(dm.map.cpu().numpy()) == out["map_sha_after"], "frame %d" % f
+    grid = dm.map.cpu().numpy()
+    assert sha(grid) == case.spec["map_sha"]
+    # fused filter + render, and the separate kernels
+    rgb, filtered = renderer.filter_and_render(dm.map, case.colors, return_filtered=True)
+    assert sha(filtered.cpu().numpy()) == case.spec["filtered_sha"]
+    assert np.array_equal(rgb.cpu().numpy(), case.arrays["rgb"])
+    assert sha(renderer.apply_filter(dm.map).cpu().numpy()) == case.spec["filtered_sha"]
+    assert sha(renderer.render_bev_map(filtered, case.colors).cpu().numpy()) == case.spec["rgb_sha"]
+    assert sha(renderer.render_bev_map(dm.map, case.colors).cpu().numpy()) == case.spec["rgb_raw_sha"]
+    thr = renderer.render_bev_map_with_thresholds(dm.map, case.colors, case.spec["priority"], case.spec["thresholds"])
+    assert np.array_equal(thr.cpu().numpy(), case.arrays["rgb_thr"])
+    dm.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_parity_api_project_and_update(name):
+    case = Case(name)
+    dm = make_mapper(case)
+    for f, out in enumerate(case.spec["frames_out"]):
+        pcd, points, image, T = case.frame(f)
+        for cloud in (dev(points), dev(pcd)):
+            masked, label, uv, keep = dm.project(dm.make_frame(cloud, dev(image), T, 0), want_uv=True, want_keep=True)
+            assert masked.shape[1] == out["M"]
+            assert np.array_equal(np.flatnonzero(keep.cpu().numpy()), case.arrays["keep_idx_%d" % f])
+            assert sha(masked.cpu().numpy()) == out["masked_pcd_sha"]
+            assert sha(label.cpu().numpy()) == out["label_sha"]
+            assert sha(uv.cpu().numpy()) == out["uv_sha"]
+        dm.update(masked, label)
+        assert sha(dm.map.cpu().numpy()) == out["map_sha_after"]
+    dm.close()
+
+
+def test_edge_cases_empty_nonfinite_truncation():
+    case = Case("cfg1_c5_count")
+    dm = make_mapper(case)
+    image = dev(np.zeros((1440, 1920, 3), np.uint8))
+    # empty cloud, both layouts
+    for cloud in (torch.empty((0, 4), dtype=torch.float32, device="cuda"),
+                  torch.empty((4, 0), dtype=torch.float64, device="cuda")):
+        fr = dm.make_frame(cloud, image, np.eye(4), 0)
+        dm.integrate(fr)
+        masked, label = dm.project(fr)
+        assert masked.shape == (4, 0) and label.shape == (3, 0)
+        dm.update(masked, label)
+    assert not dm.map.any().item()
+    # truncation toward zero keeps a point 0.05 m below the boundary in cell 0; non-finite points vanish
+    pcd = np.array([[100 - 1369.0496826171875 - 0.05, np.nan, np.inf], [800 - 562.84814453125 + 0.05, 0.0, 0.0],
+                    [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
+    lab = np.array([[128, 128, 128], [64, 64, 64], [128, 128, 128]], np.uint8)
+    dm.update(dev(pcd), dev(lab))
+    got = dm.map.cpu().numpy()
+    assert got[0, 0, 0] == 1.0 and got.sum() == 1.0
+    bad = np.array([[np.nan, np.inf, -np.inf, 1e300], [0.0, 0.0, 0.0, 1e300], [0.0, 0.0, 0.0, -1e300], [0.0] * 4])
+    _, _, keep = dm.project(dm.make_frame(dev(bad), image, np.eye(4), 0), want_keep=True)
+    assert not keep.any().item()
+    dm.close()
+
+
+@pytest.mark.parametrize("c", [2, 5, 8, 9, 16, 19, 31, 32])
+def test_render_kernels_follow_numpy_order_on_general_data(c):
+    rng = np.random.default_rng(100 + c)
+    m = rng.choice([1e16, -1e16, 1.0, -1.0, 3.0, 0.1, -0.1, 0.0, 2.5e-7], size=(37, 71, c))
+    m[0, 0, :] = 0.0
+    m[1, 1, c // 2] = np.nan
+    m[2, 2, c - 1] = np.inf
+    m[3, 3, 0] = -np.inf
+    colors = rng.integers(0, 256, (c, 3))
+    pr, th = rng.permutation(c), rng.uniform(-0.5, 0.5, c)
+    md = dev(m)
+    with np.errstate(all="ignore"):
+        assert np.array_equal(renderer.render_bev_map(md, colors).cpu().numpy(), c_oracle.render_bev_map(m, colors))
+        assert np.array_equal(renderer.render_bev_map_with_thresholds(md, colors, pr, th).cpu().numpy(),
+                              c_oracle.render_bev_map_with_thresholds(m, colors, pr, th))
+        smooth = rng.normal(0, 1e3, (37, 71, c)) * rng.choice([1.0, 1e-9, 1e9], (37, 71, c))
+        want = c_oracle.apply_filter(smooth)
+        assert np.array_equal(renderer.apply_filter(dev(smooth)).cpu().numpy(), want)
+        rgb, filt = renderer.filter_and_render(dev(smooth), colors, return_filtered=True)
+        assert np.array_equal(filt.cpu().numpy(), want)
+        assert np.array_equal(rgb.cpu().numpy(), c_oracle.render_bev_map(want, colors))
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 3), (1, 7, 2), (6, 1, 4), (2, 2, 2), (8, 32, 5), (9, 33, 5), (64, 100, 19)])
+def test_filter_borders(shape):
+    rng = np.random.default_rng(7)
+    src = rng.normal(0, 10, shape)
+    assert np.array_equal(renderer.apply_filter(dev(src)).cpu().numpy(), c_oracle.apply_filter(src))
+
+
+@pytest.mark.parametrize("full19,log_cm", [(False, False), (True, False), (True, True)])
+def test_full_size_frame_against_oracle(full19, log_cm):
+    """BASELINE.json configs[1] shape: 2M-point cloud + 1920x1440 frame, checked in full against the oracle,
+    plus size-independent properties (linearity of the count grid in the number of replays)."""
+    labels, names, colors = syn.class_setup(full19)
+    c = len(labels)
+    cm = np.eye(c)
+    if log_cm:
+        from oracle import numpy_port
+        cm = numpy_port.confusion_submatrix_log(syn.synthetic_confusion_matrix(7), labels)
+    from vision_semantic_segmentation_b200.camera import camera_setup_1
+    cam = camera_setup_1()
+    boundary, res, mh, mw = [[100, 300], [800, 1000]], 0.1, 2000, 2000
+    lane = names.index("lane")
+    dm = DeviceMapper(mh, mw, colors, cm, boundary, res, 100.0, True, lane, cameras=[cam], device=0)
+    ref = np.zeros((mh, mw, c))
+    for f in range(2):
+        fr = syn.synthetic_frame(1000, f, 2000000, blocky=(f == 1))
+        T = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
+        dm.integrate(dm.make_frame(dev(fr["points"]), dev(fr["semantic_image"]), T, 0))
+        mp, lab, _, _ = c_oracle.project_pcd(fr["pcd"], T, cam.P, fr["semantic_image"], 100.0)
+        st = c_oracle.update_map(ref, mp, lab, colors, cm, boundary, res, True, lane)
+        assert dm.stats()["touched_cells"] == st[1]
+        assert np.array_equal(dm.map.cpu().numpy(), ref), "frame %d" % f
+    if not log_cm:
+        # replaying the same two frames again doubles every count exactly
+        for f in range(2):
+            fr = syn.synthetic_frame(1000, f, 2000000, blocky=(f == 1))
+            T = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
+            dm.integrate(dm.make_frame(dev(fr["points"]), dev(fr["semantic_image"]), T, 0))
+        assert np.array_equal(dm.map.cpu().numpy(), 2.0 * ref)
+    rgb = renderer.filter_and_render(dm.map, colors)
+    want = c_oracle.render_bev_map(c_oracle.apply_filter(dm.map.cpu().numpy()), colors)
+    assert np.array_equal(rgb.cpu().numpy(), want)
+    dm.close()
+
+
+def test_host_staged_integrate_matches_device_path():
+    case = Case("cfg1_c19_count")
+    a, b = make_mapper(case), make_mapper(case)
+    keep = []
+    for f in range(3):
+        pcd, points, image, T = case.frame(f)
+        a.integrate(a.make_frame(dev(points), dev(image), T, 0))
+        hp, hi = torch.from_numpy(points).pin_memory(), torch.from_numpy(image).pin_memory()
+        keep.append((hp, hi))
+        b.integrate_host(b.make_frame(hp, hi, T, 0, host=True))
+    torch.cuda.synchronize()
+    assert sha(b.map.cpu().numpy()) == case.spec["map_sha"]
+    assert torch.equal(a.map, b.map)
+    a.close()
+    b.close()

@@ -1,0 +1,135 @@
+"""ctypes binding of the C ABI in ``include/smap.h`` (``csrc/libsmap_b200.so``).
+
+This is the only door between the Python host code and the CUDA kernels.  There is no
+CPU fallback: if the library is missing, or no CUDA device is present when a device
+call is made, the call raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsmap_b200.so")
+
+SMAP_PTS_F32X4 = 0
+SMAP_PTS_F64_SOA = 1
+SMAP_MAX_CLASSES = 31
+SMAP_MAX_CAMERAS = 8
+
+EXPORTS = [
+    "smap_abi_version", "smap_last_error", "smap_device_count", "smap_device_info", "smap_create",
+    "smap_destroy", "smap_set_camera", "smap_set_classes", "smap_project", "smap_update", "smap_integrate",
+    "smap_integrate_batch", "smap_integrate_host", "smap_apply_filter", "smap_render", "smap_filter_render",
+    "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_download", "smap_upload", "smap_get_stats",
+]
+
+
+class SmapConfig(ctypes.Structure):
+    _fields_ = [
+        ("map_height", ctypes.c_int32), ("map_width", ctypes.c_int32), ("num_classes", ctypes.c_int32),
+        ("use_intensity", ctypes.c_int32), ("lane_index", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("boundary_x_min", ctypes.c_double), ("boundary_y_min", ctypes.c_double), ("resolution", ctypes.c_double),
+        ("origin_offset_x", ctypes.c_double), ("origin_offset_y", ctypes.c_double), ("range_max", ctypes.c_double),
+        ("map_dev", ctypes.c_void_p),
+    ]
+
+
+class SmapFrame(ctypes.Structure):
+    _fields_ = [
+        ("points_dev", ctypes.c_void_p), ("n_points", ctypes.c_int64), ("ld", ctypes.c_int64),
+        ("layout", ctypes.c_int32), ("camera", ctypes.c_int32), ("image_dev", ctypes.c_void_p),
+        ("image_width", ctypes.c_int32), ("image_height", ctypes.c_int32), ("has_transform", ctypes.c_int32),
+        ("reserved", ctypes.c_int32), ("world_to_velodyne", ctypes.c_double * 16),
+    ]
+
+
+class SmapStats(ctypes.Structure):
+    _fields_ = [("frames", ctypes.c_int64), ("points", ctypes.c_int64), ("touched_cells", ctypes.c_int64),
+                ("kernel_launches", ctypes.c_int64)]
+
+
+class SmapError(RuntimeError):
+    def __init__(self, code, message):
+        super(SmapError, self).__init__("smap error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "CUDA extension %s not found; build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C vision_semantic_segmentation_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    L.smap_abi_version.restype = i32
+    L.smap_abi_version.argtypes = []
+    L.smap_last_error.restype = ctypes.c_char_p
+    L.smap_last_error.argtypes = []
+    L.smap_device_count.restype = i32
+    L.smap_device_count.argtypes = []
+    L.smap_device_info.restype = i32
+    L.smap_device_info.argtypes = [i32, ctypes.c_char_p, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.smap_create.restype = i32
+    L.smap_create.argtypes = [ctypes.POINTER(SmapConfig), ctypes.POINTER(vp)]
+    L.smap_destroy.restype = i32
+    L.smap_destroy.argtypes = [vp]
+    L.smap_set_camera.restype = i32
+    L.smap_set_camera.argtypes = [vp, i32, ctypes.POINTER(dbl)]
+    L.smap_set_classes.restype = i32
+    L.smap_set_classes.argtypes = [vp, vp, vp]
+    L.smap_project.restype = i32
+    L.smap_project.argtypes = [vp, ctypes.POINTER(SmapFrame), vp, vp, vp, vp, i64, ctypes.POINTER(i64), vp]
+    L.smap_update.restype = i32
+    L.smap_update.argtypes = [vp, vp, vp, i64, vp, i64, i64, vp]
+    L.smap_integrate.restype = i32
+    L.smap_integrate.argtypes = [vp, ctypes.POINTER(SmapFrame), vp]
+    L.smap_integrate_batch.restype = i32
+    L.smap_integrate_batch.argtypes = [vp, ctypes.POINTER(SmapFrame), i32, vp]
+    L.smap_integrate_host.restype = i32
+    L.smap_integrate_host.argtypes = [vp, ctypes.POINTER(SmapFrame), vp]
+    L.smap_apply_filter.restype = i32
+    L.smap_apply_filter.argtypes = [vp, i32, i32, i32, vp, i32, vp]
+    L.smap_render.restype = i32
+    L.smap_render.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
+    L.smap_filter_render.restype = i32
+    L.smap_filter_render.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp]
+    L.smap_render_thresholds.restype = i32
+    L.smap_render_thresholds.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
+    L.smap_map_ptr.restype = i32
+    L.smap_map_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+    L.smap_clear.restype = i32
+    L.smap_clear.argtypes = [vp, vp]
+    L.smap_download.restype = i32
+    L.smap_download.argtypes = [vp, vp]
+    L.smap_upload.restype = i32
+    L.smap_upload.argtypes = [vp, vp]
+    L.smap_get_stats.restype = i32
+    L.smap_get_stats.argtypes = [vp, ctypes.POINTER(SmapStats)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise SmapError(rc, (load().smap_last_error() or b"").decode("utf-8", "replace"))
+    return rc
+
+
+def require_cuda():
+    """torch supplies device memory and streams; the kernels need a CUDA device. No fallback."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("vision_semantic_segmentation_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback for the mapping path.")
+    return torch
+
+
+def current_stream_ptr(device=None):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,549 @@
+// C ABI (include/smap.h) of the B200 semantic-mapping path: host-side launch logic.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/smap.h"
+#include "smap_kernels.cuh"
+
+using namespace smap;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, a, b);
+    g_err = buf;
+    return code;
+}
+
+#define CK(expr)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess) return fail(SMAP_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+struct smap_handle {
+    smap_config cfg;
+    GridParams gp;
+    double* map = nullptr;
+    bool own_map = false;
+    int64_t cells = 0;
+    // deterministic path: frame cell mask + touched list + double-buffered counter
+    uint32_t* mask = nullptr;
+    uint32_t* touched = nullptr;
+    int64_t touched_cap = 0;
+    uint32_t* counters = nullptr;  // [2]
+    int parity = 0;
+    // class tables
+    double* cm_dev = nullptr;
+    uint8_t colors[SMAP_MAX_CLASSES * 3];
+    bool classes_set = false;
+    double P[SMAP_MAX_CAMERAS][12];
+    bool cam_set[SMAP_MAX_CAMERAS] = {};
+    // project_pcd scratch
+    uint8_t* keep = nullptr;
+    int32_t* iu = nullptr;
+    int32_t* iv = nullptr;
+    uint32_t* blk_count = nullptr;
+    int64_t* blk_offset = nullptr;
+    int64_t* total_dev = nullptr;
+    int64_t scratch_cap = 0;
+    // host-buffer staging ring (smap_integrate_host)
+    static constexpr int kStages = 2;
+    void* stage_pts[kStages] = {};
+    uint8_t* stage_img[kStages] = {};
+    size_t stage_pts_cap[kStages] = {};
+    size_t stage_img_cap[kStages] = {};
+    cudaEvent_t stage_done[kStages] = {};
+    int stage_next = 0;
+    // bookkeeping
+    smap_stats stats = {};
+    cudaStream_t last_stream = nullptr;
+};
+
+namespace {
+
+int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp) {
+    if (!f) return fail(SMAP_ERR_INVALID, "frame is NULL");
+    if (f->camera < 0 || f->camera >= SMAP_MAX_CAMERAS || !h->cam_set[f->camera])
+        return fail(SMAP_ERR_STATE, "camera slot not set (smap_set_camera)");
+    if (f->n_points < 0) return fail(SMAP_ERR_INVALID, "n_points < 0");
+    if (f->layout != SMAP_PTS_F32X4 && f->layout != SMAP_PTS_F64_SOA) return fail(SMAP_ERR_INVALID, "unknown point layout");
+    if (f->layout == SMAP_PTS_F64_SOA && f->ld < f->n_points) return fail(SMAP_ERR_INVALID, "ld < n_points");
+    if (f->image_width <= 0 || f->image_height <= 0) return fail(SMAP_ERR_INVALID, "empty label image");
+    if (f->n_points > 0 && (!f->points_dev || !f->image_dev)) return fail(SMAP_ERR_INVALID, "NULL points / image");
+    if (f->layout == SMAP_PTS_F32X4 && (reinterpret_cast<uintptr_t>(f->points_dev) & 15u))
+        return fail(SMAP_ERR_INVALID, "float4 cloud must be 16-byte aligned");
+    memcpy(fp.T, f->world_to_velodyne, sizeof fp.T);
+    memcpy(fp.P, h->P[f->camera], sizeof fp.P);
+    fp.range_max = h->cfg.range_max;
+    fp.has_T = f->has_transform ? 1 : 0;
+    fp.img_w = f->image_width;
+    fp.img_h = f->image_height;
+    fp.pad = 0;
+    return SMAP_OK;
+}
+
+int ensure_touched(smap_handle* h, int64_t n) {
+    int64_t need = n < h->cells ? n : h->cells;
+    // a block appends at most its tile, so the list never exceeds min(n, cells) entries
+    if (need <= h->touched_cap) return SMAP_OK;
+    if (h->touched) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaFree(h->touched));
+        h->touched = nullptr;
+        h->touched_cap = 0;
+    }
+    int64_t cap = need + need / 4 + 1024;
+    if (cap > h->cells) cap = h->cells;
+    CK(cudaMalloc(&h->touched, sizeof(uint32_t) * (size_t)cap));
+    h->touched_cap = cap;
+    return SMAP_OK;
+}
+
+int ensure_scratch(smap_handle* h, int64_t n) {
+    if (n <= h->scratch_cap) return SMAP_OK;
+    CK(cudaDeviceSynchronize());
+    cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
+    h->keep = nullptr; h->iu = nullptr; h->iv = nullptr; h->blk_count = nullptr; h->blk_offset = nullptr;
+    h->scratch_cap = 0;
+    const int64_t cap = n + n / 4 + 1024;
+    const int64_t nb = ceil_div(cap, kCompactTile);
+    CK(cudaMalloc(&h->keep, (size_t)cap));
+    CK(cudaMalloc(&h->iu, sizeof(int32_t) * (size_t)cap));
+    CK(cudaMalloc(&h->iv, sizeof(int32_t) * (size_t)cap));
+    CK(cudaMalloc(&h->blk_count, sizeof(uint32_t) * (size_t)nb));
+    CK(cudaMalloc(&h->blk_offset, sizeof(int64_t) * (size_t)nb));
+    h->scratch_cap = cap;
+    return SMAP_OK;
+}
+
+// K3b launch: apply + clear the masks of the frame whose counter is counters[parity]; flips parity.
+int launch_apply(smap_handle* h, double* map, cudaStream_t st) {
+    const int c = h->cfg.num_classes;
+    const uint32_t* counter = h->counters + h->parity;
+    uint32_t* next_counter = h->counters + (h->parity ^ 1);
+    const size_t smem = sizeof(double) * c * c;
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    const int grid = sm * 4;
+    if (c <= 8)
+        k_apply<8><<<grid, kThreads, smem, st>>>(map, h->mask, h->touched, counter, next_counter, h->cm_dev, c, h->cfg.lane_index);
+    else if (c <= 16)
+        k_apply<16><<<grid, kThreads, smem, st>>>(map, h->mask, h->touched, counter, next_counter, h->cm_dev, c, h->cfg.lane_index);
+    else
+        k_apply<32><<<grid, kThreads, smem, st>>>(map, h->mask, h->touched, counter, next_counter, h->cm_dev, c, h->cfg.lane_index);
+    CK(cudaGetLastError());
+    h->parity ^= 1;
+    h->stats.kernel_launches += 1;
+    return SMAP_OK;
+}
+
+constexpr int kIntegratePts = 4;
+
+int launch_integrate(smap_handle* h, const smap_frame* f, const FrameParams& fp, cudaStream_t st) {
+    const int64_t n = f->n_points;
+    if (n > 0) {
+        const int64_t tile = (int64_t)kThreads * kIntegratePts;
+        const unsigned grid = (unsigned)ceil_div(n, tile);
+        uint32_t* counter = h->counters + h->parity;
+        if (f->layout == SMAP_PTS_F32X4)
+            k_integrate<SMAP_PTS_F32X4, kIntegratePts><<<grid, kThreads, 0, st>>>(
+                f->points_dev, n, f->ld, f->image_dev, fp, h->gp, h->mask, h->touched, counter);
+        else
+            k_integrate<SMAP_PTS_F64_SOA, kIntegratePts><<<grid, kThreads, 0, st>>>(
+                f->points_dev, n, f->ld, f->image_dev, fp, h->gp, h->mask, h->touched, counter);
+        CK(cudaGetLastError());
+        h->stats.kernel_launches += 1;
+    }
+    return SMAP_OK;
+}
+
+int render_common_checks(const void* map, int mh, int mw, int c) {
+    if (!map) return fail(SMAP_ERR_INVALID, "map is NULL");
+    if (mh <= 0 || mw <= 0) return fail(SMAP_ERR_INVALID, "empty grid");
+    if (c < 1 || c > 32) return fail(SMAP_ERR_INVALID, "num_classes must be in 1..32 for rendering");
+    return SMAP_OK;
+}
+
+template <bool FILTER>
+int launch_render(const double* map, int mh, int mw, int c, const uint8_t* colors_host, uint8_t* rgb,
+                  double* filtered, cudaStream_t st) {
+    RenderColors rc;
+    memset(&rc, 0, sizeof rc);
+    if (colors_host) memcpy(rc.rgb, colors_host, (size_t)c * 3);
+    dim3 grid((unsigned)ceil_div(mw, kTileX), (unsigned)ceil_div(mh, kTileY));
+    size_t smem = FILTER ? sizeof(double) * (size_t)(kTileY + 2) * (kTileX + 2) * c : 0;
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_render<FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_render<FILTER><<<grid, kTileX * kTileY, smem, st>>>(map, mh, mw, c, rc, rgb, filtered);
+    CK(cudaGetLastError());
+    return SMAP_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int smap_abi_version(void) { return SMAP_ABI_VERSION; }
+
+const char* smap_last_error(void) { return g_err.c_str(); }
+
+int smap_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SMAP_ERR_NO_DEVICE, "cudaGetDeviceCount failed");
+    }
+    return n;
+}
+
+int smap_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor) {
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    if (name && name_len > 0) {
+        strncpy(name, p.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return SMAP_OK;
+}
+
+int smap_create(const smap_config* cfg, smap_handle** out) {
+    if (!cfg || !out) return fail(SMAP_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (cfg->map_height <= 0 || cfg->map_width <= 0) return fail(SMAP_ERR_INVALID, "empty grid");
+    if (cfg->num_classes < 1 || cfg->num_classes > SMAP_MAX_CLASSES)
+        return fail(SMAP_ERR_INVALID, "num_classes must be in 1..31");
+    if ((int64_t)cfg->map_height * cfg->map_width >= (int64_t)1 << 31)
+        return fail(SMAP_ERR_INVALID, "grid has more than 2^31 cells");
+    if (cfg->lane_index >= cfg->num_classes) return fail(SMAP_ERR_INVALID, "lane_index out of range");
+    if (!(cfg->resolution == cfg->resolution) || cfg->resolution == 0.0)
+        return fail(SMAP_ERR_INVALID, "resolution must be non-zero");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return fail(SMAP_ERR_NO_DEVICE, "no such CUDA device");
+    }
+    DeviceGuard guard(cfg->device);
+    if (!guard.ok) return fail(SMAP_ERR_CUDA, "cudaSetDevice failed");
+    smap_handle* h = new (std::nothrow) smap_handle();
+    if (!h) return fail(SMAP_ERR_NOMEM, "out of host memory");
+    h->cfg = *cfg;
+    h->cells = (int64_t)cfg->map_height * cfg->map_width;
+    GridParams& g = h->gp;
+    memset(&g, 0, sizeof g);
+    g.off_x = cfg->origin_offset_x; g.off_y = cfg->origin_offset_y;
+    g.bx0 = cfg->boundary_x_min; g.by0 = cfg->boundary_y_min;
+    g.res = cfg->resolution;
+    g.mh = cfg->map_height; g.mw = cfg->map_width; g.c = cfg->num_classes;
+    g.lane = cfg->lane_index < 0 ? -1 : cfg->lane_index;
+    g.use_intensity = cfg->use_intensity ? 1 : 0;
+    const size_t map_bytes = sizeof(double) * (size_t)h->cells * cfg->num_classes;
+    cudaError_t e = cudaSuccess;
+    if (cfg->map_dev) {
+        h->map = static_cast<double*>(cfg->map_dev);
+    } else {
+        e = cudaMalloc(&h->map, map_bytes);
+        if (e == cudaSuccess) { h->own_map = true; e = cudaMemset(h->map, 0, map_bytes); }
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->cells);
+    if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->cells);
+    if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(uint32_t) * 2);
+    if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(uint32_t) * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&h->cm_dev, sizeof(double) * SMAP_MAX_CLASSES * SMAP_MAX_CLASSES);
+    if (e == cudaSuccess) e = cudaMalloc(&h->total_dev, sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        fail(e == cudaErrorMemoryAllocation ? SMAP_ERR_NOMEM : SMAP_ERR_CUDA, "smap_create: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        smap_destroy(h);
+        return e == cudaErrorMemoryAllocation ? SMAP_ERR_NOMEM : SMAP_ERR_CUDA;
+    }
+    *out = h;
+    return SMAP_OK;
+}
+
+int smap_destroy(smap_handle* h) {
+    if (!h) return SMAP_OK;
+    DeviceGuard guard(h->cfg.device);
+    cudaDeviceSynchronize();
+    if (h->own_map) cudaFree(h->map);
+    cudaFree(h->mask); cudaFree(h->touched); cudaFree(h->counters); cudaFree(h->cm_dev); cudaFree(h->total_dev);
+    cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
+    for (int i = 0; i < smap_handle::kStages; ++i) {
+        cudaFree(h->stage_pts[i]);
+        cudaFree(h->stage_img[i]);
+        if (h->stage_done[i]) cudaEventDestroy(h->stage_done[i]);
+    }
+    cudaGetLastError();
+    delete h;
+    return SMAP_OK;
+}
+
+int smap_set_camera(smap_handle* h, int camera, const double P_host[12]) {
+    if (!h || !P_host) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (camera < 0 || camera >= SMAP_MAX_CAMERAS) return fail(SMAP_ERR_INVALID, "camera slot out of range");
+    memcpy(h->P[camera], P_host, sizeof(double) * 12);
+    h->cam_set[camera] = true;
+    return SMAP_OK;
+}
+
+int smap_set_classes(smap_handle* h, const uint8_t* colors_host, const double* cm_host) {
+    if (!h || !colors_host || !cm_host) return fail(SMAP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->cfg.device);
+    const int c = h->cfg.num_classes;
+    memcpy(h->colors, colors_host, (size_t)c * 3);
+    for (int i = 0; i < c; ++i) {
+        h->gp.col_r[i] = colors_host[3 * i];
+        h->gp.col_g[i] = colors_host[3 * i + 1];
+    }
+    CK(cudaDeviceSynchronize());  // a previous frame may still be reading the table
+    CK(cudaMemcpy(h->cm_dev, cm_host, sizeof(double) * c * c, cudaMemcpyHostToDevice));
+    h->classes_set = true;
+    return SMAP_OK;
+}
+
+int smap_project(smap_handle* h, const smap_frame* frame, double* out_pcd, uint8_t* out_label, int32_t* out_uv,
+                 uint8_t* out_keep, int64_t out_ld, int64_t* m_host, void* stream) {
+    if (!h || !m_host) return fail(SMAP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->cfg.device);
+    FrameParams fp;
+    int rc = fill_frame_params(h, frame, fp);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t n = frame->n_points;
+    *m_host = 0;
+    if (n == 0) return SMAP_OK;
+    if (!out_pcd || !out_label) return fail(SMAP_ERR_INVALID, "NULL output");
+    if (out_ld < n) return fail(SMAP_ERR_INVALID, "out_ld < n_points");
+    rc = ensure_scratch(h, n);
+    if (rc) return rc;
+    const int64_t nb = ceil_div(n, kCompactTile);
+    if (frame->layout == SMAP_PTS_F32X4)
+        k_project_flags<SMAP_PTS_F32X4><<<(unsigned)nb, kThreads, 0, st>>>(frame->points_dev, n, frame->ld, fp, h->keep, h->iu, h->iv, h->blk_count);
+    else
+        k_project_flags<SMAP_PTS_F64_SOA><<<(unsigned)nb, kThreads, 0, st>>>(frame->points_dev, n, frame->ld, fp, h->keep, h->iu, h->iv, h->blk_count);
+    CK(cudaGetLastError());
+    k_scan_blocks<<<1, 1024, 0, st>>>(h->blk_count, h->blk_offset, nb, h->total_dev);
+    CK(cudaGetLastError());
+    if (frame->layout == SMAP_PTS_F32X4)
+        k_compact<SMAP_PTS_F32X4><<<(unsigned)nb, kThreads, 0, st>>>(frame->points_dev, n, frame->ld, frame->image_dev, fp.img_w, h->keep, h->iu, h->iv, h->blk_offset, out_pcd, out_label, out_uv, out_ld);
+    else
+        k_compact<SMAP_PTS_F64_SOA><<<(unsigned)nb, kThreads, 0, st>>>(frame->points_dev, n, frame->ld, frame->image_dev, fp.img_w, h->keep, h->iu, h->iv, h->blk_offset, out_pcd, out_label, out_uv, out_ld);
+    CK(cudaGetLastError());
+    if (out_keep) CK(cudaMemcpyAsync(out_keep, h->keep, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(m_host, h->total_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->stats.kernel_launches += 3;
+    h->last_stream = st;
+    return SMAP_OK;
+}
+
+int smap_update(smap_handle* h, double* map_dev, const double* pcd, int64_t ld, const uint8_t* label, int64_t ldl,
+                int64_t m, void* stream) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    if (!h->classes_set) return fail(SMAP_ERR_STATE, "classes not set (smap_set_classes)");
+    if (m < 0 || ld < m || ldl < m) return fail(SMAP_ERR_INVALID, "bad point count / strides");
+    if (m > 0 && (!pcd || !label)) return fail(SMAP_ERR_INVALID, "NULL pcd / label");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (m == 0) return SMAP_OK;
+    int rc = ensure_touched(h, m);
+    if (rc) return rc;
+    constexpr int PTS = 2;
+    const unsigned grid = (unsigned)ceil_div(m, (int64_t)kThreads * PTS);
+    k_update_scatter<PTS><<<grid, kThreads, 0, st>>>(pcd, ld, label, ldl, m, h->gp, h->mask, h->touched, h->counters + h->parity);
+    CK(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    h->last_stream = st;
+    return launch_apply(h, map_dev ? map_dev : h->map, st);
+}
+
+int smap_integrate(smap_handle* h, const smap_frame* frame, void* stream) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    if (!h->classes_set) return fail(SMAP_ERR_STATE, "classes not set (smap_set_classes)");
+    DeviceGuard guard(h->cfg.device);
+    FrameParams fp;
+    int rc = fill_frame_params(h, frame, fp);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    h->stats.frames += 1;
+    h->stats.points += frame->n_points;
+    h->last_stream = st;
+    if (frame->n_points == 0) return SMAP_OK;
+    rc = ensure_touched(h, frame->n_points);
+    if (rc) return rc;
+    rc = launch_integrate(h, frame, fp, st);
+    if (rc) return rc;
+    return launch_apply(h, h->map, st);
+}
+
+int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames, void* stream) {
+    if (!h || (n_frames > 0 && !frames)) return fail(SMAP_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < n_frames; ++i) {
+        int rc = smap_integrate(h, frames + i, stream);
+        if (rc) return rc;
+    }
+    return SMAP_OK;
+}
+
+int smap_integrate_host(smap_handle* h, const smap_frame* f, void* stream) {
+    if (!h || !f) return fail(SMAP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (f->n_points < 0 || f->image_width <= 0 || f->image_height <= 0) return fail(SMAP_ERR_INVALID, "bad frame sizes");
+    const size_t pts_bytes = f->layout == SMAP_PTS_F32X4 ? (size_t)f->n_points * 16 : (size_t)f->ld * 4 * sizeof(double);
+    const size_t img_bytes = (size_t)f->image_width * f->image_height * 3;
+    const int s = h->stage_next;
+    h->stage_next = (s + 1) % smap_handle::kStages;
+    if (!h->stage_done[s]) CK(cudaEventCreateWithFlags(&h->stage_done[s], cudaEventDisableTiming));
+    // the kernels of the frame that last used this stage must be finished before it is overwritten
+    CK(cudaStreamWaitEvent(st, h->stage_done[s], 0));
+    if (pts_bytes > h->stage_pts_cap[s]) {
+        CK(cudaEventSynchronize(h->stage_done[s]));
+        cudaFree(h->stage_pts[s]);
+        h->stage_pts[s] = nullptr; h->stage_pts_cap[s] = 0;
+        CK(cudaMalloc(&h->stage_pts[s], pts_bytes + pts_bytes / 4));
+        h->stage_pts_cap[s] = pts_bytes + pts_bytes / 4;
+    }
+    if (img_bytes > h->stage_img_cap[s]) {
+        CK(cudaEventSynchronize(h->stage_done[s]));
+        cudaFree(h->stage_img[s]);
+        h->stage_img[s] = nullptr; h->stage_img_cap[s] = 0;
+        CK(cudaMalloc(&h->stage_img[s], img_bytes));
+        h->stage_img_cap[s] = img_bytes;
+    }
+    if (pts_bytes) CK(cudaMemcpyAsync(h->stage_pts[s], f->points_dev, pts_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->stage_img[s], f->image_dev, img_bytes, cudaMemcpyHostToDevice, st));
+    smap_frame dev = *f;
+    dev.points_dev = h->stage_pts[s];
+    dev.image_dev = h->stage_img[s];
+    int rc = smap_integrate(h, &dev, stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->stage_done[s], st));
+    return SMAP_OK;
+}
+
+int smap_apply_filter(const double* src, int mh, int mw, int c, double* dst, int device, void* stream) {
+    int rc = render_common_checks(src, mh, mw, c);
+    if (rc) return rc;
+    if (!dst || dst == src) return fail(SMAP_ERR_INVALID, "dst must be a distinct buffer");
+    DeviceGuard guard(device);
+    return launch_render<true>(src, mh, mw, c, nullptr, nullptr, dst, static_cast<cudaStream_t>(stream));
+}
+
+int smap_render(const double* map, int mh, int mw, int c, const uint8_t* colors_host, uint8_t* rgb, int device,
+                void* stream) {
+    int rc = render_common_checks(map, mh, mw, c);
+    if (rc) return rc;
+    if (!rgb || !colors_host) return fail(SMAP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(device);
+    return launch_render<false>(map, mh, mw, c, colors_host, rgb, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int smap_filter_render(const double* map, int mh, int mw, int c, const uint8_t* colors_host, uint8_t* rgb,
+                       double* filtered, int device, void* stream) {
+    int rc = render_common_checks(map, mh, mw, c);
+    if (rc) return rc;
+    if (!rgb || !colors_host) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (filtered == map) return fail(SMAP_ERR_INVALID, "filtered must be a distinct buffer");
+    DeviceGuard guard(device);
+    return launch_render<true>(map, mh, mw, c, colors_host, rgb, filtered, static_cast<cudaStream_t>(stream));
+}
+
+int smap_render_thresholds(const double* map, int mh, int mw, int c, const uint8_t* colors_host,
+                           const int32_t* priority_host, const double* thresholds_host, uint8_t* rgb, int device,
+                           void* stream) {
+    int rc = render_common_checks(map, mh, mw, c);
+    if (rc) return rc;
+    if (!rgb || !colors_host || !priority_host || !thresholds_host) return fail(SMAP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(device);
+    RenderColors rcol;
+    ThresholdParams tp;
+    memset(&rcol, 0, sizeof rcol);
+    memset(&tp, 0, sizeof tp);
+    memcpy(rcol.rgb, colors_host, (size_t)c * 3);
+    for (int i = 0; i < c; ++i) {
+        if (priority_host[i] < 0 || priority_host[i] >= c) return fail(SMAP_ERR_INVALID, "priority entry out of range");
+        tp.priority[i] = priority_host[i];
+        tp.thresholds[i] = thresholds_host[i];
+    }
+    const int64_t cells = (int64_t)mh * mw;
+    k_render_thresholds<<<(unsigned)ceil_div(cells, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        map, cells, c, rcol, tp, rgb);
+    CK(cudaGetLastError());
+    return SMAP_OK;
+}
+
+int smap_map_ptr(smap_handle* h, double** map_dev, int64_t* n_elements) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    if (map_dev) *map_dev = h->map;
+    if (n_elements) *n_elements = h->cells * h->cfg.num_classes;
+    return SMAP_OK;
+}
+
+int smap_clear(smap_handle* h, void* stream) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    DeviceGuard guard(h->cfg.device);
+    CK(cudaMemsetAsync(h->map, 0, sizeof(double) * (size_t)h->cells * h->cfg.num_classes, static_cast<cudaStream_t>(stream)));
+    h->stats.frames = 0;
+    h->stats.points = 0;
+    h->last_stream = static_cast<cudaStream_t>(stream);
+    return SMAP_OK;
+}
+
+int smap_download(smap_handle* h, double* map_host) {
+    if (!h || !map_host) return fail(SMAP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->cfg.device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(map_host, h->map, sizeof(double) * (size_t)h->cells * h->cfg.num_classes, cudaMemcpyDeviceToHost));
+    return SMAP_OK;
+}
+
+int smap_upload(smap_handle* h, const double* map_host) {
+    if (!h || !map_host) return fail(SMAP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->cfg.device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h->map, map_host, sizeof(double) * (size_t)h->cells * h->cfg.num_classes, cudaMemcpyHostToDevice));
+    return SMAP_OK;
+}
+
+int smap_get_stats(smap_handle* h, smap_stats* out) {
+    if (!h || !out) return fail(SMAP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->cfg.device);
+    CK(cudaStreamSynchronize(h->last_stream));
+    // after launch_apply flipped the parity, the finished frame's count sits in counters[parity ^ 1]
+    uint32_t k = 0;
+    CK(cudaMemcpy(&k, h->counters + (h->parity ^ 1), sizeof k, cudaMemcpyDeviceToHost));
+    h->stats.touched_cells = k;
+    *out = h->stats;
+    return SMAP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+"""Handle on the device-resident BEV grid: thin object layer over the C ABI (``include/smap.h``).
+
+``DeviceMapper`` owns one ``smap_handle`` on one GPU.  The grid itself is a ``torch`` CUDA tensor
+(torch is the allocator and the stream provider; ``torch.distributed`` reduces this tensor across
+ranks) whose pointer is lent to the handle.  All arithmetic happens in the CUDA kernels.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from ._native import SmapConfig, SmapFrame, SmapStats, SMAP_PTS_F32X4, SMAP_PTS_F64_SOA
+
+PCD_ORIGIN_OFFSET = (1369.0496826171875, 562.84814453125)  # reference src/mapping_replay.py:261
+
+_IDENTITY16 = (ctypes.c_double * 16)(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1)
+
+
+class DeviceMapper(object):
+    def __init__(self, map_height, map_width, label_colors, update_matrix, boundary, resolution, range_max,
+                 use_intensity, lane_index, cameras, device=None, origin_offset=PCD_ORIGIN_OFFSET):
+        torch = _native.require_cuda()
+        self._lib = _native.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device if isinstance(device, int) else torch.device(device).index or 0))
+        colors = np.ascontiguousarray(np.asarray(label_colors).astype(np.uint8))
+        cm = np.ascontiguousarray(update_matrix, dtype=np.float64)
+        c = colors.shape[0]
+        if colors.shape != (c, 3) or cm.shape != (c, c):
+            raise ValueError("label_colors must be (C,3) and the update matrix (C,C)")
+        if not 1 <= c <= _native.SMAP_MAX_CLASSES:
+            raise ValueError("between 1 and %d classes are supported" % _native.SMAP_MAX_CLASSES)
+        self.map_height, self.map_width, self.num_classes = int(map_height), int(map_width), c
+        with torch.cuda.device(self.device):
+            self.map = torch.zeros((self.map_height, self.map_width, c), dtype=torch.float64, device=self.device)
+        cfg = SmapConfig()
+        cfg.map_height, cfg.map_width, cfg.num_classes = self.map_height, self.map_width, c
+        cfg.use_intensity = int(bool(use_intensity))
+        cfg.lane_index = int(lane_index)
+        cfg.device = self.device.index
+        cfg.boundary_x_min, cfg.boundary_y_min = float(boundary[0][0]), float(boundary[1][0])
+        cfg.resolution = float(resolution)
+        cfg.origin_offset_x, cfg.origin_offset_y = float(origin_offset[0]), float(origin_offset[1])
+        cfg.range_max = float(range_max)
+        cfg.map_dev = self.map.data_ptr()
+        handle = ctypes.c_void_p()
+        _native.check(self._lib.smap_create(ctypes.byref(cfg), ctypes.byref(handle)))
+        self._h = handle
+        self._colors, self._cm = colors, cm
+        _native.check(self._lib.smap_set_classes(self._h, colors.ctypes.data_as(ctypes.c_void_p),
+                                                 cm.ctypes.data_as(ctypes.c_void_p)))
+        self._camera_slots = {}
+        for slot, cam in enumerate(cameras):
+            P = np.ascontiguousarray(cam.P if hasattr(cam, "P") else cam, dtype=np.float64)
+            if P.shape != (3, 4):
+                raise ValueError("camera projection must be 3x4")
+            _native.check(self._lib.smap_set_camera(self._h, slot, P.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+            self._camera_slots[id(cam)] = slot
+        self._keepalive = []
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.smap_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return _native.current_stream_ptr(self.device)
+
+    def camera_slot(self, camera):
+        if isinstance(camera, int):
+            return camera
+        try:
+            return self._camera_slots[id(camera)]
+        except KeyError:
+            raise ValueError("unknown camera calibration object; pass it in `cameras` at construction")
+
+    def make_frame(self, points, image, world_to_velodyne, camera=0, host=False):
+        """Describe one frame for the C ABI.  ``points``: torch tensor (N,4) float32 [float4 layout] or
+        (4,N) float64 [the reference's pcd layout]; ``image``: (H,W,3) uint8; ``world_to_velodyne``: 4x4
+        float64 numpy or None for a cloud already in the velodyne frame.  host=True: tensors live in
+        (pinned) host memory and are meant for ``integrate_host``."""
+        torch = _native.require_cuda()
+        f = SmapFrame()
+        if points.dtype == torch.float32:
+            if points.dim() != 2 or points.shape[1] != 4 or not points.is_contiguous():
+                raise ValueError("float32 clouds must be contiguous (N, 4)")
+            f.layout, f.n_points, f.ld = SMAP_PTS_F32X4, points.shape[0], 0
+        elif points.dtype == torch.float64:
+            if points.dim() != 2 or points.shape[0] < 4 or points.stride(1) != 1:
+                raise ValueError("float64 clouds must be (4, N) with unit column stride")
+            f.layout, f.n_points, f.ld = SMAP_PTS_F64_SOA, points.shape[1], points.stride(0)
+            if points.shape[1] == 0:
+                f.ld = 0
+        else:
+            raise TypeError("cloud must be float32 (N,4) or float64 (4,N)")
+        if image.dtype != torch.uint8 or image.dim() != 3 or image.shape[2] != 3 or not image.is_contiguous():
+            raise ValueError("label image must be contiguous (H, W, 3) uint8")
+        if not host and (not points.is_cuda or not image.is_cuda):
+            raise ValueError("device frames need CUDA tensors")
+        f.points_dev = points.data_ptr()
+        f.image_dev = image.data_ptr()
+        f.image_height, f.image_width = image.shape[0], image.shape[1]
+        f.camera = self.camera_slot(camera)
+        if world_to_velodyne is None:
+            f.has_transform = 0
+            ctypes.memmove(f.world_to_velodyne, _IDENTITY16, 128)
+        else:
+            T = np.ascontiguousarray(world_to_velodyne, dtype=np.float64)
+            if T.shape != (4, 4):
+                raise ValueError("world_to_velodyne must be 4x4")
+            f.has_transform = 1
+            ctypes.memmove(f.world_to_velodyne, T.ctypes.data, 128)
+        return f
+
+    # ------------------------------------------------------------------ the path
+    def integrate(self, frame):
+        """project_pcd + update_map of one frame, fused, deterministic (bit-exact)."""
+        _native.check(self._lib.smap_integrate(self._h, ctypes.byref(frame), self._stream()))
+
+    def integrate_host(self, frame):
+        _native.check(self._lib.smap_integrate_host(self._h, ctypes.byref(frame), self._stream()))
+
+    def integrate_batch(self, frames):
+        arr = (SmapFrame * len(frames))(*frames)
+        _native.check(self._lib.smap_integrate_batch(self._h, arr, len(frames), self._stream()))
+
+    def project(self, frame, want_uv=False, want_keep=False):
+        """Parity API of project_pcd: returns (masked_pcd (4,M) f64, label (3,M) u8[, uv (2,M) i32][, keep (N,) bool])."""
+        torch = _native.require_cuda()
+        n = int(frame.n_points)
+        with torch.cuda.device(self.device):
+            out_pcd = torch.empty((4, n), dtype=torch.float64, device=self.device)
+            out_label = torch.empty((3, n), dtype=torch.uint8, device=self.device)
+            out_uv = torch.empty((2, n), dtype=torch.int32, device=self.device) if want_uv else None
+            out_keep = torch.empty((n,), dtype=torch.uint8, device=self.device) if want_keep else None
+            m = ctypes.c_int64(0)
+            _native.check(self._lib.smap_project(
+                self._h, ctypes.byref(frame), out_pcd.data_ptr(), out_label.data_ptr(),
+                out_uv.data_ptr() if want_uv else None, out_keep.data_ptr() if want_keep else None,
+                n, ctypes.byref(m), self._stream()))
+        m = m.value
+        res = [out_pcd[:, :m].contiguous(), out_label[:, :m].contiguous()]
+        if want_uv:
+            res.append(out_uv[:, :m].contiguous())
+        if want_keep:
+            res.append(out_keep.bool())
+        return tuple(res)
+
+    def update(self, pcd, label, map_tensor=None):
+        """Parity API of update_map on CUDA tensors: pcd (4,M) float64, label (3,M) uint8."""
+        torch = _native.require_cuda()
+        if pcd.dtype != torch.float64 or label.dtype != torch.uint8 or not pcd.is_cuda or not label.is_cuda:
+            raise TypeError("update needs CUDA float64 pcd and uint8 label")
+        if pcd.shape[0] < 4 or label.shape[0] != 3 or pcd.shape[1] != label.shape[1]:
+            raise ValueError("pcd must be (4,M) and label (3,M)")
+        m = pcd.shape[1]
+        if m and (pcd.stride(1) != 1 or label.stride(1) != 1):
+            pcd, label = pcd.contiguous(), label.contiguous()
+        target = self.map if map_tensor is None else map_tensor
+        if target.shape != self.map.shape or target.dtype != torch.float64 or not target.is_contiguous():
+            raise ValueError("map must be a contiguous float64 tensor of shape %s" % (tuple(self.map.shape),))
+        _native.check(self._lib.smap_update(self._h, target.data_ptr(), pcd.data_ptr(), pcd.stride(0) if m else 0,
+                                            label.data_ptr(), label.stride(0) if m else 0, m, self._stream()))
+        return target
+
+    def clear(self):
+        _native.check(self._lib.smap_clear(self._h, self._stream()))
+
+    def stats(self):
+        s = SmapStats()
+        _native.check(self._lib.smap_get_stats(self._h, ctypes.byref(s)))
+        return {"frames": s.frames, "points": s.points, "touched_cells": s.touched_cells,
+                "kernel_launches": s.kernel_launches}
