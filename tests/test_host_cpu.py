@@ -51,7 +51,7 @@ def test_bad_arguments_are_reported_not_thrown():
     cfg.map_height, cfg.map_width, cfg.num_classes, cfg.resolution = 0, 10, 5, 0.1
     assert lib.smap_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"empty grid" in lib.smap_last_error()
-    cfg.map_height, cfg.num_classes = 10, 40
+    cfg.map_height, cfg.num_classes = 10, 31
     assert lib.smap_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     with pytest.raises(_native.SmapError):
         _native.check(lib.smap_render(None, 4, 4, 3, None, None, 0, None))
@@ -190,8 +190,12 @@ def test_frame_sharding_world_size_2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER % {"root": ROOT})
     env = dict(os.environ, OMP_NUM_THREADS="1")
+    import socket
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout

@@ -50,8 +50,14 @@ struct smap_handle {
     double* map = nullptr;
     bool own_map = false;
     int64_t cells = 0;
-    // deterministic path: frame cell mask + touched list + double-buffered counter
+    // epoch-tagged cell masks: n_slots slots of `cells` words (slot 0 serves the single-frame paths)
     uint32_t* mask = nullptr;
+    int n_slots = 0;
+    uint32_t tag = 0;      // last frame tag handed out (0 = "never written")
+    uint32_t tag_max = 0;  // largest tag that fits above tag_shift
+    bool identity_cm = false;   // update matrix is exactly np.eye(C): the count update
+    bool deterministic = false; // force the touched-list + k_apply path even for the count update
+    // deterministic path: touched list + double-buffered counter
     uint32_t* touched = nullptr;
     int64_t touched_cap = 0;
     uint32_t* counters = nullptr;  // [2]
@@ -99,6 +105,17 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
     memcpy(fp.T, f->world_to_velodyne, sizeof fp.T);
     memcpy(fp.P, h->P[f->camera], sizeof fp.P);
     fp.range_max = h->cfg.range_max;
+    {   // float32 pre-cull matrix: row 0 = velodyne-x row of T, rows 1..3 = P * T (double product, rounded once)
+        double Tm[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        if (f->has_transform) memcpy(Tm, f->world_to_velodyne, sizeof Tm);
+        for (int j = 0; j < 4; ++j) fp.Mf[j] = (float)Tm[j];
+        for (int r = 0; r < 3; ++r)
+            for (int j = 0; j < 4; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < 4; ++k) acc += fp.P[4 * r + k] * Tm[4 * k + j];
+                fp.Mf[4 * (r + 1) + j] = (float)acc;
+            }
+    }
     fp.has_T = f->has_transform ? 1 : 0;
     fp.img_w = f->image_width;
     fp.img_h = f->image_height;
@@ -140,7 +157,35 @@ int ensure_scratch(smap_handle* h, int64_t n) {
     return SMAP_OK;
 }
 
-// K3b launch: apply + clear the masks of the frame whose counter is counters[parity]; flips parity.
+// Make room for `want` mask slots (slot 0 always exists).  New memory is zero = "never written".
+int ensure_slots(smap_handle* h, int want) {
+    if (want <= h->n_slots) return SMAP_OK;
+    uint32_t* fresh = nullptr;
+    const size_t slot_bytes = sizeof(uint32_t) * (size_t)h->cells;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMalloc(&fresh, slot_bytes * want));
+    CK(cudaMemset(fresh, 0, slot_bytes * want));
+    if (h->mask) {
+        CK(cudaMemcpy(fresh, h->mask, slot_bytes * h->n_slots, cudaMemcpyDeviceToDevice));
+        CK(cudaFree(h->mask));
+    }
+    h->mask = fresh;
+    h->n_slots = want;
+    return SMAP_OK;
+}
+
+// Next frame tag; when the tag field is exhausted every slot is wiped and the count restarts.
+int next_tag(smap_handle* h, cudaStream_t st, uint32_t* tagword) {
+    if (h->tag >= h->tag_max) {
+        CK(cudaMemsetAsync(h->mask, 0, sizeof(uint32_t) * (size_t)h->cells * h->n_slots, st));
+        h->tag = 0;
+    }
+    h->tag += 1;
+    *tagword = h->tag << h->gp.tag_shift;
+    return SMAP_OK;
+}
+
+// K3b launch: apply the masks of the frame whose counter is counters[parity]; flips parity.
 int launch_apply(smap_handle* h, double* map, cudaStream_t st) {
     const int c = h->cfg.num_classes;
     const uint32_t* counter = h->counters + h->parity;
@@ -148,36 +193,52 @@ int launch_apply(smap_handle* h, double* map, cudaStream_t st) {
     const size_t smem = sizeof(double) * c * c;
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->cfg.device);
-    const int grid = sm * 4;
-    if (c <= 8)
-        k_apply<8><<<grid, kThreads, smem, st>>>(map, h->mask, h->touched, counter, next_counter, h->cm_dev, c, h->cfg.lane_index);
-    else if (c <= 16)
-        k_apply<16><<<grid, kThreads, smem, st>>>(map, h->mask, h->touched, counter, next_counter, h->cm_dev, c, h->cfg.lane_index);
-    else
-        k_apply<32><<<grid, kThreads, smem, st>>>(map, h->mask, h->touched, counter, next_counter, h->cm_dev, c, h->cfg.lane_index);
+    k_apply<<<sm * 8, kThreads, smem, st>>>(map, h->mask, h->touched, counter, next_counter, h->cm_dev, c, h->cfg.lane_index);
     CK(cudaGetLastError());
     h->parity ^= 1;
     h->stats.kernel_launches += 1;
     return SMAP_OK;
 }
 
-constexpr int kIntegratePts = 4;
-
-int launch_integrate(smap_handle* h, const smap_frame* f, const FrameParams& fp, cudaStream_t st) {
-    const int64_t n = f->n_points;
-    if (n > 0) {
-        const int64_t tile = (int64_t)kThreads * kIntegratePts;
-        const unsigned grid = (unsigned)ceil_div(n, tile);
-        uint32_t* counter = h->counters + h->parity;
-        if (f->layout == SMAP_PTS_F32X4)
-            k_integrate<SMAP_PTS_F32X4, kIntegratePts><<<grid, kThreads, 0, st>>>(
-                f->points_dev, n, f->ld, f->image_dev, fp, h->gp, h->mask, h->touched, counter);
-        else
-            k_integrate<SMAP_PTS_F64_SOA, kIntegratePts><<<grid, kThreads, 0, st>>>(
-                f->points_dev, n, f->ld, f->image_dev, fp, h->gp, h->mask, h->touched, counter);
-        CK(cudaGetLastError());
-        h->stats.kernel_launches += 1;
+// One launch of k_fuse over up to kMaxBatch frames (already validated; fps[i] filled).
+// mode 0: deterministic scatter of ONE frame into slot 0 (caller launches k_apply afterwards)
+// mode 1: count update with atomics, frame i uses mask slot i
+int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, int mode, cudaStream_t st) {
+    BatchParams bp;
+    memset(&bp, 0, sizeof bp);
+    uint32_t tagword = 0;
+    int rc = next_tag(h, st, &tagword);
+    if (rc) return rc;
+    uint32_t blocks = 0;
+    int layout = frames[0].layout;
+    int used = 0;
+    for (int i = 0; i < n_frames; ++i) {
+        if (frames[i].n_points == 0) continue;
+        if (frames[i].layout != layout) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
+        BatchFrame& b = bp.f[used];
+        b.fp = fps[i];
+        b.pts = frames[i].points_dev;
+        b.image = frames[i].image_dev;
+        b.mask = h->mask + (size_t)(mode == 1 ? used : 0) * h->cells;
+        b.n = frames[i].n_points;
+        b.ld = frames[i].ld;
+        b.tagword = tagword;
+        b.block_begin = blocks;
+        blocks += (uint32_t)ceil_div(frames[i].n_points, kFuseTile);
+        ++used;
     }
+    if (used == 0) return SMAP_OK;
+    bp.n_frames = used;
+    uint32_t* counter = h->counters + h->parity;
+    if (layout == SMAP_PTS_F32X4) {
+        if (mode == 0) k_fuse<SMAP_PTS_F32X4, 0><<<blocks, kThreads, 0, st>>>(bp, h->gp, h->map, h->touched, counter);
+        else k_fuse<SMAP_PTS_F32X4, 1><<<blocks, kThreads, 0, st>>>(bp, h->gp, h->map, h->touched, counter);
+    } else {
+        if (mode == 0) k_fuse<SMAP_PTS_F64_SOA, 0><<<blocks, kThreads, 0, st>>>(bp, h->gp, h->map, h->touched, counter);
+        else k_fuse<SMAP_PTS_F64_SOA, 1><<<blocks, kThreads, 0, st>>>(bp, h->gp, h->map, h->touched, counter);
+    }
+    CK(cudaGetLastError());
+    h->stats.kernel_launches += 1;
     return SMAP_OK;
 }
 
@@ -239,7 +300,7 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     *out = nullptr;
     if (cfg->map_height <= 0 || cfg->map_width <= 0) return fail(SMAP_ERR_INVALID, "empty grid");
     if (cfg->num_classes < 1 || cfg->num_classes > SMAP_MAX_CLASSES)
-        return fail(SMAP_ERR_INVALID, "num_classes must be in 1..31");
+        return fail(SMAP_ERR_INVALID, "num_classes must be in 1..30");
     if ((int64_t)cfg->map_height * cfg->map_width >= (int64_t)1 << 31)
         return fail(SMAP_ERR_INVALID, "grid has more than 2^31 cells");
     if (cfg->lane_index >= cfg->num_classes) return fail(SMAP_ERR_INVALID, "lane_index out of range");
@@ -264,6 +325,8 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     g.mh = cfg->map_height; g.mw = cfg->map_width; g.c = cfg->num_classes;
     g.lane = cfg->lane_index < 0 ? -1 : cfg->lane_index;
     g.use_intensity = cfg->use_intensity ? 1 : 0;
+    g.tag_shift = cfg->num_classes + 1;
+    h->tag_max = (g.tag_shift >= 32) ? 0u : ((1u << (32 - g.tag_shift)) - 1u);
     const size_t map_bytes = sizeof(double) * (size_t)h->cells * cfg->num_classes;
     cudaError_t e = cudaSuccess;
     if (cfg->map_dev) {
@@ -274,6 +337,7 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     }
     if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->cells);
     if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->cells);
+    if (e == cudaSuccess) h->n_slots = 1;
     if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(uint32_t) * 2);
     if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(uint32_t) * 2);
     if (e == cudaSuccess) e = cudaMalloc(&h->cm_dev, sizeof(double) * SMAP_MAX_CLASSES * SMAP_MAX_CLASSES);
@@ -325,6 +389,10 @@ int smap_set_classes(smap_handle* h, const uint8_t* colors_host, const double* c
     }
     CK(cudaDeviceSynchronize());  // a previous frame may still be reading the table
     CK(cudaMemcpy(h->cm_dev, cm_host, sizeof(double) * c * c, cudaMemcpyHostToDevice));
+    h->identity_cm = true;
+    for (int i = 0; i < c; ++i)
+        for (int j = 0; j < c; ++j)
+            if (cm_host[i * c + j] != (i == j ? 1.0 : 0.0)) h->identity_cm = false;
     h->classes_set = true;
     return SMAP_OK;
 }
@@ -378,39 +446,62 @@ int smap_update(smap_handle* h, double* map_dev, const double* pcd, int64_t ld, 
     if (rc) return rc;
     constexpr int PTS = 2;
     const unsigned grid = (unsigned)ceil_div(m, (int64_t)kThreads * PTS);
-    k_update_scatter<PTS><<<grid, kThreads, 0, st>>>(pcd, ld, label, ldl, m, h->gp, h->mask, h->touched, h->counters + h->parity);
+    uint32_t tagword = 0;
+    rc = next_tag(h, st, &tagword);
+    if (rc) return rc;
+    k_update_scatter<PTS><<<grid, kThreads, 0, st>>>(pcd, ld, label, ldl, m, h->gp, h->mask, tagword, h->touched, h->counters + h->parity);
     CK(cudaGetLastError());
     h->stats.kernel_launches += 1;
     h->last_stream = st;
     return launch_apply(h, map_dev ? map_dev : h->map, st);
 }
 
-int smap_integrate(smap_handle* h, const smap_frame* frame, void* stream) {
+int smap_set_deterministic(smap_handle* h, int on) {
     if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
-    if (!h->classes_set) return fail(SMAP_ERR_STATE, "classes not set (smap_set_classes)");
-    DeviceGuard guard(h->cfg.device);
-    FrameParams fp;
-    int rc = fill_frame_params(h, frame, fp);
-    if (rc) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    h->stats.frames += 1;
-    h->stats.points += frame->n_points;
-    h->last_stream = st;
-    if (frame->n_points == 0) return SMAP_OK;
-    rc = ensure_touched(h, frame->n_points);
-    if (rc) return rc;
-    rc = launch_integrate(h, frame, fp, st);
-    if (rc) return rc;
-    return launch_apply(h, h->map, st);
+    h->deterministic = on != 0;
+    return SMAP_OK;
 }
 
 int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames, void* stream) {
     if (!h || (n_frames > 0 && !frames)) return fail(SMAP_ERR_INVALID, "NULL argument");
-    for (int i = 0; i < n_frames; ++i) {
-        int rc = smap_integrate(h, frames + i, stream);
+    if (n_frames < 0) return fail(SMAP_ERR_INVALID, "n_frames < 0");
+    if (!h->classes_set) return fail(SMAP_ERR_STATE, "classes not set (smap_set_classes)");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    h->last_stream = st;
+    const bool atomic_counts = h->identity_cm && !h->deterministic;
+    FrameParams fps[kMaxBatch];
+    for (int begin = 0; begin < n_frames;) {
+        // the count update takes up to kMaxBatch frames per launch; the ordered (bit-exact) update one frame
+        const int chunk = atomic_counts ? ((n_frames - begin < kMaxBatch) ? n_frames - begin : kMaxBatch) : 1;
+        int64_t max_pts = 0;
+        for (int i = 0; i < chunk; ++i) {
+            int rc = fill_frame_params(h, frames + begin + i, fps[i]);
+            if (rc) return rc;
+            h->stats.frames += 1;
+            h->stats.points += frames[begin + i].n_points;
+            if (frames[begin + i].n_points > max_pts) max_pts = frames[begin + i].n_points;
+        }
+        int rc;
+        if (atomic_counts) {
+            rc = ensure_slots(h, chunk);
+            if (!rc) rc = launch_fuse(h, frames + begin, fps, chunk, 1, st);
+        } else if (max_pts > 0) {
+            rc = ensure_touched(h, max_pts);
+            if (!rc) rc = launch_fuse(h, frames + begin, fps, 1, 0, st);
+            if (!rc) rc = launch_apply(h, h->map, st);
+        } else {
+            rc = SMAP_OK;
+        }
         if (rc) return rc;
+        begin += chunk;
     }
     return SMAP_OK;
+}
+
+int smap_integrate(smap_handle* h, const smap_frame* frame, void* stream) {
+    if (!h || !frame) return fail(SMAP_ERR_INVALID, "NULL argument");
+    return smap_integrate_batch(h, frame, 1, stream);
 }
 
 int smap_integrate_host(smap_handle* h, const smap_frame* f, void* stream) {

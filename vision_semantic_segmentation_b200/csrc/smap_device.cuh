@@ -12,13 +12,18 @@
 
 namespace smap {
 
-constexpr uint32_t kBoostBit = 0x80000000u;  // "lane point with strong/weak LiDAR return" flag in a cell mask
+// Cell-mask word (32 bit):  [ tag : 31-C bits | boost : 1 bit (bit C) | class bits : C bits ].
+// The tag is the serial number of the frame that last wrote the word, so a mask never has to be cleared:
+// a word whose tag is not the current frame's reads as empty.
+constexpr int kMaxBatch = 16;  // frames per launch of the batched kernel (one mask slot each)
 
 // Per-frame projection constants (passed by value as a kernel parameter -> constant bank).
 struct FrameParams {
     double T[16];      // world -> velodyne, row-major (src/mapping_replay.py:225-226)
     double P[12];      // camera projection (src/camera.py:28)
     double range_max;  // cfg.MAPPING.PCD.RANGE_MAX
+    // float32 pre-cull: row 0 = T row 0 (velodyne x), rows 1..3 = rows of P*T (q0, q1, q2); see precull()
+    float Mf[16];
     int has_T;         // 0: cloud already in the velodyne frame
     int img_w, img_h;  // image.shape[1], image.shape[0]
     int pad;
@@ -32,7 +37,7 @@ struct GridParams {
     int mh, mw, c;
     int lane;             // class index named "lane", or -1
     int use_intensity;
-    int pad;
+    int tag_shift;        // C + 1: first bit of the frame tag in a cell-mask word
     uint8_t col_r[32];    // cfg.LABEL_COLORS[:, 0]
     uint8_t col_g[32];    // cfg.LABEL_COLORS[:, 1]   (blue is never compared, src/mapping_replay.py:276)
 };
@@ -88,8 +93,57 @@ __device__ __forceinline__ uint32_t class_bits(const GridParams& g, uint8_t r, u
     uint32_t bits = 0;
     for (int i = 0; i < g.c; ++i) bits |= (uint32_t)((r == g.col_r[i]) & (gch == g.col_g[i])) << i;
     if (g.use_intensity && g.lane >= 0 && ((bits >> g.lane) & 1u) && (intensity < 2.0 || intensity > 14.0))
-        bits |= kBoostBit;
+        bits |= 1u << g.c;
     return bits;
+}
+
+// Same classes from two 256-entry tables (built once per block in shared memory):
+// tab_r[v] has bit i set iff LABEL_COLORS[i].R == v, tab_g likewise for G.
+__device__ __forceinline__ void build_color_tables(const GridParams& g, uint32_t* tab_r, uint32_t* tab_g) {
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+        uint32_t br = 0, bg = 0;
+        for (int i = 0; i < g.c; ++i) {
+            br |= (uint32_t)(g.col_r[i] == v) << i;
+            bg |= (uint32_t)(g.col_g[i] == v) << i;
+        }
+        tab_r[v] = br;
+        tab_g[v] = bg;
+    }
+}
+
+__device__ __forceinline__ uint32_t class_bits_lut(const GridParams& g, const uint32_t* tab_r, const uint32_t* tab_g,
+                                                   uint8_t r, uint8_t gch, float intensity) {
+    uint32_t bits = tab_r[r] & tab_g[gch];
+    // float32 intensity compared as a double in the reference; 2 and 14 are exact in both, so the tests agree
+    if (g.use_intensity && g.lane >= 0 && ((bits >> g.lane) & 1u) && (intensity < 2.0f || intensity > 14.0f))
+        bits |= 1u << g.c;
+    return bits;
+}
+
+// Conservative float32 cull.  Returns false only when the exact double-precision rule
+// (project_point) is CERTAIN to reject the point, so that the expensive path runs on ~1/3 of the cloud.
+// Each float dot product carries a rigorous error bound e = kSlack * sum(|m_i| |x_i|), kSlack covering the
+// float rounding of the inputs, of the composed matrix and of the four-term sum (<= 6 * 2^-24 < 4e-7);
+// the double chain's own rounding (1e-16) and the division's (1e-16) disappear in the slack.
+__device__ __forceinline__ bool precull_pass(const FrameParams& f, float x, float y, float z) {
+    constexpr float kSlack = 1e-6f;
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    float v[4], e[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float* m = f.Mf + 4 * r;
+        v[r] = fmaf(m[0], x, fmaf(m[1], y, fmaf(m[2], z, m[3])));
+        e[r] = kSlack * fmaf(fabsf(m[0]), ax, fmaf(fabsf(m[1]), ay, fmaf(fabsf(m[2]), az, fabsf(m[3]))));
+    }
+    // anything not comfortably finite in float goes to the exact path (it rejects NaN / inf itself)
+    if (!(e[0] + e[1] + e[2] + e[3] < 1e30f)) return true;
+    if (!(v[0] + e[0] > 0.0f) || !(v[0] - e[0] < (float)f.range_max * (1.0f + kSlack))) return false;
+    if (v[3] - e[3] > 0.0f) {  // depth certainly positive: -q2 < q0 < W q2 and -q2 < q1 < H q2 must be possible
+        const float q2hi = (v[3] + e[3]) * (1.0f + kSlack);
+        if (!(v[1] + e[1] > -q2hi) || !(v[1] - e[1] < (float)f.img_w * q2hi)) return false;
+        if (!(v[2] + e[2] > -q2hi) || !(v[2] - e[2] < (float)f.img_h * q2hi)) return false;
+    }
+    return true;  // includes depth <= 0 or uncertain: decided exactly
 }
 
 template <int LAYOUT>

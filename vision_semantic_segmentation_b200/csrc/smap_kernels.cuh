@@ -46,55 +46,179 @@ __device__ __forceinline__ void touch_flush(TouchList<CAP>& tl, uint32_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1+K2+K3a fused (deterministic path): project -> cull -> gather label -> class bits -> cell ->
-// atomicOr into the frame's cell mask; the thread that turns a mask from 0 to non-zero records the cell.
-// Replaces src/mapping_replay.py:223-244 and :261-277,:288-290 for one frame.
+// Epoch-tagged cell masks.
+// OR `bits` into the word of `cell` for the frame whose tag is `tagword` (tag already shifted into the
+// high bits) and return the class/boost bits the word held FOR THIS FRAME before the call.
+// A word carrying an older tag is stale and reads as empty; tags only grow within a mask slot, so
+// atomicMax installs the new tag (clearing the old bits) without a read-modify-write loop.
+// A plain L2 load first: a point whose bits are already present costs no atomic at all.
 // ------------------------------------------------------------------------------------------------
-template <int LAYOUT, int PTS>
-__global__ void __launch_bounds__(kThreads)
-k_integrate(const void* __restrict__ pts, int64_t n, int64_t ld, const uint8_t* __restrict__ image,
-            const __grid_constant__ FrameParams fp, const __grid_constant__ GridParams gp,
-            uint32_t* __restrict__ mask, uint32_t* __restrict__ touched, uint32_t* __restrict__ counter) {
-    __shared__ TouchList<kThreads * PTS> tl;
-    if (threadIdx.x == 0) tl.n = 0;
+__device__ __forceinline__ uint32_t tagged_or(uint32_t* __restrict__ word, uint32_t tagword, uint32_t bits, int shift) {
+    const uint32_t low = (1u << shift) - 1u;
+    uint32_t cur = __ldcg(word);
+    if ((cur >> shift) != (tagword >> shift)) {
+        atomicMax(word, tagword);
+    } else if ((cur & bits) == bits) {
+        return cur & low;
+    }
+    return atomicOr(word, bits) & low;
+}
+
+// One frame of a batched launch.
+struct BatchFrame {
+    FrameParams fp;
+    const void* pts;
+    const uint8_t* image;
+    uint32_t* mask;       // this frame's mask slot (MH*MW words)
+    int64_t n;
+    int64_t ld;
+    uint32_t tagword;     // frame tag << tag_shift
+    uint32_t block_begin; // first block of this frame in the launch
+};
+
+struct BatchParams {
+    int n_frames;
+    int pad;
+    BatchFrame f[kMaxBatch];
+};
+
+constexpr int kFusePts = 8;                      // points per thread in the pre-cull phase
+constexpr int kFuseTile = kThreads * kFusePts;   // 2048 points per block
+
+// ------------------------------------------------------------------------------------------------
+// K1+K2+K3 fused: the whole per-frame rule of SURVEY.md section 9 in one kernel, several frames per launch.
+//   phase 1  every thread streams kFusePts points (coalesced float4 / double rows), runs the float32
+//            conservative cull and appends the survivors (~35 %) to a shared-memory list;
+//   phase 2  the block walks the dense survivor list: exact double projection (src/mapping_replay.py:223-240),
+//            label gather (:244), class bits from the shared colour tables (:276,:288-290), cell (:261-268),
+//            tagged OR into the frame's mask (the per-frame (cell, class) de-duplication of :281/:294);
+//   MODE 0   (deterministic) the thread that first touches a cell records it for k_apply;
+//   MODE 1   (count update, CM = identity) every NEWLY set class bit adds 1.0 to map[cell, class] and a newly
+//            set boost bit adds 2.0 to map[cell, lane] with a float64 atomic: integer-valued sums, exact in any order.
+// ------------------------------------------------------------------------------------------------
+template <int LAYOUT, int MODE>
+__global__ void __launch_bounds__(kThreads, 3)
+k_fuse(const __grid_constant__ BatchParams bp, const __grid_constant__ GridParams gp, double* __restrict__ map,
+       uint32_t* __restrict__ touched, uint32_t* __restrict__ counter) {
+    __shared__ uint32_t s_tab_r[256], s_tab_g[256];
+    __shared__ float4 s_surv[LAYOUT == 0 ? kFuseTile : 1];     // surviving points (float4 layout)
+    __shared__ uint32_t s_idx[LAYOUT == 0 ? 1 : kFuseTile];    // or their index in the tile (float64 layout)
+    __shared__ uint32_t s_nsurv;
+    __shared__ TouchList<MODE == 0 ? kFuseTile : 1> tl;
+
+    int fi = 0;
+    while (fi + 1 < bp.n_frames && blockIdx.x >= bp.f[fi + 1].block_begin) ++fi;
+    const BatchFrame& F = bp.f[fi];
+    const FrameParams& fp = F.fp;
+
+    build_color_tables(gp, s_tab_r, s_tab_g);
+    if (threadIdx.x == 0) {
+        s_nsurv = 0;
+        tl.n = 0;
+    }
     __syncthreads();
 
-    const int64_t base = (int64_t)blockIdx.x * (kThreads * PTS);
-    double x[PTS], y[PTS], z[PTS], it[PTS];
-    bool live[PTS];
+    // ---- phase 1: stream + float32 pre-cull + compaction
+    const int64_t base = (int64_t)(blockIdx.x - F.block_begin) * kFuseTile;
+    const int lane = threadIdx.x & 31;
+    if (LAYOUT == 0) {
+        const float4* p4 = reinterpret_cast<const float4*>(F.pts);
+        float4 p[kFusePts];
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        const int64_t k = base + j * kThreads + threadIdx.x;
-        live[j] = k < n;
-        if (live[j]) load_point<LAYOUT>(pts, ld, k, x[j], y[j], z[j], it[j]);
+        for (int j = 0; j < kFusePts; ++j) {
+            const int64_t k = base + j * kThreads + threadIdx.x;
+            p[j] = (k < F.n) ? __ldcs(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < kFusePts; ++j) {
+            const int64_t k = base + j * kThreads + threadIdx.x;
+            const bool pass = (k < F.n) && precull_pass(fp, p[j].x, p[j].y, p[j].z);
+            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+            if (ballot) {
+                const int leader = __ffs(ballot) - 1;
+                uint32_t slot = 0;
+                if (lane == leader) slot = atomicAdd(&s_nsurv, (uint32_t)__popc(ballot));
+                slot = __shfl_sync(0xffffffffu, slot, leader);
+                if (pass) s_surv[slot + __popc(ballot & ((1u << lane) - 1u))] = p[j];
+            }
+        }
+    } else {
+        const double* pd = reinterpret_cast<const double*>(F.pts);
+#pragma unroll 2
+        for (int j = 0; j < kFusePts; ++j) {
+            const int64_t k = base + j * kThreads + threadIdx.x;
+            bool pass = false;
+            if (k < F.n) pass = precull_pass(fp, (float)__ldg(pd + k), (float)__ldg(pd + F.ld + k), (float)__ldg(pd + 2 * F.ld + k));
+            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+            if (ballot) {
+                const int leader = __ffs(ballot) - 1;
+                uint32_t slot = 0;
+                if (lane == leader) slot = atomicAdd(&s_nsurv, (uint32_t)__popc(ballot));
+                slot = __shfl_sync(0xffffffffu, slot, leader);
+                if (pass) s_idx[slot + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)(j * kThreads + threadIdx.x);
+            }
+        }
     }
-#pragma unroll
-    for (int j = 0; j < PTS; ++j) {
+    __syncthreads();
+
+    // ---- phase 2: exact path on the dense survivor list
+    const uint32_t nsurv = s_nsurv;
+    for (uint32_t s0 = 0; s0 < nsurv; s0 += kThreads) {
+        const uint32_t s = s0 + threadIdx.x;
         bool first = false;
         uint32_t cell = 0;
-        if (live[j]) {
+        if (s < nsurv) {
+            double x, y, z;
+            float it;
+            if (LAYOUT == 0) {
+                const float4 q = s_surv[s];
+                x = (double)q.x; y = (double)q.y; z = (double)q.z; it = q.w;
+            } else {
+                const double* pd = reinterpret_cast<const double*>(F.pts);
+                const int64_t k = base + s_idx[s];
+                x = __ldg(pd + k); y = __ldg(pd + F.ld + k); z = __ldg(pd + 2 * F.ld + k);
+                // the boost test compares the float64 intensity with 2 and 14; rounding to float32 could move a
+                // value across them, so clamp the float onto the same side as the double
+                const double itd = __ldg(pd + 3 * F.ld + k);
+                it = (itd < 2.0) ? 0.0f : ((itd > 14.0) ? 15.0f : 8.0f);
+                if (itd != itd) it = 8.0f;  // NaN: neither < 2 nor > 14
+            }
             int iu, iv;
-            if (project_point(fp, x[j], y[j], z[j], iu, iv)) {
-                const uint8_t* px = image + 3 * ((int64_t)iv * fp.img_w + iu);
+            if (project_point(fp, x, y, z, iu, iv)) {
+                const uint8_t* px = F.image + 3 * ((int64_t)iv * fp.img_w + iu);
                 const uint8_t r = __ldg(px), g = __ldg(px + 1);
-                const uint32_t bits = class_bits(gp, r, g, it[j]);
-                if (bits && cell_of(gp, x[j], y[j], cell)) {
-                    const uint32_t old = atomicOr(mask + cell, bits);
-                    first = (old == 0u);
+                const uint32_t bits = class_bits_lut(gp, s_tab_r, s_tab_g, r, g, it);
+                if (bits && cell_of(gp, x, y, cell)) {
+                    const uint32_t prev = tagged_or(F.mask + cell, F.tagword, bits, gp.tag_shift);
+                    if (MODE == 0) {
+                        first = (prev == 0u);
+                    } else {
+                        uint32_t fresh = bits & ~prev;
+                        double* row = map + (size_t)cell * gp.c;
+                        if (fresh >> gp.c) {  // boost bit newly set: +2 on the lane class (src/mapping_replay.py:294)
+                            atomicAdd(row + gp.lane, 2.0);
+                            fresh &= (1u << gp.c) - 1u;
+                        }
+                        while (fresh) {
+                            const int i = __ffs(fresh) - 1;
+                            fresh &= fresh - 1u;
+                            atomicAdd(row + i, 1.0);
+                        }
+                    }
                 }
             }
         }
-        touch_push(tl, first, cell);
+        if (MODE == 0) touch_push(tl, first, cell);
     }
-    touch_flush(tl, touched, counter);
+    if (MODE == 0) touch_flush(tl, touched, counter);
 }
 
-// Parity kernel for update_map (src/mapping_replay.py:261-277,:288-290): same scatter, but from an already
-// projected cloud (4, M) float64 + its (3, M) RGB labels.
+// Parity kernel for update_map (src/mapping_replay.py:261-277,:288-290): same scatter as k_fuse MODE 0, but from
+// an already projected cloud (4, M) float64 + its (3, M) RGB labels.
 template <int PTS>
 __global__ void __launch_bounds__(kThreads)
 k_update_scatter(const double* __restrict__ pcd, int64_t ld, const uint8_t* __restrict__ label, int64_t ldl,
-                 int64_t m, const __grid_constant__ GridParams gp, uint32_t* __restrict__ mask,
+                 int64_t m, const __grid_constant__ GridParams gp, uint32_t* __restrict__ mask, uint32_t tagword,
                  uint32_t* __restrict__ touched, uint32_t* __restrict__ counter) {
     __shared__ TouchList<kThreads * PTS> tl;
     if (threadIdx.x == 0) tl.n = 0;
@@ -107,7 +231,8 @@ k_update_scatter(const double* __restrict__ pcd, int64_t ld, const uint8_t* __re
         uint32_t cell = 0;
         if (k < m) {
             const uint32_t bits = class_bits(gp, label[k], label[ldl + k], pcd[3 * ld + k]);
-            if (bits && cell_of(gp, pcd[k], pcd[ld + k], cell)) first = (atomicOr(mask + cell, bits) == 0u);
+            if (bits && cell_of(gp, pcd[k], pcd[ld + k], cell))
+                first = (tagged_or(mask + cell, tagword, bits, gp.tag_shift) == 0u);
         }
         touch_push(tl, first, cell);
     }
@@ -115,51 +240,46 @@ k_update_scatter(const double* __restrict__ pcd, int64_t ld, const uint8_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3b: apply the frame's cell masks to the grid, classes in ascending order, then clear the masks.
-// Replaces the "+=" statements at src/mapping_replay.py:281 and :294.
-// A group of G lanes (G = 8, 16 or 32 >= C) owns one touched cell; lane j owns class j, so the
-// 8*C-byte row of the grid is read and written coalesced.
-// `counter` points at this frame's touched count; `next_counter` (the other half of the double
-// buffer) is zeroed for the next frame.
+// K3b (deterministic path): apply the frame's cell masks to the grid, classes in ascending order.
+// Replaces the "+=" statements at src/mapping_replay.py:281 and :294 bit for bit, any update matrix.
+// One thread per touched cell: touched[] is read coalesced, then mask word and the C-element grid row are
+// independent random accesses, so ~all touched cells of a frame are in flight at once (the first version
+// walked 8-lane groups through a serial load chain and took 100 us for 137 k cells).
+// `counter` is this frame's touched count; `next_counter` (other half of the double buffer) is zeroed.
 // ------------------------------------------------------------------------------------------------
-template <int G>
 __global__ void __launch_bounds__(kThreads)
-k_apply(double* __restrict__ map, uint32_t* __restrict__ mask, const uint32_t* __restrict__ touched,
+k_apply(double* __restrict__ map, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ touched,
         const uint32_t* __restrict__ counter, uint32_t* __restrict__ next_counter,
         const double* __restrict__ cm, int c, int lane_cls) {
-    extern __shared__ double s_cm[];  // C x C
-    for (int i = threadIdx.x; i < c * c; i += blockDim.x) s_cm[i] = cm[i];
+    extern __shared__ double s_cm[];  // C x C, transposed: s_cm[i * c + j] = cm[j * c + i] (column i contiguous)
+    for (int e = threadIdx.x; e < c * c; e += blockDim.x) s_cm[(e % c) * c + e / c] = cm[e];
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) *next_counter = 0u;
-
     const uint32_t count = *counter;
-    const int j = threadIdx.x % G;
-    const uint32_t groups_per_block = kThreads / G;
-    const uint32_t stride = gridDim.x * groups_per_block;
-    // every lane of a warp runs the same number of iterations (count is uniform, groups differ only in t)
-    const uint32_t iters = (count + stride - 1) / stride;
-    uint32_t t = blockIdx.x * groups_per_block + threadIdx.x / G;
-    for (uint32_t it = 0; it < iters; ++it, t += stride) {
-        const bool active = t < count;
-        uint32_t cell = 0, bits = 0;
-        if (active) {
-            cell = touched[t];
-            bits = mask[cell];
-        }
-        __syncwarp();  // all lanes of the group have read the mask before it is cleared
-        if (active) {
-            if (j == 0) mask[cell] = 0u;
-            if (j < c) {
-                double* p = map + (size_t)cell * c + j;
-                double acc = *p;
-                for (int i = 0; i < c; ++i) {
-                    if ((bits >> i) & 1u) {
-                        acc = __dadd_rn(acc, s_cm[j * c + i]);
-                        if (i == lane_cls && j == i && (bits & kBoostBit)) acc = __dadd_rn(acc, 2.0);
-                    }
+    const uint32_t boost = 1u << c;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const uint32_t cell = touched[t];
+        const uint32_t bits = __ldcg(mask + cell);
+        double* row = map + (size_t)cell * c;
+        for (int j0 = 0; j0 < c; j0 += 8) {
+            double acc[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) acc[jj] = (j0 + jj < c) ? row[j0 + jj] : 0.0;
+            for (int i = 0; i < c; ++i) {
+                if (!((bits >> i) & 1u)) continue;
+                const double* col = s_cm + i * c + j0;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                    if (j0 + jj < c) acc[jj] = __dadd_rn(acc[jj], col[jj]);
+                if (i == lane_cls && (bits & boost) && i >= j0 && i < j0 + 8) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj)
+                        if (j0 + jj == i) acc[jj] = __dadd_rn(acc[jj], 2.0);
                 }
-                *p = acc;
             }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+                if (j0 + jj < c) row[j0 + jj] = acc[jj];
         }
     }
 }

@@ -125,6 +125,10 @@ class DeviceMapper(object):
         """project_pcd + update_map of one frame, fused, deterministic (bit-exact)."""
         _native.check(self._lib.smap_integrate(self._h, ctypes.byref(frame), self._stream()))
 
+    def set_deterministic(self, on=True):
+        """Force the ordered two-kernel update even for the count update (see include/smap.h)."""
+        _native.check(self._lib.smap_set_deterministic(self._h, int(bool(on))))
+
     def integrate_host(self, frame):
         _native.check(self._lib.smap_integrate_host(self._h, ctypes.byref(frame), self._stream()))
 
