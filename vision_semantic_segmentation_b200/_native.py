@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsmap_b200.so")
+LIB_PATH = os.environ.get("SMAP_LIB_PATH") or os.path.join(_HERE, "csrc", "libsmap_b200.so")  # env: kernel-variant sweeps
 
 SMAP_PTS_F32X4 = 0
 SMAP_PTS_F64_SOA = 1

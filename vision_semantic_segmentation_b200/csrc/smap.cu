@@ -1,5 +1,6 @@
 // C ABI (include/smap.h) of the B200 semantic-mapping path: host-side launch logic.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -57,11 +58,10 @@ struct smap_handle {
     uint32_t tag_max = 0;  // largest tag that fits above tag_shift
     bool identity_cm = false;   // update matrix is exactly np.eye(C): the count update
     bool deterministic = false; // force the touched-list + k_apply path even for the count update
-    // deterministic path: touched list + double-buffered counter
-    uint32_t* touched = nullptr;
-    int64_t touched_cap = 0;
-    uint32_t* counters = nullptr;  // [2]
+    // ordered (two-kernel) update: double-buffered bounding box of the cells a frame touched
+    FrameBox* boxes = nullptr;     // [2]
     int parity = 0;
+    int sm_count = 148;
     // class tables
     double* cm_dev = nullptr;
     uint8_t colors[SMAP_MAX_CLASSES * 3];
@@ -99,6 +99,8 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
     if (f->layout != SMAP_PTS_F32X4 && f->layout != SMAP_PTS_F64_SOA) return fail(SMAP_ERR_INVALID, "unknown point layout");
     if (f->layout == SMAP_PTS_F64_SOA && f->ld < f->n_points) return fail(SMAP_ERR_INVALID, "ld < n_points");
     if (f->image_width <= 0 || f->image_height <= 0) return fail(SMAP_ERR_INVALID, "empty label image");
+    if ((int64_t)f->image_width * f->image_height * 3 >= ((int64_t)1 << 32)) return fail(SMAP_ERR_INVALID, "label image larger than 4 GB");
+    if (f->layout == SMAP_PTS_F64_SOA && f->n_points >= ((int64_t)1 << 32)) return fail(SMAP_ERR_INVALID, "more than 2^32 points in a float64 cloud");
     if (f->n_points > 0 && (!f->points_dev || !f->image_dev)) return fail(SMAP_ERR_INVALID, "NULL points / image");
     if (f->layout == SMAP_PTS_F32X4 && (reinterpret_cast<uintptr_t>(f->points_dev) & 15u))
         return fail(SMAP_ERR_INVALID, "float4 cloud must be 16-byte aligned");
@@ -115,28 +117,21 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
                 for (int k = 0; k < 4; ++k) acc += fp.P[4 * r + k] * Tm[4 * k + j];
                 fp.Mf[4 * (r + 1) + j] = (float)acc;
             }
+        for (int r = 0; r < 4; ++r) {
+            float a = 0.f;
+            for (int j = 0; j < 3; ++j) a = fmaxf(a, fabsf(fp.Mf[4 * r + j]));
+            // next float up so that the bound survives the rounding of these two products
+            fp.Ea[r] = nextafterf(kCullSlack * a, INFINITY);
+            fp.Eb[r] = nextafterf(kCullSlack * fabsf(fp.Mf[4 * r + 3]), INFINITY);
+        }
+        fp.range_hi = (float)fp.range_max * (1.0f + kCullSlack);
+        fp.img_wf = (float)f->image_width;
+        fp.img_hf = (float)f->image_height;
     }
     fp.has_T = f->has_transform ? 1 : 0;
     fp.img_w = f->image_width;
     fp.img_h = f->image_height;
     fp.pad = 0;
-    return SMAP_OK;
-}
-
-int ensure_touched(smap_handle* h, int64_t n) {
-    int64_t need = n < h->cells ? n : h->cells;
-    // a block appends at most its tile, so the list never exceeds min(n, cells) entries
-    if (need <= h->touched_cap) return SMAP_OK;
-    if (h->touched) {
-        CK(cudaDeviceSynchronize());
-        CK(cudaFree(h->touched));
-        h->touched = nullptr;
-        h->touched_cap = 0;
-    }
-    int64_t cap = need + need / 4 + 1024;
-    if (cap > h->cells) cap = h->cells;
-    CK(cudaMalloc(&h->touched, sizeof(uint32_t) * (size_t)cap));
-    h->touched_cap = cap;
     return SMAP_OK;
 }
 
@@ -185,32 +180,32 @@ int next_tag(smap_handle* h, cudaStream_t st, uint32_t* tagword) {
     return SMAP_OK;
 }
 
-// K3b launch: apply the masks of the frame whose counter is counters[parity]; flips parity.
-int launch_apply(smap_handle* h, double* map, cudaStream_t st) {
+// K3b launch: apply the masks of the frame whose box is boxes[parity]; flips parity.
+int launch_apply(smap_handle* h, double* map, uint32_t tagword, cudaStream_t st) {
     const int c = h->cfg.num_classes;
-    const uint32_t* counter = h->counters + h->parity;
-    uint32_t* next_counter = h->counters + (h->parity ^ 1);
     const size_t smem = sizeof(double) * c * c;
-    int sm = 148;
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->cfg.device);
-    k_apply<<<sm * 8, kThreads, smem, st>>>(map, h->mask, h->touched, counter, next_counter, h->cm_dev, c, h->cfg.lane_index);
+    k_apply<<<h->sm_count * 8, kThreads, smem, st>>>(map, h->mask, tagword, h->gp.tag_shift, h->boxes + h->parity,
+                                                    h->boxes + (h->parity ^ 1), h->cm_dev, c, h->cfg.lane_index,
+                                                    h->cfg.map_width);
     CK(cudaGetLastError());
     h->parity ^= 1;
     h->stats.kernel_launches += 1;
     return SMAP_OK;
 }
 
-// One launch of k_fuse over up to kMaxBatch frames (already validated; fps[i] filled).
-// mode 0: deterministic scatter of ONE frame into slot 0 (caller launches k_apply afterwards)
+// One launch of k_stream over up to kMaxBatch frames (already validated; fps[i] filled).
+// mode 0: ordered update, ONE frame, masks + bounding box only (caller launches k_apply with *tagword_out)
 // mode 1: count update with atomics, frame i uses mask slot i
-int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, int mode, cudaStream_t st) {
-    BatchParams bp;
+int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, int mode,
+                  cudaStream_t st, uint32_t* tagword_out) {
+    static BatchParams bp;  // 7 KB: keep it off the stack; handles are single-threaded per the ABI contract
     memset(&bp, 0, sizeof bp);
     uint32_t tagword = 0;
     int rc = next_tag(h, st, &tagword);
     if (rc) return rc;
-    uint32_t blocks = 0;
-    int layout = frames[0].layout;
+    if (tagword_out) *tagword_out = tagword;
+    uint32_t units = 0;
+    const int layout = frames[0].layout;
     int used = 0;
     for (int i = 0; i < n_frames; ++i) {
         if (frames[i].n_points == 0) continue;
@@ -223,19 +218,23 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         b.n = frames[i].n_points;
         b.ld = frames[i].ld;
         b.tagword = tagword;
-        b.block_begin = blocks;
-        blocks += (uint32_t)ceil_div(frames[i].n_points, kFuseTile);
+        b.unit_begin = units;
+        units += (uint32_t)ceil_div(frames[i].n_points, kUnitPts);
         ++used;
     }
     if (used == 0) return SMAP_OK;
     bp.n_frames = used;
-    uint32_t* counter = h->counters + h->parity;
+    bp.n_units = units;
+    // persistent grid: as many blocks as stay resident, never more than there are units
+    uint32_t grid = (uint32_t)h->sm_count * SMAP_STREAM_MINB;
+    if (grid > units) grid = units;
+    FrameBox* box = h->boxes + h->parity;
     if (layout == SMAP_PTS_F32X4) {
-        if (mode == 0) k_fuse<SMAP_PTS_F32X4, 0><<<blocks, kThreads, 0, st>>>(bp, h->gp, h->map, h->touched, counter);
-        else k_fuse<SMAP_PTS_F32X4, 1><<<blocks, kThreads, 0, st>>>(bp, h->gp, h->map, h->touched, counter);
+        if (mode == 0) k_stream<SMAP_PTS_F32X4, 0><<<grid, kThreads, 0, st>>>(bp, h->gp, h->map, box);
+        else k_stream<SMAP_PTS_F32X4, 1><<<grid, kThreads, 0, st>>>(bp, h->gp, h->map, box);
     } else {
-        if (mode == 0) k_fuse<SMAP_PTS_F64_SOA, 0><<<blocks, kThreads, 0, st>>>(bp, h->gp, h->map, h->touched, counter);
-        else k_fuse<SMAP_PTS_F64_SOA, 1><<<blocks, kThreads, 0, st>>>(bp, h->gp, h->map, h->touched, counter);
+        if (mode == 0) k_stream<SMAP_PTS_F64_SOA, 0><<<grid, kThreads, 0, st>>>(bp, h->gp, h->map, box);
+        else k_stream<SMAP_PTS_F64_SOA, 1><<<grid, kThreads, 0, st>>>(bp, h->gp, h->map, box);
     }
     CK(cudaGetLastError());
     h->stats.kernel_launches += 1;
@@ -338,8 +337,16 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->cells);
     if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->cells);
     if (e == cudaSuccess) h->n_slots = 1;
-    if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(uint32_t) * 2);
-    if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(uint32_t) * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&h->boxes, sizeof(FrameBox) * 2);
+    if (e == cudaSuccess) {
+        FrameBox init[2];
+        for (int i = 0; i < 2; ++i) {
+            init[i].x0 = 0x7fffffff; init[i].x1 = -1; init[i].y0 = 0x7fffffff; init[i].y1 = -1;
+            init[i].touched = 0; init[i].pad[0] = init[i].pad[1] = init[i].pad[2] = 0;
+        }
+        e = cudaMemcpy(h->boxes, init, sizeof init, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     if (e == cudaSuccess) e = cudaMalloc(&h->cm_dev, sizeof(double) * SMAP_MAX_CLASSES * SMAP_MAX_CLASSES);
     if (e == cudaSuccess) e = cudaMalloc(&h->total_dev, sizeof(int64_t));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -358,7 +365,7 @@ int smap_destroy(smap_handle* h) {
     DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
     if (h->own_map) cudaFree(h->map);
-    cudaFree(h->mask); cudaFree(h->touched); cudaFree(h->counters); cudaFree(h->cm_dev); cudaFree(h->total_dev);
+    cudaFree(h->mask); cudaFree(h->boxes); cudaFree(h->cm_dev); cudaFree(h->total_dev);
     cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
     for (int i = 0; i < smap_handle::kStages; ++i) {
         cudaFree(h->stage_pts[i]);
@@ -442,18 +449,16 @@ int smap_update(smap_handle* h, double* map_dev, const double* pcd, int64_t ld, 
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (m == 0) return SMAP_OK;
-    int rc = ensure_touched(h, m);
-    if (rc) return rc;
-    constexpr int PTS = 2;
-    const unsigned grid = (unsigned)ceil_div(m, (int64_t)kThreads * PTS);
     uint32_t tagword = 0;
-    rc = next_tag(h, st, &tagword);
+    int rc = next_tag(h, st, &tagword);
     if (rc) return rc;
-    k_update_scatter<PTS><<<grid, kThreads, 0, st>>>(pcd, ld, label, ldl, m, h->gp, h->mask, tagword, h->touched, h->counters + h->parity);
+    int64_t grid = ceil_div(m, kThreads);
+    if (grid > (int64_t)h->sm_count * 16) grid = (int64_t)h->sm_count * 16;
+    k_update_scatter<<<(unsigned)grid, kThreads, 0, st>>>(pcd, ld, label, ldl, m, h->gp, h->mask, tagword, h->boxes + h->parity);
     CK(cudaGetLastError());
     h->stats.kernel_launches += 1;
     h->last_stream = st;
-    return launch_apply(h, map_dev ? map_dev : h->map, st);
+    return launch_apply(h, map_dev ? map_dev : h->map, tagword, st);
 }
 
 int smap_set_deterministic(smap_handle* h, int on) {
@@ -482,16 +487,14 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
             h->stats.points += frames[begin + i].n_points;
             if (frames[begin + i].n_points > max_pts) max_pts = frames[begin + i].n_points;
         }
-        int rc;
+        int rc = SMAP_OK;
         if (atomic_counts) {
             rc = ensure_slots(h, chunk);
-            if (!rc) rc = launch_fuse(h, frames + begin, fps, chunk, 1, st);
+            if (!rc) rc = launch_stream(h, frames + begin, fps, chunk, 1, st, nullptr);
         } else if (max_pts > 0) {
-            rc = ensure_touched(h, max_pts);
-            if (!rc) rc = launch_fuse(h, frames + begin, fps, 1, 0, st);
-            if (!rc) rc = launch_apply(h, h->map, st);
-        } else {
-            rc = SMAP_OK;
+            uint32_t tagword = 0;
+            rc = launch_stream(h, frames + begin, fps, 1, 0, st, &tagword);
+            if (!rc) rc = launch_apply(h, h->map, tagword, st);
         }
         if (rc) return rc;
         begin += chunk;
@@ -629,10 +632,10 @@ int smap_get_stats(smap_handle* h, smap_stats* out) {
     if (!h || !out) return fail(SMAP_ERR_INVALID, "NULL argument");
     DeviceGuard guard(h->cfg.device);
     CK(cudaStreamSynchronize(h->last_stream));
-    // after launch_apply flipped the parity, the finished frame's count sits in counters[parity ^ 1]
-    uint32_t k = 0;
-    CK(cudaMemcpy(&k, h->counters + (h->parity ^ 1), sizeof k, cudaMemcpyDeviceToHost));
-    h->stats.touched_cells = k;
+    // after launch_apply flipped the parity, the finished frame's box sits in boxes[parity ^ 1]
+    FrameBox b;
+    CK(cudaMemcpy(&b, h->boxes + (h->parity ^ 1), sizeof b, cudaMemcpyDeviceToHost));
+    h->stats.touched_cells = b.touched;
     *out = h->stats;
     return SMAP_OK;
 }

@@ -22,12 +22,18 @@ struct FrameParams {
     double T[16];      // world -> velodyne, row-major (src/mapping_replay.py:225-226)
     double P[12];      // camera projection (src/camera.py:28)
     double range_max;  // cfg.MAPPING.PCD.RANGE_MAX
-    // float32 pre-cull: row 0 = T row 0 (velodyne x), rows 1..3 = rows of P*T (q0, q1, q2); see precull()
+    // float32 pre-cull (see precull_pass): row 0 = T row 0 (velodyne x), rows 1..3 = rows of P*T (q0, q1, q2)
     float Mf[16];
+    float Ea[4];       // kSlack * max(|m_r0|, |m_r1|, |m_r2|)   error bound of row r = Ea[r] * (|x|+|y|+|z|) + Eb[r]
+    float Eb[4];       // kSlack * |m_r3|
+    float range_hi;    // range_max * (1 + kSlack)
+    float img_wf, img_hf;
     int has_T;         // 0: cloud already in the velodyne frame
     int img_w, img_h;  // image.shape[1], image.shape[0]
     int pad;
 };
+
+constexpr float kCullSlack = 1e-6f;
 
 // Grid + class constants of a mapper handle.
 struct GridParams {
@@ -88,6 +94,14 @@ __device__ __forceinline__ bool cell_of(const GridParams& g, double x, double y,
     return a && b;
 }
 
+__device__ __forceinline__ bool cell_xy(const GridParams& g, double x, double y, int& cx, int& cy) {
+    const double gx = __ddiv_rn(__dsub_rn(__dadd_rn(x, g.off_x), g.bx0), g.res);
+    const double gy = __ddiv_rn(__dsub_rn(__dadd_rn(y, g.off_y), g.by0), g.res);
+    const bool a = trunc_in_range(gx, g.mh, cx);
+    const bool b = trunc_in_range(gy, g.mw, cy);
+    return a && b;
+}
+
 // src/mapping_replay.py:276 and :288-290: classes whose (R, G) equal the pixel's, plus the boost flag.
 __device__ __forceinline__ uint32_t class_bits(const GridParams& g, uint8_t r, uint8_t gch, double intensity) {
     uint32_t bits = 0;
@@ -120,30 +134,34 @@ __device__ __forceinline__ uint32_t class_bits_lut(const GridParams& g, const ui
     return bits;
 }
 
-// Conservative float32 cull.  Returns false only when the exact double-precision rule
-// (project_point) is CERTAIN to reject the point, so that the expensive path runs on ~1/3 of the cloud.
-// Each float dot product carries a rigorous error bound e = kSlack * sum(|m_i| |x_i|), kSlack covering the
-// float rounding of the inputs, of the composed matrix and of the four-term sum (<= 6 * 2^-24 < 4e-7);
-// the double chain's own rounding (1e-16) and the division's (1e-16) disappear in the slack.
-__device__ __forceinline__ bool precull_pass(const FrameParams& f, float x, float y, float z) {
-    constexpr float kSlack = 1e-6f;
-    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+// Conservative float32 cull.  Returns false only when the exact double-precision rule (project_point) is
+// CERTAIN to reject the point, so that the expensive path runs on ~1/3 of the cloud.
+// Row r of Mf evaluated in float differs from the exact value by at most
+//     e_r = Ea[r] * (|x|+|y|+|z|) + Eb[r]   >=   kCullSlack * sum_i |m_ri| |x_i|
+// where kCullSlack = 1e-6 covers the float rounding of the inputs (6e-8), of the composed matrix (6e-8) and
+// of the four-term fused sum (< 2.4e-7) with a 2x margin for the comparisons below; the double chain's own
+// rounding and the final division's (1e-16) disappear in it.  Branch-free: one predicate per point.
+struct CullConsts {
+    float m[16], ea[4], eb[4], range_hi, wf, hf;
+};
+
+__device__ __forceinline__ bool precull_pass(const CullConsts& k, float x, float y, float z) {
+    const float s = fabsf(x) + fabsf(y) + fabsf(z);
     float v[4], e[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const float* m = f.Mf + 4 * r;
-        v[r] = fmaf(m[0], x, fmaf(m[1], y, fmaf(m[2], z, m[3])));
-        e[r] = kSlack * fmaf(fabsf(m[0]), ax, fmaf(fabsf(m[1]), ay, fmaf(fabsf(m[2]), az, fabsf(m[3]))));
+        v[r] = fmaf(k.m[4 * r], x, fmaf(k.m[4 * r + 1], y, fmaf(k.m[4 * r + 2], z, k.m[4 * r + 3])));
+        e[r] = fmaf(k.ea[r], s, k.eb[r]);
     }
-    // anything not comfortably finite in float goes to the exact path (it rejects NaN / inf itself)
-    if (!(e[0] + e[1] + e[2] + e[3] < 1e30f)) return true;
-    if (!(v[0] + e[0] > 0.0f) || !(v[0] - e[0] < (float)f.range_max * (1.0f + kSlack))) return false;
-    if (v[3] - e[3] > 0.0f) {  // depth certainly positive: -q2 < q0 < W q2 and -q2 < q1 < H q2 must be possible
-        const float q2hi = (v[3] + e[3]) * (1.0f + kSlack);
-        if (!(v[1] + e[1] > -q2hi) || !(v[1] - e[1] < (float)f.img_w * q2hi)) return false;
-        if (!(v[2] + e[2] > -q2hi) || !(v[2] - e[2] < (float)f.img_h * q2hi)) return false;
-    }
-    return true;  // includes depth <= 0 or uncertain: decided exactly
+    // anything not comfortably finite in float goes to the exact path (which rejects NaN / inf itself)
+    const bool finite = (e[0] + e[1] + e[2] + e[3]) < 1e30f;
+    const bool range_ok = (v[0] + e[0] > 0.0f) & (v[0] - e[0] < k.range_hi);
+    // depth certainly positive: -q2 < q0 < W q2 and -q2 < q1 < H q2 must be possible; otherwise decided exactly
+    const bool depth_pos = (v[3] - e[3]) > 0.0f;
+    const float q2hi = (v[3] + e[3]) * (1.0f + kCullSlack);
+    const bool u_ok = (v[1] + e[1] > -q2hi) & (v[1] - e[1] < k.wf * q2hi);
+    const bool v_ok = (v[2] + e[2] > -q2hi) & (v[2] - e[2] < k.hf * q2hi);
+    return !finite | (range_ok & (!depth_pos | (u_ok & v_ok)));
 }
 
 template <int LAYOUT>

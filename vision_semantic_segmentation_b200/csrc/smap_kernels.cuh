@@ -11,58 +11,25 @@ namespace smap {
 constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------------------------------------
-// Block-aggregated append of first-touched cells to the frame's touched list.
-// One shared counter per block, one global atomic per block (a single hot global address would
-// otherwise serialise ~1e5 atomics per frame in L2).
-// ------------------------------------------------------------------------------------------------
-template <int CAP>
-struct TouchList {
-    uint32_t cells[CAP];
-    uint32_t n;
-    uint32_t base;
-};
-
-template <int CAP>
-__device__ __forceinline__ void touch_push(TouchList<CAP>& tl, bool first, uint32_t cell) {
-    const unsigned ballot = __ballot_sync(0xffffffffu, first);
-    if (ballot) {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(ballot) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&tl.n, (uint32_t)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (first) tl.cells[base + __popc(ballot & ((1u << lane) - 1u))] = cell;
-    }
-}
-
-template <int CAP>
-__device__ __forceinline__ void touch_flush(TouchList<CAP>& tl, uint32_t* __restrict__ touched,
-                                            uint32_t* __restrict__ counter) {
-    __syncthreads();
-    if (threadIdx.x == 0 && tl.n) tl.base = atomicAdd(counter, tl.n);
-    __syncthreads();
-    const uint32_t n = tl.n, base = tl.base;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) touched[base + i] = tl.cells[i];
-}
-
-// ------------------------------------------------------------------------------------------------
 // Epoch-tagged cell masks.
-// OR `bits` into the word of `cell` for the frame whose tag is `tagword` (tag already shifted into the
-// high bits) and return the class/boost bits the word held FOR THIS FRAME before the call.
-// A word carrying an older tag is stale and reads as empty; tags only grow within a mask slot, so
-// atomicMax installs the new tag (clearing the old bits) without a read-modify-write loop.
-// A plain L2 load first: a point whose bits are already present costs no atomic at all.
+// Cell-mask word:  [ tag | boost bit (bit C) | C class bits ].  The tag is the serial number of the frame
+// that last wrote the word; a word carrying an older tag is stale and reads as empty, so masks are never
+// cleared.  Tags only grow within a mask slot, hence atomicMax installs the new tag (dropping the stale
+// bits) without a compare-and-swap loop, and the following atomicOr returns what THIS frame had already
+// put there: one L2 round trip on the critical path.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t tagged_or(uint32_t* __restrict__ word, uint32_t tagword, uint32_t bits, int shift) {
-    const uint32_t low = (1u << shift) - 1u;
-    uint32_t cur = __ldcg(word);
-    if ((cur >> shift) != (tagword >> shift)) {
-        atomicMax(word, tagword);
-    } else if ((cur & bits) == bits) {
-        return cur & low;
-    }
+__device__ __forceinline__ uint32_t tagged_or(uint32_t* __restrict__ word, uint32_t tagword, uint32_t bits, uint32_t low) {
+    atomicMax(word, tagword);
     return atomicOr(word, bits) & low;
 }
+
+// Bounding box (in cells) of everything a frame touched + number of touched cells; written by the ordered
+// (two-kernel) update so that k_apply sweeps only that window of the mask.
+struct FrameBox {
+    int x0, x1, y0, y1;   // inclusive; empty when x1 < x0
+    uint32_t touched;     // filled by k_apply (statistics)
+    uint32_t pad[3];
+};
 
 // One frame of a batched launch.
 struct BatchFrame {
@@ -73,205 +40,312 @@ struct BatchFrame {
     int64_t n;
     int64_t ld;
     uint32_t tagword;     // frame tag << tag_shift
-    uint32_t block_begin; // first block of this frame in the launch
+    uint32_t unit_begin;  // first work unit of this frame in the launch
 };
 
 struct BatchParams {
     int n_frames;
-    int pad;
+    uint32_t n_units;
     BatchFrame f[kMaxBatch];
 };
 
-constexpr int kFusePts = 8;                      // points per thread in the pre-cull phase
-constexpr int kFuseTile = kThreads * kFusePts;   // 2048 points per block
+// tuning knobs (overridable at compile time for the variant sweeps recorded in profiles/)
+#ifndef SMAP_STREAM_ROUND
+#define SMAP_STREAM_ROUND 8     // 32-point chunks a warp loads back to back (LDG.128 in flight per lane)
+#endif
+#ifndef SMAP_STREAM_ROUNDS
+#define SMAP_STREAM_ROUNDS 2    // rounds per work unit and warp
+#endif
+#ifndef SMAP_STREAM_MINB
+#define SMAP_STREAM_MINB 3      // resident blocks per SM the register allocation aims for
+#endif
+constexpr int kWarps = kThreads / 32;
+constexpr int kRound = SMAP_STREAM_ROUND;
+constexpr int kRounds = SMAP_STREAM_ROUNDS;
+constexpr int kWarpUnitPts = 32 * kRound * kRounds;   // points of a unit owned by one warp
+constexpr int kUnitPts = kWarps * kWarpUnitPts;       // points per work unit (per block iteration)
+constexpr int kQueueCap = 32 * kRound + 32;           // per-warp survivor stack: < 32 left over + one round
+
+template <int LAYOUT> struct QueueEntry { typedef float4 type; };
+template <> struct QueueEntry<1> { typedef uint32_t type; };
 
 // ------------------------------------------------------------------------------------------------
-// K1+K2+K3 fused: the whole per-frame rule of SURVEY.md section 9 in one kernel, several frames per launch.
-//   phase 1  every thread streams kFusePts points (coalesced float4 / double rows), runs the float32
-//            conservative cull and appends the survivors (~35 %) to a shared-memory list;
-//   phase 2  the block walks the dense survivor list: exact double projection (src/mapping_replay.py:223-240),
-//            label gather (:244), class bits from the shared colour tables (:276,:288-290), cell (:261-268),
-//            tagged OR into the frame's mask (the per-frame (cell, class) de-duplication of :281/:294);
-//   MODE 0   (deterministic) the thread that first touches a cell records it for k_apply;
+// K1+K2+K3 fused, persistent and warp-autonomous: the whole per-frame rule of SURVEY.md section 9 in one
+// kernel, up to kMaxBatch frames per launch.
+//
+// A block walks work units (kUnitPts consecutive points of one frame) round-robin; inside a unit every
+// warp owns a contiguous slice and never synchronises with the other warps:
+//   stream   kRound coalesced LDG.128 per lane in flight, float32 conservative cull (precull_pass), survivors
+//            (~35 %) pushed on the warp's private stack in shared memory (ballot + popc, no atomics);
+//   drain    whenever >= 32 survivors are stacked, pop 32 - one per lane, all lanes busy: exact double
+//            projection (src/mapping_replay.py:223-240), label gather (:244), class bits from the shared colour
+//            tables (:276,:288-290), cell (:261-268), tagged OR into the frame's mask slot (the per-frame
+//            (cell, class) de-duplication of :281/:294);
 //   MODE 1   (count update, CM = identity) every NEWLY set class bit adds 1.0 to map[cell, class] and a newly
-//            set boost bit adds 2.0 to map[cell, lane] with a float64 atomic: integer-valued sums, exact in any order.
+//            set boost bit adds 2.0 to map[cell, lane] with a float64 atomic: integer-valued sums, exact in any
+//            order;
+//   MODE 0   (ordered update) only the masks are written, plus the bounding box of the touched cells;
+//            k_apply then adds the matrix columns in class order.
+// Stacks survive unit boundaries and are flushed (partial warps) only when the block moves to another frame.
 // ------------------------------------------------------------------------------------------------
 template <int LAYOUT, int MODE>
-__global__ void __launch_bounds__(kThreads, 3)
-k_fuse(const __grid_constant__ BatchParams bp, const __grid_constant__ GridParams gp, double* __restrict__ map,
-       uint32_t* __restrict__ touched, uint32_t* __restrict__ counter) {
+__global__ void __launch_bounds__(kThreads, SMAP_STREAM_MINB)
+k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridParams gp, double* __restrict__ map,
+         FrameBox* __restrict__ box) {
+    typedef typename QueueEntry<LAYOUT>::type Entry;
+    __shared__ __align__(16) Entry s_queue[kWarps][kQueueCap];
     __shared__ uint32_t s_tab_r[256], s_tab_g[256];
-    __shared__ float4 s_surv[LAYOUT == 0 ? kFuseTile : 1];     // surviving points (float4 layout)
-    __shared__ uint32_t s_idx[LAYOUT == 0 ? 1 : kFuseTile];    // or their index in the tile (float64 layout)
-    __shared__ uint32_t s_nsurv;
-    __shared__ TouchList<MODE == 0 ? kFuseTile : 1> tl;
+    __shared__ FrameParams s_fp;
+    __shared__ int s_box[4];
 
-    int fi = 0;
-    while (fi + 1 < bp.n_frames && blockIdx.x >= bp.f[fi + 1].block_begin) ++fi;
-    const BatchFrame& F = bp.f[fi];
-    const FrameParams& fp = F.fp;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    Entry* const queue = s_queue[warp];
+    const uint32_t low = (1u << gp.tag_shift) - 1u;
 
     build_color_tables(gp, s_tab_r, s_tab_g);
-    if (threadIdx.x == 0) {
-        s_nsurv = 0;
-        tl.n = 0;
+    if (MODE == 0 && threadIdx.x == 0) {
+        s_box[0] = 0x7fffffff; s_box[1] = -1; s_box[2] = 0x7fffffff; s_box[3] = -1;
     }
-    __syncthreads();
 
-    // ---- phase 1: stream + float32 pre-cull + compaction
-    const int64_t base = (int64_t)(blockIdx.x - F.block_begin) * kFuseTile;
-    const int lane = threadIdx.x & 31;
-    if (LAYOUT == 0) {
-        const float4* p4 = reinterpret_cast<const float4*>(F.pts);
-        float4 p[kFusePts];
-#pragma unroll
-        for (int j = 0; j < kFusePts; ++j) {
-            const int64_t k = base + j * kThreads + threadIdx.x;
-            p[j] = (k < F.n) ? __ldcs(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur = -1;          // frame whose constants are in s_fp
+    uint32_t qn = 0;       // entries on this warp's stack (warp-uniform)
+    int bx0 = 0x7fffffff, bx1 = -1, by0 = 0x7fffffff, by1 = -1;
+
+    // frame-dependent values a lane keeps in registers
+    const void* f_pts = nullptr;
+    const uint8_t* f_image = nullptr;
+    uint32_t* f_mask = nullptr;
+    int64_t f_n = 0, f_ld = 0;
+    uint32_t f_tagword = 0;
+    bool f_words = false;   // label image can be read with aligned 32-bit loads
+
+    // ---- one batch of <= 32 stacked survivors, one per lane
+    auto drain_batch = [&](uint32_t count) {
+        const uint32_t first = qn - count;
+        qn = first;
+        if ((uint32_t)lane >= count) return;
+        double x, y, z;
+        float it;
+        if (LAYOUT == 0) {
+            const float4 w = *reinterpret_cast<const float4*>(&queue[first + lane]);
+            x = (double)w.x; y = (double)w.y; z = (double)w.z; it = w.w;
+        } else {
+            const double* pd = reinterpret_cast<const double*>(f_pts);
+            const int64_t k = (int64_t)*reinterpret_cast<const uint32_t*>(&queue[first + lane]);
+            x = __ldg(pd + k); y = __ldg(pd + f_ld + k); z = __ldg(pd + 2 * f_ld + k);
+            // the boost test compares the float64 intensity with 2 and 14; rounding to float32 could move a
+            // value across them, so map the double onto a float on the same side (NaN: neither)
+            const double itd = __ldg(pd + 3 * f_ld + k);
+            it = (itd < 2.0) ? 0.0f : ((itd > 14.0) ? 15.0f : 8.0f);
         }
-#pragma unroll
-        for (int j = 0; j < kFusePts; ++j) {
-            const int64_t k = base + j * kThreads + threadIdx.x;
-            const bool pass = (k < F.n) && precull_pass(fp, p[j].x, p[j].y, p[j].z);
-            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-            if (ballot) {
-                const int leader = __ffs(ballot) - 1;
-                uint32_t slot = 0;
-                if (lane == leader) slot = atomicAdd(&s_nsurv, (uint32_t)__popc(ballot));
-                slot = __shfl_sync(0xffffffffu, slot, leader);
-                if (pass) s_surv[slot + __popc(ballot & ((1u << lane) - 1u))] = p[j];
+        int iu, iv;
+        if (!project_point(s_fp, x, y, z, iu, iv)) return;
+        const uint32_t off = 3u * ((uint32_t)iv * (uint32_t)s_fp.img_w + (uint32_t)iu);
+        uint32_t r, g;
+        if (f_words) {
+            // R and G sit in one aligned 32-bit word unless R is its last byte
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(f_image) + off;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+            const uint32_t w0 = __ldg(wp);
+            r = (w0 >> sh) & 0xffu;
+            g = (sh == 24u) ? (__ldg(wp + 1) & 0xffu) : ((w0 >> (sh + 8u)) & 0xffu);
+        } else {
+            r = __ldg(f_image + off);
+            g = __ldg(f_image + off + 1);
+        }
+        const uint32_t bits = class_bits_lut(gp, s_tab_r, s_tab_g, (uint8_t)r, (uint8_t)g, it);
+        if (!bits) return;
+        int cx, cy;
+        if (!cell_xy(gp, x, y, cx, cy)) return;
+        const uint32_t cell = (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy;
+        const uint32_t prev = tagged_or(f_mask + cell, f_tagword, bits, low);
+        if (MODE == 0) {
+            bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
+        } else {
+            uint32_t fresh = bits & ~prev;
+            double* row = map + (size_t)cell * gp.c;
+            if (fresh >> gp.c) {  // boost bit newly set: +2 on the lane class (src/mapping_replay.py:294)
+                atomicAdd(row + gp.lane, 2.0);
+                fresh &= (1u << gp.c) - 1u;
+            }
+            while (fresh) {
+                const int i = __ffs(fresh) - 1;
+                fresh &= fresh - 1u;
+                atomicAdd(row + i, 1.0);
             }
         }
-    } else {
-        const double* pd = reinterpret_cast<const double*>(F.pts);
-#pragma unroll 2
-        for (int j = 0; j < kFusePts; ++j) {
-            const int64_t k = base + j * kThreads + threadIdx.x;
-            bool pass = false;
-            if (k < F.n) pass = precull_pass(fp, (float)__ldg(pd + k), (float)__ldg(pd + F.ld + k), (float)__ldg(pd + 2 * F.ld + k));
-            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-            if (ballot) {
-                const int leader = __ffs(ballot) - 1;
-                uint32_t slot = 0;
-                if (lane == leader) slot = atomicAdd(&s_nsurv, (uint32_t)__popc(ballot));
-                slot = __shfl_sync(0xffffffffu, slot, leader);
-                if (pass) s_idx[slot + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)(j * kThreads + threadIdx.x);
-            }
-        }
-    }
-    __syncthreads();
+    };
 
-    // ---- phase 2: exact path on the dense survivor list
-    const uint32_t nsurv = s_nsurv;
-    for (uint32_t s0 = 0; s0 < nsurv; s0 += kThreads) {
-        const uint32_t s = s0 + threadIdx.x;
-        bool first = false;
-        uint32_t cell = 0;
-        if (s < nsurv) {
-            double x, y, z;
-            float it;
+    auto flush_box = [&]() {  // MODE 0: fold the lanes' boxes into the block's
+        if (MODE != 0) return;
+        if (bx1 >= bx0) {
+            atomicMin(&s_box[0], bx0); atomicMax(&s_box[1], bx1);
+            atomicMin(&s_box[2], by0); atomicMax(&s_box[3], by1);
+        }
+    };
+
+    for (uint32_t unit = blockIdx.x; unit < bp.n_units; unit += gridDim.x) {
+        int fi = cur < 0 ? 0 : cur;
+        while (fi + 1 < bp.n_frames && unit >= bp.f[fi + 1].unit_begin) ++fi;
+        if (fi != cur) {  // block-uniform: units are frame-major and every warp sees the same sequence
+            while (qn) {  // the old frame's leftovers still need the old constants
+                drain_batch(qn < 32u ? qn : 32u);
+                __syncwarp();
+            }
+            __syncthreads();
+            const BatchFrame& F = bp.f[fi];
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&F.fp);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(&s_fp);
+            for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x) dst[i] = src[i];
+            f_pts = F.pts; f_image = F.image; f_mask = F.mask; f_n = F.n; f_ld = F.ld; f_tagword = F.tagword;
+            f_words = ((reinterpret_cast<uintptr_t>(F.image) & 3u) == 0u) &&
+                      (((int64_t)F.fp.img_w * F.fp.img_h * 3) % 4 == 0);
+            cur = fi;
+            __syncthreads();
+        }
+        CullConsts kc;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) kc.m[i] = s_fp.Mf[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            kc.ea[i] = s_fp.Ea[i];
+            kc.eb[i] = s_fp.Eb[i];
+        }
+        kc.range_hi = s_fp.range_hi;
+        kc.wf = s_fp.img_wf;
+        kc.hf = s_fp.img_hf;
+
+        const int64_t wbase = (int64_t)(unit - bp.f[fi].unit_begin) * kUnitPts + (int64_t)warp * kWarpUnitPts;
+#pragma unroll 1
+        for (int rd = 0; rd < kRounds; ++rd) {
+            const int64_t rbase = wbase + (int64_t)rd * (32 * kRound);
+            if (rbase >= f_n) break;
             if (LAYOUT == 0) {
-                const float4 q = s_surv[s];
-                x = (double)q.x; y = (double)q.y; z = (double)q.z; it = q.w;
+                const float4* p4 = reinterpret_cast<const float4*>(f_pts);
+                float4 p[kRound];
+#pragma unroll
+                for (int c = 0; c < kRound; ++c) {
+                    const int64_t k = rbase + c * 32 + lane;
+                    p[c] = (k < f_n) ? __ldcs(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int c = 0; c < kRound; ++c) {
+                    const int64_t k = rbase + c * 32 + lane;
+                    const bool pass = (k < f_n) & precull_pass(kc, p[c].x, p[c].y, p[c].z);
+                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                    if (pass) *reinterpret_cast<float4*>(&queue[qn + __popc(ballot & lt_mask)]) = p[c];
+                    qn += __popc(ballot);
+                }
             } else {
-                const double* pd = reinterpret_cast<const double*>(F.pts);
-                const int64_t k = base + s_idx[s];
-                x = __ldg(pd + k); y = __ldg(pd + F.ld + k); z = __ldg(pd + 2 * F.ld + k);
-                // the boost test compares the float64 intensity with 2 and 14; rounding to float32 could move a
-                // value across them, so clamp the float onto the same side as the double
-                const double itd = __ldg(pd + 3 * F.ld + k);
-                it = (itd < 2.0) ? 0.0f : ((itd > 14.0) ? 15.0f : 8.0f);
-                if (itd != itd) it = 8.0f;  // NaN: neither < 2 nor > 14
-            }
-            int iu, iv;
-            if (project_point(fp, x, y, z, iu, iv)) {
-                const uint8_t* px = F.image + 3 * ((int64_t)iv * fp.img_w + iu);
-                const uint8_t r = __ldg(px), g = __ldg(px + 1);
-                const uint32_t bits = class_bits_lut(gp, s_tab_r, s_tab_g, r, g, it);
-                if (bits && cell_of(gp, x, y, cell)) {
-                    const uint32_t prev = tagged_or(F.mask + cell, F.tagword, bits, gp.tag_shift);
-                    if (MODE == 0) {
-                        first = (prev == 0u);
-                    } else {
-                        uint32_t fresh = bits & ~prev;
-                        double* row = map + (size_t)cell * gp.c;
-                        if (fresh >> gp.c) {  // boost bit newly set: +2 on the lane class (src/mapping_replay.py:294)
-                            atomicAdd(row + gp.lane, 2.0);
-                            fresh &= (1u << gp.c) - 1u;
-                        }
-                        while (fresh) {
-                            const int i = __ffs(fresh) - 1;
-                            fresh &= fresh - 1u;
-                            atomicAdd(row + i, 1.0);
-                        }
-                    }
+                const double* pd = reinterpret_cast<const double*>(f_pts);
+#pragma unroll 2
+                for (int c = 0; c < kRound; ++c) {
+                    const int64_t k = rbase + c * 32 + lane;
+                    bool pass = false;
+                    if (k < f_n)
+                        pass = precull_pass(kc, (float)__ldg(pd + k), (float)__ldg(pd + f_ld + k), (float)__ldg(pd + 2 * f_ld + k));
+                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                    if (pass) *reinterpret_cast<uint32_t*>(&queue[qn + __popc(ballot & lt_mask)]) = (uint32_t)k;
+                    qn += __popc(ballot);
                 }
             }
+            __syncwarp();
+            while (qn >= 32u) {
+                drain_batch(32u);
+                __syncwarp();
+            }
         }
-        if (MODE == 0) touch_push(tl, first, cell);
     }
-    if (MODE == 0) touch_flush(tl, touched, counter);
+    while (qn) {
+        drain_batch(qn < 32u ? qn : 32u);
+        __syncwarp();
+    }
+    if (MODE == 0) {
+        flush_box();
+        __syncthreads();
+        if (threadIdx.x == 0 && s_box[1] >= s_box[0]) {
+            atomicMin(&box->x0, s_box[0]); atomicMax(&box->x1, s_box[1]);
+            atomicMin(&box->y0, s_box[2]); atomicMax(&box->y1, s_box[3]);
+        }
+    }
 }
 
-// Parity kernel for update_map (src/mapping_replay.py:261-277,:288-290): same scatter as k_fuse MODE 0, but from
+// Parity kernel for update_map (src/mapping_replay.py:261-277,:288-290): the scatter half of the ordered update from
 // an already projected cloud (4, M) float64 + its (3, M) RGB labels.
-template <int PTS>
 __global__ void __launch_bounds__(kThreads)
 k_update_scatter(const double* __restrict__ pcd, int64_t ld, const uint8_t* __restrict__ label, int64_t ldl,
                  int64_t m, const __grid_constant__ GridParams gp, uint32_t* __restrict__ mask, uint32_t tagword,
-                 uint32_t* __restrict__ touched, uint32_t* __restrict__ counter) {
-    __shared__ TouchList<kThreads * PTS> tl;
-    if (threadIdx.x == 0) tl.n = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * (kThreads * PTS);
-#pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        const int64_t k = base + j * kThreads + threadIdx.x;
-        bool first = false;
-        uint32_t cell = 0;
-        if (k < m) {
-            const uint32_t bits = class_bits(gp, label[k], label[ldl + k], pcd[3 * ld + k]);
-            if (bits && cell_of(gp, pcd[k], pcd[ld + k], cell))
-                first = (tagged_or(mask + cell, tagword, bits, gp.tag_shift) == 0u);
-        }
-        touch_push(tl, first, cell);
+                 FrameBox* __restrict__ box) {
+    __shared__ int s_box[4];
+    if (threadIdx.x == 0) {
+        s_box[0] = 0x7fffffff; s_box[1] = -1; s_box[2] = 0x7fffffff; s_box[3] = -1;
     }
-    touch_flush(tl, touched, counter);
+    __syncthreads();
+    const uint32_t low = (1u << gp.tag_shift) - 1u;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t bits = class_bits(gp, label[k], label[ldl + k], pcd[3 * ld + k]);
+        int cx, cy;
+        if (bits && cell_xy(gp, pcd[k], pcd[ld + k], cx, cy)) {
+            tagged_or(mask + (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy, tagword, bits, low);
+            atomicMin(&s_box[0], cx); atomicMax(&s_box[1], cx);
+            atomicMin(&s_box[2], cy); atomicMax(&s_box[3], cy);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_box[1] >= s_box[0]) {
+        atomicMin(&box->x0, s_box[0]); atomicMax(&box->x1, s_box[1]);
+        atomicMin(&box->y0, s_box[2]); atomicMax(&box->y1, s_box[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3b (deterministic path): apply the frame's cell masks to the grid, classes in ascending order.
-// Replaces the "+=" statements at src/mapping_replay.py:281 and :294 bit for bit, any update matrix.
-// One thread per touched cell: touched[] is read coalesced, then mask word and the C-element grid row are
-// independent random accesses, so ~all touched cells of a frame are in flight at once (the first version
-// walked 8-lane groups through a serial load chain and took 100 us for 137 k cells).
-// `counter` is this frame's touched count; `next_counter` (other half of the double buffer) is zeroed.
+// K3b (ordered update): sweep the frame's bounding box of the mask slot; every cell whose word carries this
+// frame's tag gets the matrix columns of its classes added in ascending class order, then the lane boost:
+// the "+=" statements at src/mapping_replay.py:281 and :294 bit for bit, for any update matrix.
+// The box rows are contiguous in memory (axis 1), so the 4-byte mask reads are coalesced; the window of a
+// 100 m frustum at 0.1 m is ~1.2 M words = 5 MB, cheaper than maintaining a list of touched cells with
+// contended atomics.  `box` is this frame's window, `next_box` (other half of the double buffer) is reset.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_apply(double* __restrict__ map, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ touched,
-        const uint32_t* __restrict__ counter, uint32_t* __restrict__ next_counter,
-        const double* __restrict__ cm, int c, int lane_cls) {
+k_apply(double* __restrict__ map, const uint32_t* __restrict__ mask, uint32_t tagword, int tag_shift,
+        FrameBox* __restrict__ box, FrameBox* __restrict__ next_box, const double* __restrict__ cm, int c, int lane_cls, int mw) {
     extern __shared__ double s_cm[];  // C x C, transposed: s_cm[i * c + j] = cm[j * c + i] (column i contiguous)
+    __shared__ uint32_t s_count;
     for (int e = threadIdx.x; e < c * c; e += blockDim.x) s_cm[(e % c) * c + e / c] = cm[e];
+    if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) *next_counter = 0u;
-    const uint32_t count = *counter;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        next_box->x0 = 0x7fffffff; next_box->x1 = -1; next_box->y0 = 0x7fffffff; next_box->y1 = -1;
+        next_box->touched = 0;
+    }
+    const int x0 = box->x0, x1 = box->x1, y0 = box->y0, y1 = box->y1;
+    if (x1 < x0) return;
+    const uint32_t ncols = (uint32_t)(y1 - y0 + 1);
+    const uint64_t total = (uint64_t)(x1 - x0 + 1) * ncols;
     const uint32_t boost = 1u << c;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
-        const uint32_t cell = touched[t];
-        const uint32_t bits = __ldcg(mask + cell);
+    const uint32_t tag = tagword >> tag_shift;
+    uint32_t mine = 0;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t rr = (uint32_t)(t / ncols), cc = (uint32_t)(t - (uint64_t)rr * ncols);
+        const uint32_t cell = (uint32_t)(x0 + (int)rr) * (uint32_t)mw + (uint32_t)(y0 + (int)cc);
+        const uint32_t word = __ldcg(mask + cell);
+        if ((word >> tag_shift) != tag) continue;
+        ++mine;
         double* row = map + (size_t)cell * c;
         for (int j0 = 0; j0 < c; j0 += 8) {
             double acc[8];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) acc[jj] = (j0 + jj < c) ? row[j0 + jj] : 0.0;
             for (int i = 0; i < c; ++i) {
-                if (!((bits >> i) & 1u)) continue;
+                if (!((word >> i) & 1u)) continue;
                 const double* col = s_cm + i * c + j0;
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj)
                     if (j0 + jj < c) acc[jj] = __dadd_rn(acc[jj], col[jj]);
-                if (i == lane_cls && (bits & boost) && i >= j0 && i < j0 + 8) {
+                if (i == lane_cls && (word & boost) && i >= j0 && i < j0 + 8) {
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj)
                         if (j0 + jj == i) acc[jj] = __dadd_rn(acc[jj], 2.0);
@@ -282,6 +356,9 @@ k_apply(double* __restrict__ map, const uint32_t* __restrict__ mask, const uint3
                 if (j0 + jj < c) row[j0 + jj] = acc[jj];
         }
     }
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) atomicAdd(&box->touched, s_count);
 }
 
 // ------------------------------------------------------------------------------------------------
