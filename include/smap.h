@@ -33,7 +33,7 @@ extern "C" {
 #endif
 
 #define SMAP_ABI_VERSION 1
-#define SMAP_MAX_CLASSES 30 /* C class bits + 1 intensity-boost bit + >= 1 frame-tag bit in a 32-bit cell mask */
+#define SMAP_MAX_CLASSES 31 /* C class bits + 1 intensity-boost bit in a 32-bit cell mask */
 #define SMAP_MAX_CAMERAS 8
 
 enum {
@@ -57,7 +57,7 @@ typedef struct smap_handle smap_handle;
 typedef struct smap_config {
     int32_t map_height;      /* int((B[0][1]-B[0][0]) / res) */
     int32_t map_width;       /* int((B[1][1]-B[1][0]) / res) */
-    int32_t num_classes;     /* len(cfg.LABELS), 1..30 */
+    int32_t num_classes;     /* len(cfg.LABELS), 1..31 */
     int32_t use_intensity;   /* cfg.MAPPING.PCD.USE_INTENSITY */
     int32_t lane_index;      /* index of the class named "lane", -1 if none (src/mapping_replay.py:288) */
     int32_t device;          /* CUDA device ordinal */
@@ -89,7 +89,7 @@ typedef struct smap_frame {
 typedef struct smap_stats {
     int64_t frames;          /* frames integrated since create / clear */
     int64_t points;          /* points read */
-    int64_t touched_cells;   /* K of the last deterministic frame (distinct cells updated) */
+    int64_t touched_cells;   /* (cell, frame) pairs updated by the most recent launch: K for a single frame */
     int64_t kernel_launches; /* kernels launched by this handle */
 } smap_stats;
 
@@ -130,21 +130,16 @@ SMAP_API int smap_update(smap_handle *h, double *map_dev, const double *pcd_dev,
                 int64_t ldl, int64_t m, void *stream);
 
 /* ---- fused path: project_pcd + update_map of ONE frame, nothing materialised -------------------
- * (src/mapping_replay.py:184-192 loop body).  Bit-exact with the reference in both update modes:
- *   - count update (update matrix == np.eye(C)): one kernel; every newly set (cell, class) of the frame adds
- *     1.0 (and the lane boost 2.0) with a float64 atomic -- sums of small integers, exact in any order as long
- *     as the grid holds integer-valued counts (always true for a grid built by this path);
- *   - any other matrix (log-likelihood update), or after smap_set_deterministic(h, 1): the frame's touched
- *     cells are listed and a second kernel adds the matrix columns in ascending class order. */
+ * (src/mapping_replay.py:184-192 loop body).  Bit-exact with the reference for any update matrix (count or
+ * log-likelihood): a streaming kernel ORs the frame's class bits into a per-frame cell mask (the per-frame
+ * (cell, class) de-duplication), a second kernel adds the matrix columns to the touched cells in ascending
+ * class order and clears the mask. */
 SMAP_API int smap_integrate(smap_handle *h, const smap_frame *frame, void *stream);
 
-/* Same rule for n_frames frames in order.  With the count update up to 16 frames share one launch, each
- * de-duplicated in its own mask slot; frames of one call must share a point layout. */
+/* Same rule for n_frames frames IN ORDER.  Up to 16 frames share one pair of launches: each frame scatters
+ * into its own mask slot and the apply kernel replays the slots in frame order per cell, so the result is
+ * bit-identical to n_frames calls of smap_integrate.  Frames of one call must share a point layout. */
 SMAP_API int smap_integrate_batch(smap_handle *h, const smap_frame *frames_host, int n_frames, void *stream);
-
-/* on != 0: always use the ordered two-kernel update (needed only when the grid may hold non-integers
- * while the update matrix is the identity). */
-SMAP_API int smap_set_deterministic(smap_handle *h, int on);
 
 /* Same as smap_integrate with HOST buffers: points (layout as in frame) and image are copied to the
  * device through the handle's staging ring inside the call (async on `stream`; pass pinned memory

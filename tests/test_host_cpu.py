@@ -51,7 +51,7 @@ def test_bad_arguments_are_reported_not_thrown():
     cfg.map_height, cfg.map_width, cfg.num_classes, cfg.resolution = 0, 10, 5, 0.1
     assert lib.smap_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"empty grid" in lib.smap_last_error()
-    cfg.map_height, cfg.num_classes = 10, 31
+    cfg.map_height, cfg.num_classes = 10, 32
     assert lib.smap_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     with pytest.raises(_native.SmapError):
         _native.check(lib.smap_render(None, 4, 4, 3, None, None, 0, None))

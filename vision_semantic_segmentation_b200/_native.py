@@ -12,13 +12,13 @@ LIB_PATH = os.environ.get("SMAP_LIB_PATH") or os.path.join(_HERE, "csrc", "libsm
 
 SMAP_PTS_F32X4 = 0
 SMAP_PTS_F64_SOA = 1
-SMAP_MAX_CLASSES = 30
+SMAP_MAX_CLASSES = 31
 SMAP_MAX_CAMERAS = 8
 
 EXPORTS = [
     "smap_abi_version", "smap_last_error", "smap_device_count", "smap_device_info", "smap_create",
     "smap_destroy", "smap_set_camera", "smap_set_classes", "smap_project", "smap_update", "smap_integrate",
-    "smap_integrate_batch", "smap_set_deterministic", "smap_integrate_host", "smap_apply_filter", "smap_render", "smap_filter_render",
+    "smap_integrate_batch", "smap_integrate_host", "smap_apply_filter", "smap_render", "smap_filter_render",
     "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_download", "smap_upload", "smap_get_stats",
 ]
 
@@ -91,8 +91,6 @@ def load():
     L.smap_integrate.argtypes = [vp, ctypes.POINTER(SmapFrame), vp]
     L.smap_integrate_batch.restype = i32
     L.smap_integrate_batch.argtypes = [vp, ctypes.POINTER(SmapFrame), i32, vp]
-    L.smap_set_deterministic.restype = i32
-    L.smap_set_deterministic.argtypes = [vp, i32]
     L.smap_integrate_host.restype = i32
     L.smap_integrate_host.argtypes = [vp, ctypes.POINTER(SmapFrame), vp]
     L.smap_apply_filter.restype = i32

@@ -1,6 +1,7 @@
 // C ABI (include/smap.h) of the B200 semantic-mapping path: host-side launch logic.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <cmath>
+#include <cfloat>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -51,15 +52,12 @@ struct smap_handle {
     double* map = nullptr;
     bool own_map = false;
     int64_t cells = 0;
-    // epoch-tagged cell masks: n_slots slots of `cells` words (slot 0 serves the single-frame paths)
+    // per-frame cell masks: n_slots slots of `cells` words, all zero between launches
     uint32_t* mask = nullptr;
     int n_slots = 0;
-    uint32_t tag = 0;      // last frame tag handed out (0 = "never written")
-    uint32_t tag_max = 0;  // largest tag that fits above tag_shift
-    bool identity_cm = false;   // update matrix is exactly np.eye(C): the count update
-    bool deterministic = false; // force the touched-list + k_apply path even for the count update
-    // ordered (two-kernel) update: double-buffered bounding box of the cells a frame touched
-    FrameBox* boxes = nullptr;     // [2]
+    // double-buffered per-slot bounding boxes + touched counters (k_stream writes [parity], k_apply resets [parity^1])
+    FrameBox* boxes = nullptr;                // [2][kMaxBatch]
+    unsigned long long* touched = nullptr;    // [2]
     int parity = 0;
     int sm_count = 148;
     // class tables
@@ -127,6 +125,31 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
         fp.range_hi = (float)fp.range_max * (1.0f + kCullSlack);
         fp.img_wf = (float)f->image_width;
         fp.img_hf = (float)f->image_height;
+        // certified fast projection: M = P * T and the error bounds of smap_device.cuh (fast_project)
+        const double u64 = 64.0 * 1.1102230246251565e-16;  // 64 * 2^-53
+        double e[3];
+        for (int r = 0; r < 3; ++r) {
+            double axyz = 0.0, aw = 0.0;
+            for (int j = 0; j < 4; ++j) {
+                double acc = 0.0, aabs = 0.0;
+                for (int k = 0; k < 4; ++k) {
+                    acc += fp.P[4 * r + k] * Tm[4 * k + j];
+                    aabs += fabs(fp.P[4 * r + k]) * fabs(Tm[4 * k + j]);
+                }
+                fp.M[4 * r + j] = acc;
+                if (j < 3) axyz = fmax(axyz, aabs); else aw = aabs;
+            }
+            e[r] = u64 * (axyz * 3.0 * kCoordBound + aw);
+        }
+        const double umax = (double)(f->image_width > f->image_height ? f->image_width : f->image_height) + 2.0;
+        fp.e3x4 = 4.0 * e[2];
+        fp.cgu = (4.0 / 3.0) * (e[0] + umax * e[2]) * (1.0 + 1e-9);
+        fp.cgv = (4.0 / 3.0) * (e[1] + umax * e[2]) * (1.0 + 1e-9);
+        fp.c0 = umax * 5.6843418860808015e-14;  // 2^-44
+        fp.img_wd = (double)f->image_width;
+        fp.img_hd = (double)f->image_height;
+        // non-finite bounds (absurd matrices) switch the fast path off: q2 > inf never holds
+        if (!(fp.cgu == fp.cgu) || !(fp.cgv == fp.cgv) || !(fp.e3x4 == fp.e3x4)) fp.e3x4 = INFINITY;
     }
     fp.has_T = f->has_transform ? 1 : 0;
     fp.img_w = f->image_width;
@@ -169,41 +192,36 @@ int ensure_slots(smap_handle* h, int want) {
     return SMAP_OK;
 }
 
-// Next frame tag; when the tag field is exhausted every slot is wiped and the count restarts.
-int next_tag(smap_handle* h, cudaStream_t st, uint32_t* tagword) {
-    if (h->tag >= h->tag_max) {
-        CK(cudaMemsetAsync(h->mask, 0, sizeof(uint32_t) * (size_t)h->cells * h->n_slots, st));
-        h->tag = 0;
-    }
-    h->tag += 1;
-    *tagword = h->tag << h->gp.tag_shift;
-    return SMAP_OK;
-}
-
-// K3b launch: apply the masks of the frame whose box is boxes[parity]; flips parity.
-int launch_apply(smap_handle* h, double* map, uint32_t tagword, cudaStream_t st) {
+// K3b launch: ordered apply of the `n_slots_used` mask slots whose boxes are boxes[parity]; flips parity.
+int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st) {
     const int c = h->cfg.num_classes;
+    ApplyParams ap;
+    memset(&ap, 0, sizeof ap);
+    ap.n_frames = n_slots_used;
+    for (int i = 0; i < n_slots_used; ++i) ap.mask[i] = h->mask + (size_t)i * h->cells;
     const size_t smem = sizeof(double) * c * c;
-    k_apply<<<h->sm_count * 8, kThreads, smem, st>>>(map, h->mask, tagword, h->gp.tag_shift, h->boxes + h->parity,
-                                                    h->boxes + (h->parity ^ 1), h->cm_dev, c, h->cfg.lane_index,
-                                                    h->cfg.map_width);
+    FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch;
+    FrameBox* next_boxes = h->boxes + (size_t)(h->parity ^ 1) * kMaxBatch;
+    unsigned long long* tt = h->touched + h->parity;
+    unsigned long long* ntt = h->touched + (h->parity ^ 1);
+    const unsigned grid = (unsigned)h->sm_count * 8;
+    const int lane = h->cfg.lane_index, mw = h->cfg.map_width;
+    if (c <= 8) k_apply<1><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw);
+    else if (c <= 16) k_apply<2><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw);
+    else if (c <= 24) k_apply<3><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw);
+    else k_apply<4><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw);
     CK(cudaGetLastError());
     h->parity ^= 1;
     h->stats.kernel_launches += 1;
     return SMAP_OK;
 }
 
-// One launch of k_stream over up to kMaxBatch frames (already validated; fps[i] filled).
-// mode 0: ordered update, ONE frame, masks + bounding box only (caller launches k_apply with *tagword_out)
-// mode 1: count update with atomics, frame i uses mask slot i
-int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, int mode,
-                  cudaStream_t st, uint32_t* tagword_out) {
-    static BatchParams bp;  // 7 KB: keep it off the stack; handles are single-threaded per the ABI contract
+// One launch of k_stream over up to kMaxBatch frames (already validated; fps[i] filled); frame i of the
+// non-empty ones scatters into mask slot i.  Returns the number of slots used in *slots_used.
+int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, cudaStream_t st,
+                  int* slots_used) {
+    static BatchParams bp;  // ~8 KB: keep it off the stack; handles are single-threaded per the ABI contract
     memset(&bp, 0, sizeof bp);
-    uint32_t tagword = 0;
-    int rc = next_tag(h, st, &tagword);
-    if (rc) return rc;
-    if (tagword_out) *tagword_out = tagword;
     uint32_t units = 0;
     const int layout = frames[0].layout;
     int used = 0;
@@ -214,28 +232,23 @@ int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* f
         b.fp = fps[i];
         b.pts = frames[i].points_dev;
         b.image = frames[i].image_dev;
-        b.mask = h->mask + (size_t)(mode == 1 ? used : 0) * h->cells;
+        b.mask = h->mask + (size_t)used * h->cells;
         b.n = frames[i].n_points;
         b.ld = frames[i].ld;
-        b.tagword = tagword;
         b.unit_begin = units;
         units += (uint32_t)ceil_div(frames[i].n_points, kUnitPts);
         ++used;
     }
+    *slots_used = used;
     if (used == 0) return SMAP_OK;
     bp.n_frames = used;
     bp.n_units = units;
     // persistent grid: as many blocks as stay resident, never more than there are units
     uint32_t grid = (uint32_t)h->sm_count * SMAP_STREAM_MINB;
     if (grid > units) grid = units;
-    FrameBox* box = h->boxes + h->parity;
-    if (layout == SMAP_PTS_F32X4) {
-        if (mode == 0) k_stream<SMAP_PTS_F32X4, 0><<<grid, kThreads, 0, st>>>(bp, h->gp, h->map, box);
-        else k_stream<SMAP_PTS_F32X4, 1><<<grid, kThreads, 0, st>>>(bp, h->gp, h->map, box);
-    } else {
-        if (mode == 0) k_stream<SMAP_PTS_F64_SOA, 0><<<grid, kThreads, 0, st>>>(bp, h->gp, h->map, box);
-        else k_stream<SMAP_PTS_F64_SOA, 1><<<grid, kThreads, 0, st>>>(bp, h->gp, h->map, box);
-    }
+    FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch;
+    if (layout == SMAP_PTS_F32X4) k_stream<SMAP_PTS_F32X4><<<grid, kThreads, 0, st>>>(bp, h->gp, boxes);
+    else k_stream<SMAP_PTS_F64_SOA><<<grid, kThreads, 0, st>>>(bp, h->gp, boxes);
     CK(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return SMAP_OK;
@@ -299,7 +312,7 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     *out = nullptr;
     if (cfg->map_height <= 0 || cfg->map_width <= 0) return fail(SMAP_ERR_INVALID, "empty grid");
     if (cfg->num_classes < 1 || cfg->num_classes > SMAP_MAX_CLASSES)
-        return fail(SMAP_ERR_INVALID, "num_classes must be in 1..30");
+        return fail(SMAP_ERR_INVALID, "num_classes must be in 1..31");
     if ((int64_t)cfg->map_height * cfg->map_width >= (int64_t)1 << 31)
         return fail(SMAP_ERR_INVALID, "grid has more than 2^31 cells");
     if (cfg->lane_index >= cfg->num_classes) return fail(SMAP_ERR_INVALID, "lane_index out of range");
@@ -324,8 +337,7 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     g.mh = cfg->map_height; g.mw = cfg->map_width; g.c = cfg->num_classes;
     g.lane = cfg->lane_index < 0 ? -1 : cfg->lane_index;
     g.use_intensity = cfg->use_intensity ? 1 : 0;
-    g.tag_shift = cfg->num_classes + 1;
-    h->tag_max = (g.tag_shift >= 32) ? 0u : ((1u << (32 - g.tag_shift)) - 1u);
+    g.rinv = 1.0 / cfg->resolution;
     const size_t map_bytes = sizeof(double) * (size_t)h->cells * cfg->num_classes;
     cudaError_t e = cudaSuccess;
     if (cfg->map_dev) {
@@ -337,15 +349,14 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->cells);
     if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->cells);
     if (e == cudaSuccess) h->n_slots = 1;
-    if (e == cudaSuccess) e = cudaMalloc(&h->boxes, sizeof(FrameBox) * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&h->boxes, sizeof(FrameBox) * 2 * kMaxBatch);
     if (e == cudaSuccess) {
-        FrameBox init[2];
-        for (int i = 0; i < 2; ++i) {
-            init[i].x0 = 0x7fffffff; init[i].x1 = -1; init[i].y0 = 0x7fffffff; init[i].y1 = -1;
-            init[i].touched = 0; init[i].pad[0] = init[i].pad[1] = init[i].pad[2] = 0;
-        }
+        FrameBox init[2 * kMaxBatch];
+        for (int i = 0; i < 2 * kMaxBatch; ++i) { init[i].x0 = 0x7fffffff; init[i].x1 = -1; init[i].y0 = 0x7fffffff; init[i].y1 = -1; }
         e = cudaMemcpy(h->boxes, init, sizeof init, cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess) e = cudaMalloc(&h->touched, sizeof(unsigned long long) * 2);
+    if (e == cudaSuccess) e = cudaMemset(h->touched, 0, sizeof(unsigned long long) * 2);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     if (e == cudaSuccess) e = cudaMalloc(&h->cm_dev, sizeof(double) * SMAP_MAX_CLASSES * SMAP_MAX_CLASSES);
     if (e == cudaSuccess) e = cudaMalloc(&h->total_dev, sizeof(int64_t));
@@ -365,7 +376,7 @@ int smap_destroy(smap_handle* h) {
     DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
     if (h->own_map) cudaFree(h->map);
-    cudaFree(h->mask); cudaFree(h->boxes); cudaFree(h->cm_dev); cudaFree(h->total_dev);
+    cudaFree(h->mask); cudaFree(h->boxes); cudaFree(h->touched); cudaFree(h->cm_dev); cudaFree(h->total_dev);
     cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
     for (int i = 0; i < smap_handle::kStages; ++i) {
         cudaFree(h->stage_pts[i]);
@@ -396,10 +407,6 @@ int smap_set_classes(smap_handle* h, const uint8_t* colors_host, const double* c
     }
     CK(cudaDeviceSynchronize());  // a previous frame may still be reading the table
     CK(cudaMemcpy(h->cm_dev, cm_host, sizeof(double) * c * c, cudaMemcpyHostToDevice));
-    h->identity_cm = true;
-    for (int i = 0; i < c; ++i)
-        for (int j = 0; j < c; ++j)
-            if (cm_host[i * c + j] != (i == j ? 1.0 : 0.0)) h->identity_cm = false;
     h->classes_set = true;
     return SMAP_OK;
 }
@@ -449,22 +456,14 @@ int smap_update(smap_handle* h, double* map_dev, const double* pcd, int64_t ld, 
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (m == 0) return SMAP_OK;
-    uint32_t tagword = 0;
-    int rc = next_tag(h, st, &tagword);
-    if (rc) return rc;
     int64_t grid = ceil_div(m, kThreads);
     if (grid > (int64_t)h->sm_count * 16) grid = (int64_t)h->sm_count * 16;
-    k_update_scatter<<<(unsigned)grid, kThreads, 0, st>>>(pcd, ld, label, ldl, m, h->gp, h->mask, tagword, h->boxes + h->parity);
+    k_update_scatter<<<(unsigned)grid, kThreads, 0, st>>>(pcd, ld, label, ldl, m, h->gp, h->mask,
+                                                         h->boxes + (size_t)h->parity * kMaxBatch);
     CK(cudaGetLastError());
     h->stats.kernel_launches += 1;
     h->last_stream = st;
-    return launch_apply(h, map_dev ? map_dev : h->map, tagword, st);
-}
-
-int smap_set_deterministic(smap_handle* h, int on) {
-    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
-    h->deterministic = on != 0;
-    return SMAP_OK;
+    return launch_apply(h, map_dev ? map_dev : h->map, 1, st);
 }
 
 int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames, void* stream) {
@@ -474,28 +473,19 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     h->last_stream = st;
-    const bool atomic_counts = h->identity_cm && !h->deterministic;
     FrameParams fps[kMaxBatch];
     for (int begin = 0; begin < n_frames;) {
-        // the count update takes up to kMaxBatch frames per launch; the ordered (bit-exact) update one frame
-        const int chunk = atomic_counts ? ((n_frames - begin < kMaxBatch) ? n_frames - begin : kMaxBatch) : 1;
-        int64_t max_pts = 0;
+        const int chunk = (n_frames - begin < kMaxBatch) ? n_frames - begin : kMaxBatch;
         for (int i = 0; i < chunk; ++i) {
             int rc = fill_frame_params(h, frames + begin + i, fps[i]);
             if (rc) return rc;
             h->stats.frames += 1;
             h->stats.points += frames[begin + i].n_points;
-            if (frames[begin + i].n_points > max_pts) max_pts = frames[begin + i].n_points;
         }
-        int rc = SMAP_OK;
-        if (atomic_counts) {
-            rc = ensure_slots(h, chunk);
-            if (!rc) rc = launch_stream(h, frames + begin, fps, chunk, 1, st, nullptr);
-        } else if (max_pts > 0) {
-            uint32_t tagword = 0;
-            rc = launch_stream(h, frames + begin, fps, 1, 0, st, &tagword);
-            if (!rc) rc = launch_apply(h, h->map, tagword, st);
-        }
+        int rc = ensure_slots(h, chunk);
+        int used = 0;
+        if (!rc) rc = launch_stream(h, frames + begin, fps, chunk, st, &used);
+        if (!rc && used > 0) rc = launch_apply(h, h->map, used, st);
         if (rc) return rc;
         begin += chunk;
     }
@@ -632,10 +622,10 @@ int smap_get_stats(smap_handle* h, smap_stats* out) {
     if (!h || !out) return fail(SMAP_ERR_INVALID, "NULL argument");
     DeviceGuard guard(h->cfg.device);
     CK(cudaStreamSynchronize(h->last_stream));
-    // after launch_apply flipped the parity, the finished frame's box sits in boxes[parity ^ 1]
-    FrameBox b;
-    CK(cudaMemcpy(&b, h->boxes + (h->parity ^ 1), sizeof b, cudaMemcpyDeviceToHost));
-    h->stats.touched_cells = b.touched;
+    // after launch_apply flipped the parity, the finished launch's counter sits in touched[parity ^ 1]
+    unsigned long long k = 0;
+    CK(cudaMemcpy(&k, h->touched + (h->parity ^ 1), sizeof k, cudaMemcpyDeviceToHost));
+    h->stats.touched_cells = (int64_t)k;
     *out = h->stats;
     return SMAP_OK;
 }

@@ -12,21 +12,24 @@
 
 namespace smap {
 
-// Cell-mask word (32 bit):  [ tag : 31-C bits | boost : 1 bit (bit C) | class bits : C bits ].
-// The tag is the serial number of the frame that last wrote the word, so a mask never has to be cleared:
-// a word whose tag is not the current frame's reads as empty.
-constexpr int kMaxBatch = 16;  // frames per launch of the batched kernel (one mask slot each)
+constexpr int kMaxBatch = 16;  // frames per launch (one cell-mask slot each)
 
-// Per-frame projection constants (passed by value as a kernel parameter -> constant bank).
+// Per-frame projection constants (kernel parameter -> copied to shared memory once per block and frame).
 struct FrameParams {
     double T[16];      // world -> velodyne, row-major (src/mapping_replay.py:225-226)
     double P[12];      // camera projection (src/camera.py:28)
     double range_max;  // cfg.MAPPING.PCD.RANGE_MAX
-    // float32 pre-cull (see precull_pass): row 0 = T row 0 (velodyne x), rows 1..3 = rows of P*T (q0, q1, q2)
+    // ---- certified fast projection (see fast_project): M = P * T composed in double on the host
+    double M[12];      // rows q0, q1, q2
+    double e3x4;       // 4 * e[2]: the depth must exceed this for the fast path
+    double cgu, cgv;   // guard slopes: (4/3) (e_row + Umax e_depth)
+    double c0;         // guard offset: Umax * 2^-44
+    double img_wd, img_hd;
+    // ---- float32 pre-cull (see precull_pass): row 0 = T row 0 (velodyne x), rows 1..3 = rows of P*T
     float Mf[16];
-    float Ea[4];       // kSlack * max(|m_r0|, |m_r1|, |m_r2|)   error bound of row r = Ea[r] * (|x|+|y|+|z|) + Eb[r]
-    float Eb[4];       // kSlack * |m_r3|
-    float range_hi;    // range_max * (1 + kSlack)
+    float Ea[4];       // kCullSlack * max(|m_r0|, |m_r1|, |m_r2|)   error bound of row r = Ea[r] * (|x|+|y|+|z|) + Eb[r]
+    float Eb[4];       // kCullSlack * |m_r3|
+    float range_hi;    // range_max * (1 + kCullSlack)
     float img_wf, img_hf;
     int has_T;         // 0: cloud already in the velodyne frame
     int img_w, img_h;  // image.shape[1], image.shape[0]
@@ -34,16 +37,18 @@ struct FrameParams {
 };
 
 constexpr float kCullSlack = 1e-6f;
+constexpr double kCoordBound = 1048576.0;  // fast-path error bounds assume |x|, |y|, |z| < 2^20 m; beyond: exact path
 
 // Grid + class constants of a mapper handle.
 struct GridParams {
     double off_x, off_y;  // pcd origin w.r.t. map origin (src/mapping_replay.py:261)
     double bx0, by0;      // cfg.MAPPING.BOUNDARY[0][0], [1][0]
     double res;           // cfg.MAPPING.RESOLUTION
+    double rinv;          // fl(1 / res) for the certified fast cell index
     int mh, mw, c;
     int lane;             // class index named "lane", or -1
     int use_intensity;
-    int tag_shift;        // C + 1: first bit of the frame tag in a cell-mask word
+    int pad;
     uint8_t col_r[32];    // cfg.LABEL_COLORS[:, 0]
     uint8_t col_g[32];    // cfg.LABEL_COLORS[:, 1]   (blue is never compared, src/mapping_replay.py:276)
 };
@@ -162,6 +167,80 @@ __device__ __forceinline__ bool precull_pass(const CullConsts& k, float x, float
     const bool u_ok = (v[1] + e[1] > -q2hi) & (v[1] - e[1] < k.wf * q2hi);
     const bool v_ok = (v[2] + e[2] > -q2hi) & (v[2] - e[2] < k.hf * q2hi);
     return !finite | (range_ok & (!depth_pos | (u_ok & v_ok)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Certified fast path ("filtered predicate"): the integer results the reference produces -- keep / drop,
+// pixel (iu, iv), cell (cx, cy) -- are floors of real quantities; a cheaper evaluation with a rigorous error
+// bound yields the same integers unless the quantity sits within the bound of an integer.  Only then is the
+// reference's own rounding chain (project_point / cell_xy) evaluated.  Results are bit-identical by construction.
+//
+// Projection: q~ = M p with M = P T composed on the host (12 FMAs instead of 28).  Both q~ and the reference
+// chain q^ approximate the exact product within 8.1 u sum_j (|P||T|)_rj |x_j|, so |q~ - q^| <= e_r with
+// e_r = 64 u ((|P||T|)_r,xyz 3 B + (|P||T|)_r,w) for |x|,|y|,|z| < B (u = 2^-53; 4x safety factor).
+// With depth q~2 > 4 e_3:  |q~0/q~2 - q^0/q^2| <= (4/3)(e_1 + |u| e_3) / q~2.  The reciprocal (MUFU seed + two
+// Newton steps) is good to 2^-45, the reference's own division to 2^-53.  Guard:
+//      g = (cg * r + c0),  cg = (4/3)(e_row + Umax e_3),  c0 = Umax 2^-44,  Umax = max(W, H) + 2.
+// The range test uses the velodyne x of the reference chain itself (same four operations), so it is exact.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    r = __fma_rn(r, __fma_rn(-a, r, 1.0), r);
+    r = __fma_rn(r, __fma_rn(-a, r, 1.0), r);
+    return r;
+}
+
+// floor of t when t is farther than `guard` from every integer; returns false when it is not (or t is not in
+// (-2, limit + 1), where the magic-number rounding below is valid and the answer may matter).
+// Caller has already established that a t outside (-2, limit + 1) means "out of range" for certain.
+__device__ __forceinline__ bool certified_floor(double t, double guard, int& k) {
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+    const double rn = __dadd_rn(__dadd_rn(t, kMagic), -kMagic);
+    const double d = __dadd_rn(t, -rn);
+    k = __double2int_rn(rn) - (d < 0.0 ? 1 : 0);
+    return fabs(d) > guard;
+}
+
+// Fast version of project_point.  Returns 1 = kept (iu, iv valid), 0 = dropped, -1 = undecided (use project_point).
+__device__ __forceinline__ int fast_project(const FrameParams& f, double x, double y, double z, bool coords_ok,
+                                            int& iu, int& iv) {
+    const double vx = f.has_T ? dot4(f.T, x, y, z, 1.0) : x;   // the reference's own value
+    if (!((0.0 < vx) && (vx < f.range_max))) return 0;          // src/mapping_replay.py:235, exact
+    const double q0 = __fma_rn(f.M[0], x, __fma_rn(f.M[1], y, __fma_rn(f.M[2], z, f.M[3])));
+    const double q1 = __fma_rn(f.M[4], x, __fma_rn(f.M[5], y, __fma_rn(f.M[6], z, f.M[7])));
+    const double q2 = __fma_rn(f.M[8], x, __fma_rn(f.M[9], y, __fma_rn(f.M[10], z, f.M[11])));
+    if (!coords_ok || !(q2 > f.e3x4)) return -1;
+    const double r = fast_rcp(q2);
+    const double tu = __dmul_rn(q0, r), tv = __dmul_rn(q1, r);
+    const double gu = __fma_rn(r, f.cgu, f.c0), gv = __fma_rn(r, f.cgv, f.c0);
+    if (!(gu < 0.25 && gv < 0.25)) return -1;
+    // farther than 1 outside the image: dropped for certain (the guards are < 1/4)
+    if (!(tu > -2.0 && tu < f.img_wd + 1.0 && tv > -2.0 && tv < f.img_hd + 1.0)) return 0;
+    int ku, kv;
+    if (!certified_floor(tu, gu, ku) || !certified_floor(tv, gv, kv)) return -1;
+    if (ku < -1 || ku >= f.img_w || kv < -1 || kv >= f.img_h) return 0;
+    iu = ku < 0 ? 0 : ku;   // (-1, 0) truncates to 0
+    iv = kv < 0 ? 0 : kv;
+    return 1;
+}
+
+// Fast version of cell_xy: n = (x + off) - b0 exactly as the reference, then n * fl(1/res) instead of n / res
+// (they differ by at most 4 u |n / res|).  Returns 1 / 0 / -1 as above.
+__device__ __forceinline__ int fast_cell(const GridParams& g, double x, double y, int& cx, int& cy) {
+    const double nx = __dsub_rn(__dadd_rn(x, g.off_x), g.bx0);
+    const double ny = __dsub_rn(__dadd_rn(y, g.off_y), g.by0);
+    const double tx = __dmul_rn(nx, g.rinv), ty = __dmul_rn(ny, g.rinv);
+    if (!(tx > -2.0 && tx < (double)g.mh + 1.0 && ty > -2.0 && ty < (double)g.mw + 1.0))
+        return (tx == tx && ty == ty) ? 0 : -1;   // clearly off the grid; NaN: let the exact path decide
+    int kx, ky;
+    const double k50 = 8.8817841970012523e-16;  // 2^-50
+    if (!certified_floor(tx, __fma_rn(fabs(tx), k50, 1e-300), kx) || !certified_floor(ty, __fma_rn(fabs(ty), k50, 1e-300), ky))
+        return -1;
+    if (kx < -1 || kx >= g.mh || ky < -1 || ky >= g.mw) return 0;
+    cx = kx < 0 ? 0 : kx;
+    cy = ky < 0 ? 0 : ky;
+    return 1;
 }
 
 template <int LAYOUT>

@@ -11,25 +11,21 @@ namespace smap {
 constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------------------------------------
-// Epoch-tagged cell masks.
-// Cell-mask word:  [ tag | boost bit (bit C) | C class bits ].  The tag is the serial number of the frame
-// that last wrote the word; a word carrying an older tag is stale and reads as empty, so masks are never
-// cleared.  Tags only grow within a mask slot, hence atomicMax installs the new tag (dropping the stale
-// bits) without a compare-and-swap loop, and the following atomicOr returns what THIS frame had already
-// put there: one L2 round trip on the critical path.
+// Per-frame cell masks.
+// One 32-bit word per BEV cell and frame slot: bit i = "class i observed in this cell by this frame", bit C =
+// "lane point with a strong/weak LiDAR return" (the intensity boost).  OR-ing bits is the per-frame
+// (cell, class) de-duplication of the reference's fancy-index "+=" (src/mapping_replay.py:281,294).  The
+// scatter only issues fire-and-forget RED.OR (no returned atomics); k_apply reads the words inside the
+// frame's bounding box, adds the update-matrix columns in frame and class order, and writes the words back
+// to zero, so a slot is always clean between launches.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t tagged_or(uint32_t* __restrict__ word, uint32_t tagword, uint32_t bits, uint32_t low) {
-    atomicMax(word, tagword);
-    return atomicOr(word, bits) & low;
-}
 
-// Bounding box (in cells) of everything a frame touched + number of touched cells; written by the ordered
-// (two-kernel) update so that k_apply sweeps only that window of the mask.
+// Bounding box (in cells, inclusive) of everything a frame touched; written by the scatter kernels.
 struct FrameBox {
-    int x0, x1, y0, y1;   // inclusive; empty when x1 < x0
-    uint32_t touched;     // filled by k_apply (statistics)
-    uint32_t pad[3];
+    int x0, x1, y0, y1;   // empty when x1 < x0
 };
+
+__device__ __forceinline__ void box_reset(int* b) { b[0] = 0x7fffffff; b[1] = -1; b[2] = 0x7fffffff; b[3] = -1; }
 
 // One frame of a batched launch.
 struct BatchFrame {
@@ -39,8 +35,8 @@ struct BatchFrame {
     uint32_t* mask;       // this frame's mask slot (MH*MW words)
     int64_t n;
     int64_t ld;
-    uint32_t tagword;     // frame tag << tag_shift
     uint32_t unit_begin;  // first work unit of this frame in the launch
+    uint32_t pad;
 };
 
 struct BatchParams {
@@ -51,10 +47,10 @@ struct BatchParams {
 
 // tuning knobs (overridable at compile time for the variant sweeps recorded in profiles/)
 #ifndef SMAP_STREAM_ROUND
-#define SMAP_STREAM_ROUND 8     // 32-point chunks a warp loads back to back (LDG.128 in flight per lane)
+#define SMAP_STREAM_ROUND 4     // 32-point chunks per round: LDG.128 per lane in flight (x2 with the prefetch)
 #endif
 #ifndef SMAP_STREAM_ROUNDS
-#define SMAP_STREAM_ROUNDS 2    // rounds per work unit and warp
+#define SMAP_STREAM_ROUNDS 4    // rounds per work unit and warp
 #endif
 #ifndef SMAP_STREAM_MINB
 #define SMAP_STREAM_MINB 3      // resident blocks per SM the register allocation aims for
@@ -62,36 +58,46 @@ struct BatchParams {
 constexpr int kWarps = kThreads / 32;
 constexpr int kRound = SMAP_STREAM_ROUND;
 constexpr int kRounds = SMAP_STREAM_ROUNDS;
-constexpr int kWarpUnitPts = 32 * kRound * kRounds;   // points of a unit owned by one warp
+constexpr int kRoundPts = 32 * kRound;
+constexpr int kWarpUnitPts = kRoundPts * kRounds;     // points of a unit owned by one warp
 constexpr int kUnitPts = kWarps * kWarpUnitPts;       // points per work unit (per block iteration)
-constexpr int kQueueCap = 32 * kRound + 32;           // per-warp survivor stack: < 32 left over + one round
+constexpr int kQueueCap = kRoundPts + 32;             // per-warp survivor stack: < 32 left over + one round
 
 template <int LAYOUT> struct QueueEntry { typedef float4 type; };
 template <> struct QueueEntry<1> { typedef uint32_t type; };
 
+// The reference's own rounding chain for one point; only reached when the certified fast path cannot decide.
+__device__ __noinline__ int exact_project_slow(const FrameParams* f, double x, double y, double z, int* iu, int* iv) {
+    int a, b;
+    const bool ok = project_point(*f, x, y, z, a, b);
+    *iu = a; *iv = b;
+    return ok ? 1 : 0;
+}
+
+__device__ __noinline__ int exact_cell_slow(const GridParams* g, double x, double y, int* cx, int* cy) {
+    int a, b;
+    const bool ok = cell_xy(*g, x, y, a, b);
+    *cx = a; *cy = b;
+    return ok ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------------
-// K1+K2+K3 fused, persistent and warp-autonomous: the whole per-frame rule of SURVEY.md section 9 in one
-// kernel, up to kMaxBatch frames per launch.
+// K1+K2+K3a fused, persistent and warp-autonomous: project -> cull -> label lookup -> class bits -> cell ->
+// mask scatter for up to kMaxBatch frames per launch (src/mapping_replay.py:223-244, :261-277, :288-290).
 //
 // A block walks work units (kUnitPts consecutive points of one frame) round-robin; inside a unit every
 // warp owns a contiguous slice and never synchronises with the other warps:
-//   stream   kRound coalesced LDG.128 per lane in flight, float32 conservative cull (precull_pass), survivors
-//            (~35 %) pushed on the warp's private stack in shared memory (ballot + popc, no atomics);
-//   drain    whenever >= 32 survivors are stacked, pop 32 - one per lane, all lanes busy: exact double
-//            projection (src/mapping_replay.py:223-240), label gather (:244), class bits from the shared colour
-//            tables (:276,:288-290), cell (:261-268), tagged OR into the frame's mask slot (the per-frame
-//            (cell, class) de-duplication of :281/:294);
-//   MODE 1   (count update, CM = identity) every NEWLY set class bit adds 1.0 to map[cell, class] and a newly
-//            set boost bit adds 2.0 to map[cell, lane] with a float64 atomic: integer-valued sums, exact in any
-//            order;
-//   MODE 0   (ordered update) only the masks are written, plus the bounding box of the touched cells;
-//            k_apply then adds the matrix columns in class order.
+//   stream   kRound coalesced LDG.128 per lane per round, the next round prefetched into registers before the
+//            current one is processed; float32 conservative cull (precull_pass); survivors (~35 %) pushed on
+//            the warp's private stack in shared memory (ballot + popc, no atomics);
+//   drain    whenever >= 32 survivors are stacked, pop 32 - one per lane, all lanes busy: certified fast
+//            projection (exact fallback), label gather, class bits from the shared colour tables, certified
+//            fast cell index, one RED.OR into the frame's mask slot; lanes track the bounding box.
 // Stacks survive unit boundaries and are flushed (partial warps) only when the block moves to another frame.
 // ------------------------------------------------------------------------------------------------
-template <int LAYOUT, int MODE>
+template <int LAYOUT>
 __global__ void __launch_bounds__(kThreads, SMAP_STREAM_MINB)
-k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridParams gp, double* __restrict__ map,
-         FrameBox* __restrict__ box) {
+k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridParams gp, FrameBox* __restrict__ boxes) {
     typedef typename QueueEntry<LAYOUT>::type Entry;
     __shared__ __align__(16) Entry s_queue[kWarps][kQueueCap];
     __shared__ uint32_t s_tab_r[256], s_tab_g[256];
@@ -102,14 +108,10 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
     const int warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     Entry* const queue = s_queue[warp];
-    const uint32_t low = (1u << gp.tag_shift) - 1u;
 
     build_color_tables(gp, s_tab_r, s_tab_g);
-    if (MODE == 0 && threadIdx.x == 0) {
-        s_box[0] = 0x7fffffff; s_box[1] = -1; s_box[2] = 0x7fffffff; s_box[3] = -1;
-    }
+    if (threadIdx.x == 0) box_reset(s_box);
 
-    int cur = -1;          // frame whose constants are in s_fp
     uint32_t qn = 0;       // entries on this warp's stack (warp-uniform)
     int bx0 = 0x7fffffff, bx1 = -1, by0 = 0x7fffffff, by1 = -1;
 
@@ -118,7 +120,6 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
     const uint8_t* f_image = nullptr;
     uint32_t* f_mask = nullptr;
     int64_t f_n = 0, f_ld = 0;
-    uint32_t f_tagword = 0;
     bool f_words = false;   // label image can be read with aligned 32-bit loads
 
     // ---- one batch of <= 32 stacked survivors, one per lane
@@ -128,22 +129,35 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
         if ((uint32_t)lane >= count) return;
         double x, y, z;
         float it;
+        bool coords_ok;
         if (LAYOUT == 0) {
             const float4 w = *reinterpret_cast<const float4*>(&queue[first + lane]);
+            coords_ok = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fabsf(w.z)) < (float)kCoordBound;
             x = (double)w.x; y = (double)w.y; z = (double)w.z; it = w.w;
         } else {
             const double* pd = reinterpret_cast<const double*>(f_pts);
             const int64_t k = (int64_t)*reinterpret_cast<const uint32_t*>(&queue[first + lane]);
             x = __ldg(pd + k); y = __ldg(pd + f_ld + k); z = __ldg(pd + 2 * f_ld + k);
+            coords_ok = fmax(fmax(fabs(x), fabs(y)), fabs(z)) < kCoordBound;
             // the boost test compares the float64 intensity with 2 and 14; rounding to float32 could move a
             // value across them, so map the double onto a float on the same side (NaN: neither)
             const double itd = __ldg(pd + 3 * f_ld + k);
             it = (itd < 2.0) ? 0.0f : ((itd > 14.0) ? 15.0f : 8.0f);
         }
-        int iu, iv;
-        if (!project_point(s_fp, x, y, z, iu, iv)) return;
+#ifdef SMAP_ABL_NO_DRAIN   // ablation builds (profiles/): the streaming + cull alone
+        if (x == 1234.5) atomicOr(f_mask, (uint32_t)z);
+        return;
+#endif
+        int iu = 0, iv = 0;
+        int vis = fast_project(s_fp, x, y, z, coords_ok, iu, iv);
+        if (vis < 0) vis = exact_project_slow(&s_fp, x, y, z, &iu, &iv);
+        if (!vis) return;
         const uint32_t off = 3u * ((uint32_t)iv * (uint32_t)s_fp.img_w + (uint32_t)iu);
         uint32_t r, g;
+#ifdef SMAP_ABL_NO_GATHER
+        r = (off & 1u) ? 128u : 255u; g = (off & 1u) ? 64u : 255u;
+        if (false)
+#endif
         if (f_words) {
             // R and G sit in one aligned 32-bit word unless R is its last byte
             const uintptr_t addr = reinterpret_cast<uintptr_t>(f_image) + off;
@@ -158,92 +172,125 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
         }
         const uint32_t bits = class_bits_lut(gp, s_tab_r, s_tab_g, (uint8_t)r, (uint8_t)g, it);
         if (!bits) return;
-        int cx, cy;
-        if (!cell_xy(gp, x, y, cx, cy)) return;
-        const uint32_t cell = (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy;
-        const uint32_t prev = tagged_or(f_mask + cell, f_tagword, bits, low);
-        if (MODE == 0) {
-            bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
-        } else {
-            uint32_t fresh = bits & ~prev;
-            double* row = map + (size_t)cell * gp.c;
-            if (fresh >> gp.c) {  // boost bit newly set: +2 on the lane class (src/mapping_replay.py:294)
-                atomicAdd(row + gp.lane, 2.0);
-                fresh &= (1u << gp.c) - 1u;
-            }
-            while (fresh) {
-                const int i = __ffs(fresh) - 1;
-                fresh &= fresh - 1u;
-                atomicAdd(row + i, 1.0);
-            }
-        }
+        int cx = 0, cy = 0;
+        int on = fast_cell(gp, x, y, cx, cy);
+        if (on < 0) on = exact_cell_slow(&gp, x, y, &cx, &cy);
+        if (!on) return;
+#ifdef SMAP_ABL_NO_SCATTER
+        if (cx == 0x7ffffff0) atomicOr(f_mask, bits);
+        return;
+#endif
+        atomicOr(f_mask + (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy, bits);   // result unused: RED.OR
+        bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
     };
 
-    auto flush_box = [&]() {  // MODE 0: fold the lanes' boxes into the block's
-        if (MODE != 0) return;
-        if (bx1 >= bx0) {
-            atomicMin(&s_box[0], bx0); atomicMax(&s_box[1], bx1);
-            atomicMin(&s_box[2], by0); atomicMax(&s_box[3], by1);
-        }
-    };
-
-    for (uint32_t unit = blockIdx.x; unit < bp.n_units; unit += gridDim.x) {
-        int fi = cur < 0 ? 0 : cur;
+    // ---- work cursor: (unit, round) pairs, identical for all warps of the block
+    struct Cursor { uint32_t unit; int rd; int fi; };
+    auto frame_of = [&](uint32_t unit, int fi) {
         while (fi + 1 < bp.n_frames && unit >= bp.f[fi + 1].unit_begin) ++fi;
-        if (fi != cur) {  // block-uniform: units are frame-major and every warp sees the same sequence
-            while (qn) {  // the old frame's leftovers still need the old constants
-                drain_batch(qn < 32u ? qn : 32u);
-                __syncwarp();
+        return fi;
+    };
+    auto advance = [&](Cursor c) {
+        if (c.rd + 1 < kRounds) { c.rd += 1; return c; }
+        c.rd = 0; c.unit += gridDim.x;
+        if (c.unit < bp.n_units) c.fi = frame_of(c.unit, c.fi);
+        return c;
+    };
+    auto round_base = [&](const Cursor& c) {
+        return (int64_t)(c.unit - bp.f[c.fi].unit_begin) * kUnitPts + (int64_t)warp * kWarpUnitPts + (int64_t)c.rd * kRoundPts;
+    };
+    auto fetch = [&](const Cursor& c, float4 (&buf)[kRound]) {   // LAYOUT 0 only
+        const float4* p4 = reinterpret_cast<const float4*>(f_pts);
+        const int64_t rbase = round_base(c);
+#pragma unroll
+        for (int j = 0; j < kRound; ++j) {
+            const int64_t k = rbase + j * 32 + lane;
+            buf[j] = (k < f_n) ? __ldcs(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto enter_frame = [&](int fi) {   // all threads of the block; ends with the new constants visible
+        const BatchFrame& F = bp.f[fi];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&F.fp);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_fp);
+        for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x) dst[i] = src[i];
+        f_pts = F.pts; f_image = F.image; f_mask = F.mask; f_n = F.n; f_ld = F.ld;
+        f_words = ((reinterpret_cast<uintptr_t>(F.image) & 3u) == 0u) && (((int64_t)F.fp.img_w * F.fp.img_h * 3) % 4 == 0);
+        __syncthreads();
+    };
+    auto leave_frame = [&](int fi) {   // flush the stacks and the bounding box of frame fi
+        while (qn) {
+            drain_batch(qn < 32u ? qn : 32u);
+            __syncwarp();
+        }
+        const bool any = bx1 >= bx0;
+        if (__any_sync(0xffffffffu, any)) {
+            const int a = __reduce_min_sync(0xffffffffu, bx0), b = __reduce_max_sync(0xffffffffu, bx1);
+            const int c = __reduce_min_sync(0xffffffffu, by0), d = __reduce_max_sync(0xffffffffu, by1);
+            if (lane == 0) {
+                atomicMin(&s_box[0], a); atomicMax(&s_box[1], b);
+                atomicMin(&s_box[2], c); atomicMax(&s_box[3], d);
             }
-            __syncthreads();
-            const BatchFrame& F = bp.f[fi];
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(&F.fp);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(&s_fp);
-            for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x) dst[i] = src[i];
-            f_pts = F.pts; f_image = F.image; f_mask = F.mask; f_n = F.n; f_ld = F.ld; f_tagword = F.tagword;
-            f_words = ((reinterpret_cast<uintptr_t>(F.image) & 3u) == 0u) &&
-                      (((int64_t)F.fp.img_w * F.fp.img_h * 3) % 4 == 0);
-            cur = fi;
-            __syncthreads();
         }
-        CullConsts kc;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) kc.m[i] = s_fp.Mf[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            kc.ea[i] = s_fp.Ea[i];
-            kc.eb[i] = s_fp.Eb[i];
+        bx0 = 0x7fffffff; bx1 = -1; by0 = 0x7fffffff; by1 = -1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (s_box[1] >= s_box[0]) {
+                FrameBox* gb = boxes + fi;
+                atomicMin(&gb->x0, s_box[0]); atomicMax(&gb->x1, s_box[1]);
+                atomicMin(&gb->y0, s_box[2]); atomicMax(&gb->y1, s_box[3]);
+            }
+            box_reset(s_box);
         }
-        kc.range_hi = s_fp.range_hi;
-        kc.wf = s_fp.img_wf;
-        kc.hf = s_fp.img_hf;
+        // the next enter_frame's barrier orders this against later s_box / s_fp use
+    };
 
-        const int64_t wbase = (int64_t)(unit - bp.f[fi].unit_begin) * kUnitPts + (int64_t)warp * kWarpUnitPts;
-#pragma unroll 1
-        for (int rd = 0; rd < kRounds; ++rd) {
-            const int64_t rbase = wbase + (int64_t)rd * (32 * kRound);
-            if (rbase >= f_n) break;
-            if (LAYOUT == 0) {
-                const float4* p4 = reinterpret_cast<const float4*>(f_pts);
-                float4 p[kRound];
+    Cursor cur;
+    cur.unit = blockIdx.x; cur.rd = 0; cur.fi = 0;
+    if (cur.unit >= bp.n_units) return;
+    cur.fi = frame_of(cur.unit, 0);
+    __syncthreads();   // colour tables, s_box
+    enter_frame(cur.fi);
+
+    float4 buf[kRound];
+    if constexpr (LAYOUT == 0) fetch(cur, buf);
+
+    while (true) {
+        const Cursor nxt = advance(cur);
+        const bool has_next = nxt.unit < bp.n_units;
+        const bool same_frame = has_next && nxt.fi == cur.fi;
+        float4 pre[kRound];
+        if constexpr (LAYOUT == 0) {
+            if (same_frame) fetch(nxt, pre);   // in flight while this round is processed
+        }
+
+        // ---- cull the current round
+        {
+            CullConsts kc;
 #pragma unroll
-                for (int c = 0; c < kRound; ++c) {
-                    const int64_t k = rbase + c * 32 + lane;
-                    p[c] = (k < f_n) ? __ldcs(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int i = 0; i < 16; ++i) kc.m[i] = s_fp.Mf[i];
 #pragma unroll
-                for (int c = 0; c < kRound; ++c) {
-                    const int64_t k = rbase + c * 32 + lane;
-                    const bool pass = (k < f_n) & precull_pass(kc, p[c].x, p[c].y, p[c].z);
+            for (int i = 0; i < 4; ++i) {
+                kc.ea[i] = s_fp.Ea[i];
+                kc.eb[i] = s_fp.Eb[i];
+            }
+            kc.range_hi = s_fp.range_hi;
+            kc.wf = s_fp.img_wf;
+            kc.hf = s_fp.img_hf;
+            const int64_t rbase = round_base(cur);
+            if constexpr (LAYOUT == 0) {
+#pragma unroll
+                for (int j = 0; j < kRound; ++j) {
+                    const int64_t k = rbase + j * 32 + lane;
+                    const bool pass = (k < f_n) & precull_pass(kc, buf[j].x, buf[j].y, buf[j].z);
                     const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                    if (pass) *reinterpret_cast<float4*>(&queue[qn + __popc(ballot & lt_mask)]) = p[c];
+                    if (pass) *reinterpret_cast<float4*>(&queue[qn + __popc(ballot & lt_mask)]) = buf[j];
                     qn += __popc(ballot);
                 }
             } else {
                 const double* pd = reinterpret_cast<const double*>(f_pts);
 #pragma unroll 2
-                for (int c = 0; c < kRound; ++c) {
-                    const int64_t k = rbase + c * 32 + lane;
+                for (int j = 0; j < kRound; ++j) {
+                    const int64_t k = rbase + j * 32 + lane;
                     bool pass = false;
                     if (k < f_n)
                         pass = precull_pass(kc, (float)__ldg(pd + k), (float)__ldg(pd + f_ld + k), (float)__ldg(pd + 2 * f_ld + k));
@@ -252,44 +299,41 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
                     qn += __popc(ballot);
                 }
             }
-            __syncwarp();
-            while (qn >= 32u) {
-                drain_batch(32u);
-                __syncwarp();
-            }
         }
-    }
-    while (qn) {
-        drain_batch(qn < 32u ? qn : 32u);
         __syncwarp();
-    }
-    if (MODE == 0) {
-        flush_box();
-        __syncthreads();
-        if (threadIdx.x == 0 && s_box[1] >= s_box[0]) {
-            atomicMin(&box->x0, s_box[0]); atomicMax(&box->x1, s_box[1]);
-            atomicMin(&box->y0, s_box[2]); atomicMax(&box->y1, s_box[3]);
+        while (qn >= 32u) {
+            drain_batch(32u);
+            __syncwarp();
         }
+        if (!has_next) break;
+        if (!same_frame) {   // block-uniform
+            leave_frame(cur.fi);
+            enter_frame(nxt.fi);
+            if constexpr (LAYOUT == 0) fetch(nxt, pre);
+        }
+        if constexpr (LAYOUT == 0) {
+#pragma unroll
+            for (int j = 0; j < kRound; ++j) buf[j] = pre[j];
+        }
+        cur = nxt;
     }
+    leave_frame(cur.fi);
 }
 
-// Parity kernel for update_map (src/mapping_replay.py:261-277,:288-290): the scatter half of the ordered update from
-// an already projected cloud (4, M) float64 + its (3, M) RGB labels.
+// Parity kernel for update_map (src/mapping_replay.py:261-277,:288-290): the scatter half from an already
+// projected cloud (4, M) float64 + its (3, M) RGB labels, exact arithmetic throughout.
 __global__ void __launch_bounds__(kThreads)
 k_update_scatter(const double* __restrict__ pcd, int64_t ld, const uint8_t* __restrict__ label, int64_t ldl,
-                 int64_t m, const __grid_constant__ GridParams gp, uint32_t* __restrict__ mask, uint32_t tagword,
+                 int64_t m, const __grid_constant__ GridParams gp, uint32_t* __restrict__ mask,
                  FrameBox* __restrict__ box) {
     __shared__ int s_box[4];
-    if (threadIdx.x == 0) {
-        s_box[0] = 0x7fffffff; s_box[1] = -1; s_box[2] = 0x7fffffff; s_box[3] = -1;
-    }
+    if (threadIdx.x == 0) box_reset(s_box);
     __syncthreads();
-    const uint32_t low = (1u << gp.tag_shift) - 1u;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t bits = class_bits(gp, label[k], label[ldl + k], pcd[3 * ld + k]);
         int cx, cy;
         if (bits && cell_xy(gp, pcd[k], pcd[ld + k], cx, cy)) {
-            tagged_or(mask + (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy, tagword, bits, low);
+            atomicOr(mask + (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy, bits);
             atomicMin(&s_box[0], cx); atomicMax(&s_box[1], cx);
             atomicMin(&s_box[2], cy); atomicMax(&s_box[3], cy);
         }
@@ -302,63 +346,93 @@ k_update_scatter(const double* __restrict__ pcd, int64_t ld, const uint8_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3b (ordered update): sweep the frame's bounding box of the mask slot; every cell whose word carries this
-// frame's tag gets the matrix columns of its classes added in ascending class order, then the lane boost:
-// the "+=" statements at src/mapping_replay.py:281 and :294 bit for bit, for any update matrix.
-// The box rows are contiguous in memory (axis 1), so the 4-byte mask reads are coalesced; the window of a
-// 100 m frustum at 0.1 m is ~1.2 M words = 5 MB, cheaper than maintaining a list of touched cells with
-// contended atomics.  `box` is this frame's window, `next_box` (other half of the double buffer) is reset.
+// K3b: ordered apply for up to kMaxBatch frame slots in one pass.
+// One thread per cell of the union of the frames' bounding boxes.  It reads the cell's word in every slot
+// whose box contains it (coalesced along the row), and if any is non-zero it loads the C-element grid row
+// once, replays the frames IN ORDER -- for each frame the classes in ascending order, "row += CM[:, i]" and
+// the lane boost, exactly the statements at src/mapping_replay.py:281 and :294 -- stores the row once and
+// zeroes the words.  Bit-exact for any update matrix; the grid row traffic is shared by all frames of the batch.
+// NJ = ceil(C / 8): the row lives in 8*NJ registers.
 // ------------------------------------------------------------------------------------------------
+struct ApplyParams {
+    int n_frames;
+    int pad;
+    uint32_t* mask[kMaxBatch];
+};
+
+template <int NJ>
 __global__ void __launch_bounds__(kThreads)
-k_apply(double* __restrict__ map, const uint32_t* __restrict__ mask, uint32_t tagword, int tag_shift,
-        FrameBox* __restrict__ box, FrameBox* __restrict__ next_box, const double* __restrict__ cm, int c, int lane_cls, int mw) {
+k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameBox* __restrict__ boxes,
+        FrameBox* __restrict__ next_boxes, unsigned long long* __restrict__ touched_total,
+        unsigned long long* __restrict__ next_touched_total, const double* __restrict__ cm, int c, int lane_cls, int mw) {
     extern __shared__ double s_cm[];  // C x C, transposed: s_cm[i * c + j] = cm[j * c + i] (column i contiguous)
-    __shared__ uint32_t s_count;
+    __shared__ FrameBox s_boxes[kMaxBatch];
+    __shared__ unsigned int s_count;
     for (int e = threadIdx.x; e < c * c; e += blockDim.x) s_cm[(e % c) * c + e / c] = cm[e];
+    if (threadIdx.x < ap.n_frames) s_boxes[threadIdx.x] = boxes[threadIdx.x];
     if (threadIdx.x == 0) s_count = 0;
+    if (blockIdx.x == 0 && threadIdx.x < kMaxBatch) box_reset(&next_boxes[threadIdx.x].x0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *next_touched_total = 0ull;
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        next_box->x0 = 0x7fffffff; next_box->x1 = -1; next_box->y0 = 0x7fffffff; next_box->y1 = -1;
-        next_box->touched = 0;
+    int x0 = 0x7fffffff, x1 = -1, y0 = 0x7fffffff, y1 = -1;
+    for (int f = 0; f < ap.n_frames; ++f) {
+        if (s_boxes[f].x1 < s_boxes[f].x0) continue;
+        x0 = min(x0, s_boxes[f].x0); x1 = max(x1, s_boxes[f].x1);
+        y0 = min(y0, s_boxes[f].y0); y1 = max(y1, s_boxes[f].y1);
     }
-    const int x0 = box->x0, x1 = box->x1, y0 = box->y0, y1 = box->y1;
-    if (x1 < x0) return;
+    if (x1 < x0) return;   // block-uniform
     const uint32_t ncols = (uint32_t)(y1 - y0 + 1);
     const uint64_t total = (uint64_t)(x1 - x0 + 1) * ncols;
     const uint32_t boost = 1u << c;
-    const uint32_t tag = tagword >> tag_shift;
-    uint32_t mine = 0;
+    const uint32_t lane_bit = lane_cls >= 0 ? (1u << lane_cls) : 0u;
+    unsigned int mine = 0;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t rr = (uint32_t)(t / ncols), cc = (uint32_t)(t - (uint64_t)rr * ncols);
-        const uint32_t cell = (uint32_t)(x0 + (int)rr) * (uint32_t)mw + (uint32_t)(y0 + (int)cc);
-        const uint32_t word = __ldcg(mask + cell);
-        if ((word >> tag_shift) != tag) continue;
-        ++mine;
+        const int cx = x0 + (int)rr, cy = y0 + (int)cc;
+        const uint32_t cell = (uint32_t)cx * (uint32_t)mw + (uint32_t)cy;
+        // pass 1: is the cell touched by any frame of the batch?  (independent coalesced loads)
+        uint32_t any = 0;
+#pragma unroll
+        for (int f = 0; f < kMaxBatch; ++f) {
+            if (f < ap.n_frames && cx >= s_boxes[f].x0 && cx <= s_boxes[f].x1 && cy >= s_boxes[f].y0 && cy <= s_boxes[f].y1)
+                any |= __ldcg(ap.mask[f] + cell);
+        }
+        if (!any) continue;
+        // pass 2: replay the frames in order on the row held in registers
         double* row = map + (size_t)cell * c;
-        for (int j0 = 0; j0 < c; j0 += 8) {
-            double acc[8];
+        double acc[8 * NJ];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) acc[jj] = (j0 + jj < c) ? row[j0 + jj] : 0.0;
+        for (int j = 0; j < 8 * NJ; ++j) acc[j] = (j < c) ? row[j] : 0.0;
+#pragma unroll 1
+        for (int f = 0; f < ap.n_frames; ++f) {
+            if (!(cx >= s_boxes[f].x0 && cx <= s_boxes[f].x1 && cy >= s_boxes[f].y0 && cy <= s_boxes[f].y1)) continue;
+            uint32_t* wp = ap.mask[f] + cell;
+            const uint32_t w = __ldcg(wp);
+            if (!w) continue;
+            ++mine;
+            *wp = 0u;
+#pragma unroll 1
             for (int i = 0; i < c; ++i) {
-                if (!((word >> i) & 1u)) continue;
-                const double* col = s_cm + i * c + j0;
+                if (!((w >> i) & 1u)) continue;
+                const double* col = s_cm + i * c;
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    if (j0 + jj < c) acc[jj] = __dadd_rn(acc[jj], col[jj]);
-                if (i == lane_cls && (word & boost) && i >= j0 && i < j0 + 8) {
+                for (int j = 0; j < 8 * NJ; ++j)
+                    if (j < c) acc[j] = __dadd_rn(acc[j], col[j]);
+                if (i == lane_cls && (w & boost)) {
+                    // written with a bit test per (compile-time) j so that acc[] is never indexed dynamically
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj)
-                        if (j0 + jj == i) acc[jj] = __dadd_rn(acc[jj], 2.0);
+                    for (int j = 0; j < 8 * NJ; ++j)
+                        if ((lane_bit >> j) & 1u) acc[j] = __dadd_rn(acc[j], 2.0);
                 }
             }
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-                if (j0 + jj < c) row[j0 + jj] = acc[jj];
         }
+#pragma unroll
+        for (int j = 0; j < 8 * NJ; ++j)
+            if (j < c) row[j] = acc[j];
     }
     if (mine) atomicAdd(&s_count, mine);
     __syncthreads();
-    if (threadIdx.x == 0 && s_count) atomicAdd(&box->touched, s_count);
+    if (threadIdx.x == 0 && s_count) atomicAdd(touched_total, (unsigned long long)s_count);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -122,12 +122,8 @@ class DeviceMapper(object):
 
     # ------------------------------------------------------------------ the path
     def integrate(self, frame):
-        """project_pcd + update_map of one frame, fused, deterministic (bit-exact)."""
+        """project_pcd + update_map of one frame, fused (bit-exact for any update matrix)."""
         _native.check(self._lib.smap_integrate(self._h, ctypes.byref(frame), self._stream()))
-
-    def set_deterministic(self, on=True):
-        """Force the ordered two-kernel update even for the count update (see include/smap.h)."""
-        _native.check(self._lib.smap_set_deterministic(self._h, int(bool(on))))
 
     def integrate_host(self, frame):
         _native.check(self._lib.smap_integrate_host(self._h, ctypes.byref(frame), self._stream()))
