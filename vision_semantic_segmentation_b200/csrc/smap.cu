@@ -60,6 +60,7 @@ struct smap_handle {
     unsigned long long* touched = nullptr;    // [2]
     int parity = 0;
     int sm_count = 148;
+    bool identity_cm = false;   // update matrix is exactly np.eye(C): k_apply adds unit vectors
     // class tables
     double* cm_dev = nullptr;
     uint8_t colors[SMAP_MAX_CLASSES * 3];
@@ -97,7 +98,7 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
     if (f->layout != SMAP_PTS_F32X4 && f->layout != SMAP_PTS_F64_SOA) return fail(SMAP_ERR_INVALID, "unknown point layout");
     if (f->layout == SMAP_PTS_F64_SOA && f->ld < f->n_points) return fail(SMAP_ERR_INVALID, "ld < n_points");
     if (f->image_width <= 0 || f->image_height <= 0) return fail(SMAP_ERR_INVALID, "empty label image");
-    if ((int64_t)f->image_width * f->image_height * 3 >= ((int64_t)1 << 32)) return fail(SMAP_ERR_INVALID, "label image larger than 4 GB");
+    if (f->image_width > 65535 || f->image_height > 32767) return fail(SMAP_ERR_INVALID, "label image larger than 65535 x 32767");
     if (f->layout == SMAP_PTS_F64_SOA && f->n_points >= ((int64_t)1 << 32)) return fail(SMAP_ERR_INVALID, "more than 2^32 points in a float64 cloud");
     if (f->n_points > 0 && (!f->points_dev || !f->image_dev)) return fail(SMAP_ERR_INVALID, "NULL points / image");
     if (f->layout == SMAP_PTS_F32X4 && (reinterpret_cast<uintptr_t>(f->points_dev) & 15u))
@@ -121,6 +122,11 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
             // next float up so that the bound survives the rounding of these two products
             fp.Ea[r] = nextafterf(kCullSlack * a, INFINITY);
             fp.Eb[r] = nextafterf(kCullSlack * fabsf(fp.Mf[4 * r + 3]), INFINITY);
+        }
+        for (int p = 0; p < 2; ++p) {
+            for (int j = 0; j < 4; ++j) fp.Mc[p][j] = make_float2(fp.Mf[(2 * p) * 4 + j], fp.Mf[(2 * p + 1) * 4 + j]);
+            fp.Eac[p] = make_float2(fp.Ea[2 * p], fp.Ea[2 * p + 1]);
+            fp.Ebc[p] = make_float2(fp.Eb[2 * p], fp.Eb[2 * p + 1]);
         }
         fp.range_hi = (float)fp.range_max * (1.0f + kCullSlack);
         fp.img_wf = (float)f->image_width;
@@ -148,6 +154,15 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
         fp.c0 = umax * 5.6843418860808015e-14;  // 2^-44
         fp.img_wd = (double)f->image_width;
         fp.img_hd = (double)f->image_height;
+        fp.img_wd1 = fp.img_wd + 1.0;
+        fp.img_hd1 = fp.img_hd + 1.0;
+        fp.one_d = 1.0 + 9.094947017729282e-13;  // 1 + 2^-40
+        fp.w_d = fp.img_wd * fp.one_d;
+        fp.h_d = fp.img_hd * fp.one_d;
+        fp.clo_u = e[0] + fp.one_d * e[2];
+        fp.chi_u = e[0] + fp.w_d * e[2];
+        fp.clo_v = e[1] + fp.one_d * e[2];
+        fp.chi_v = e[1] + fp.h_d * e[2];
         // non-finite bounds (absurd matrices) switch the fast path off: q2 > inf never holds
         if (!(fp.cgu == fp.cgu) || !(fp.cgv == fp.cgv) || !(fp.e3x4 == fp.e3x4)) fp.e3x4 = INFINITY;
     }
@@ -206,51 +221,50 @@ int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st)
     unsigned long long* ntt = h->touched + (h->parity ^ 1);
     const unsigned grid = (unsigned)h->sm_count * 8;
     const int lane = h->cfg.lane_index, mw = h->cfg.map_width;
-    if (c <= 8) k_apply<1><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw);
-    else if (c <= 16) k_apply<2><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw);
-    else if (c <= 24) k_apply<3><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw);
-    else k_apply<4><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw);
+#define SMAP_LAUNCH_APPLY(NJ)                                                                                          \
+    do {                                                                                                              \
+        if (h->identity_cm) k_apply<NJ, true><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw); \
+        else k_apply<NJ, false><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw); \
+    } while (0)
+    if (c <= 8) SMAP_LAUNCH_APPLY(1);
+    else if (c <= 16) SMAP_LAUNCH_APPLY(2);
+    else if (c <= 24) SMAP_LAUNCH_APPLY(3);
+    else SMAP_LAUNCH_APPLY(4);
+#undef SMAP_LAUNCH_APPLY
     CK(cudaGetLastError());
     h->parity ^= 1;
     h->stats.kernel_launches += 1;
     return SMAP_OK;
 }
 
-// One launch of k_stream over up to kMaxBatch frames (already validated; fps[i] filled); frame i of the
-// non-empty ones scatters into mask slot i.  Returns the number of slots used in *slots_used.
+// Queue one k_stream launch per non-empty frame; frame i of the non-empty ones scatters into mask slot i.
+// Returns the number of slots used in *slots_used.
 int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, cudaStream_t st,
                   int* slots_used) {
-    static BatchParams bp;  // ~8 KB: keep it off the stack; handles are single-threaded per the ABI contract
-    memset(&bp, 0, sizeof bp);
-    uint32_t units = 0;
     const int layout = frames[0].layout;
     int used = 0;
     for (int i = 0; i < n_frames; ++i) {
         if (frames[i].n_points == 0) continue;
         if (frames[i].layout != layout) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
-        BatchFrame& b = bp.f[used];
-        b.fp = fps[i];
-        b.pts = frames[i].points_dev;
-        b.image = frames[i].image_dev;
-        b.mask = h->mask + (size_t)used * h->cells;
-        b.n = frames[i].n_points;
-        b.ld = frames[i].ld;
-        b.unit_begin = units;
-        units += (uint32_t)ceil_div(frames[i].n_points, kUnitPts);
+        StreamParams sp;
+        sp.fp = fps[i];
+        sp.pts = frames[i].points_dev;
+        sp.image = frames[i].image_dev;
+        sp.mask = h->mask + (size_t)used * h->cells;
+        sp.n = frames[i].n_points;
+        sp.ld = frames[i].ld;
+        // persistent grid: as many blocks as stay resident, never more than the cloud has rounds
+        int64_t grid = (int64_t)h->sm_count * SMAP_STREAM_MINB;
+        const int64_t rounds = ceil_div(sp.n, kBlockRoundPts);
+        if (grid > rounds) grid = rounds;
+        FrameBox* box = h->boxes + (size_t)h->parity * kMaxBatch + used;
+        if (layout == SMAP_PTS_F32X4) k_stream<SMAP_PTS_F32X4><<<(unsigned)grid, kThreads, 0, st>>>(sp, h->gp, box);
+        else k_stream<SMAP_PTS_F64_SOA><<<(unsigned)grid, kThreads, 0, st>>>(sp, h->gp, box);
+        CK(cudaGetLastError());
+        h->stats.kernel_launches += 1;
         ++used;
     }
     *slots_used = used;
-    if (used == 0) return SMAP_OK;
-    bp.n_frames = used;
-    bp.n_units = units;
-    // persistent grid: as many blocks as stay resident, never more than there are units
-    uint32_t grid = (uint32_t)h->sm_count * SMAP_STREAM_MINB;
-    if (grid > units) grid = units;
-    FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch;
-    if (layout == SMAP_PTS_F32X4) k_stream<SMAP_PTS_F32X4><<<grid, kThreads, 0, st>>>(bp, h->gp, boxes);
-    else k_stream<SMAP_PTS_F64_SOA><<<grid, kThreads, 0, st>>>(bp, h->gp, boxes);
-    CK(cudaGetLastError());
-    h->stats.kernel_launches += 1;
     return SMAP_OK;
 }
 
@@ -338,6 +352,8 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     g.lane = cfg->lane_index < 0 ? -1 : cfg->lane_index;
     g.use_intensity = cfg->use_intensity ? 1 : 0;
     g.rinv = 1.0 / cfg->resolution;
+    g.mh_d1 = (double)cfg->map_height + 1.0;
+    g.mw_d1 = (double)cfg->map_width + 1.0;
     const size_t map_bytes = sizeof(double) * (size_t)h->cells * cfg->num_classes;
     cudaError_t e = cudaSuccess;
     if (cfg->map_dev) {
@@ -407,6 +423,10 @@ int smap_set_classes(smap_handle* h, const uint8_t* colors_host, const double* c
     }
     CK(cudaDeviceSynchronize());  // a previous frame may still be reading the table
     CK(cudaMemcpy(h->cm_dev, cm_host, sizeof(double) * c * c, cudaMemcpyHostToDevice));
+    h->identity_cm = true;
+    for (int i = 0; i < c; ++i)
+        for (int j = 0; j < c; ++j)
+            if (cm_host[i * c + j] != (i == j ? 1.0 : 0.0)) h->identity_cm = false;
     h->classes_set = true;
     return SMAP_OK;
 }

@@ -25,12 +25,21 @@ struct FrameParams {
     double cgu, cgv;   // guard slopes: (4/3) (e_row + Umax e_depth)
     double c0;         // guard offset: Umax * 2^-44
     double img_wd, img_hd;
+    double img_wd1, img_hd1;   // W + 1, H + 1
+    // ---- conservative cull in double (cull_pass): a point can only be kept if
+    //   q0 + (1+d) q2 > -clo_u,  W(1+d) q2 - q0 > -chi_u   (and the same for v) whenever q2 > e3x4
+    double one_d;      // 1 + 2^-40
+    double w_d, h_d;   // W (1 + 2^-40), H (1 + 2^-40)
+    double clo_u, chi_u, clo_v, chi_v;
     // ---- float32 pre-cull (see precull_pass): row 0 = T row 0 (velodyne x), rows 1..3 = rows of P*T
     float Mf[16];
     float Ea[4];       // kCullSlack * max(|m_r0|, |m_r1|, |m_r2|)   error bound of row r = Ea[r] * (|x|+|y|+|z|) + Eb[r]
     float Eb[4];       // kCullSlack * |m_r3|
     float range_hi;    // range_max * (1 + kCullSlack)
     float img_wf, img_hf;
+    // the same constants paired by rows -- {row 0, row 1} and {row 2, row 3} -- as operands of the packed
+    // FFMA2 / FADD2 instructions: Mc[p][j] = {Mf[(2p)*4 + j], Mf[(2p+1)*4 + j]}
+    float2 Mc[2][4], Eac[2], Ebc[2];
     int has_T;         // 0: cloud already in the velodyne frame
     int img_w, img_h;  // image.shape[1], image.shape[0]
     int pad;
@@ -45,6 +54,7 @@ struct GridParams {
     double bx0, by0;      // cfg.MAPPING.BOUNDARY[0][0], [1][0]
     double res;           // cfg.MAPPING.RESOLUTION
     double rinv;          // fl(1 / res) for the certified fast cell index
+    double mh_d1, mw_d1;  // MH + 1, MW + 1
     int mh, mw, c;
     int lane;             // class index named "lane", or -1
     int use_intensity;
@@ -146,17 +156,13 @@ __device__ __forceinline__ uint32_t class_bits_lut(const GridParams& g, const ui
 // where kCullSlack = 1e-6 covers the float rounding of the inputs (6e-8), of the composed matrix (6e-8) and
 // of the four-term fused sum (< 2.4e-7) with a 2x margin for the comparisons below; the double chain's own
 // rounding and the final division's (1e-16) disappear in it.  Branch-free: one predicate per point.
-struct CullConsts {
-    float m[16], ea[4], eb[4], range_hi, wf, hf;
-};
-
-__device__ __forceinline__ bool precull_pass(const CullConsts& k, float x, float y, float z) {
+__device__ __forceinline__ bool precull_pass(const FrameParams& k, float x, float y, float z) {
     const float s = fabsf(x) + fabsf(y) + fabsf(z);
     float v[4], e[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        v[r] = fmaf(k.m[4 * r], x, fmaf(k.m[4 * r + 1], y, fmaf(k.m[4 * r + 2], z, k.m[4 * r + 3])));
-        e[r] = fmaf(k.ea[r], s, k.eb[r]);
+        v[r] = fmaf(k.Mf[4 * r], x, fmaf(k.Mf[4 * r + 1], y, fmaf(k.Mf[4 * r + 2], z, k.Mf[4 * r + 3])));
+        e[r] = fmaf(k.Ea[r], s, k.Eb[r]);
     }
     // anything not comfortably finite in float goes to the exact path (which rejects NaN / inf itself)
     const bool finite = (e[0] + e[1] + e[2] + e[3]) < 1e30f;
@@ -164,8 +170,32 @@ __device__ __forceinline__ bool precull_pass(const CullConsts& k, float x, float
     // depth certainly positive: -q2 < q0 < W q2 and -q2 < q1 < H q2 must be possible; otherwise decided exactly
     const bool depth_pos = (v[3] - e[3]) > 0.0f;
     const float q2hi = (v[3] + e[3]) * (1.0f + kCullSlack);
-    const bool u_ok = (v[1] + e[1] > -q2hi) & (v[1] - e[1] < k.wf * q2hi);
-    const bool v_ok = (v[2] + e[2] > -q2hi) & (v[2] - e[2] < k.hf * q2hi);
+    const bool u_ok = (v[1] + e[1] > -q2hi) & (v[1] - e[1] < k.img_wf * q2hi);
+    const bool v_ok = (v[2] + e[2] > -q2hi) & (v[2] - e[2] < k.img_hf * q2hi);
+    return !finite | (range_ok & (!depth_pos | (u_ok & v_ok)));
+}
+
+// The same test with Blackwell's packed float32 pipe (FFMA2 / FADD2, sm_100+): rows 0,1 and rows 2,3 of the
+// pre-cull matrix are evaluated as float2 pairs, so 20 FFMA + 8 FADD become 8 FFMA2 + 4 FADD2.  That matters
+// because this kernel is issue-bound, not FP32-bound.  Every operation is the same IEEE round-to-nearest
+// operation as in precull_pass, so the two agree bit for bit (except the order of the 4-term sum that only
+// feeds the "is it finite" test).
+__device__ __forceinline__ bool precull_pass_packed(const FrameParams& k, float x, float y, float z) {
+    const float s = fabsf(x) + fabsf(y) + fabsf(z);
+    const float2 xx = make_float2(x, x), yy = make_float2(y, y), zz = make_float2(z, z), ss = make_float2(s, s);
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
+    const float2 v01 = __ffma2_rn(k.Mc[0][0], xx, __ffma2_rn(k.Mc[0][1], yy, __ffma2_rn(k.Mc[0][2], zz, k.Mc[0][3])));
+    const float2 v23 = __ffma2_rn(k.Mc[1][0], xx, __ffma2_rn(k.Mc[1][1], yy, __ffma2_rn(k.Mc[1][2], zz, k.Mc[1][3])));
+    const float2 e01 = __ffma2_rn(k.Eac[0], ss, k.Ebc[0]), e23 = __ffma2_rn(k.Eac[1], ss, k.Ebc[1]);
+    const float2 hi01 = __fadd2_rn(v01, e01), hi23 = __fadd2_rn(v23, e23);
+    const float2 lo01 = __ffma2_rn(e01, neg1, v01), lo23 = __ffma2_rn(e23, neg1, v23);   // v - e, one rounding
+    const float2 es = __fadd2_rn(e01, e23);
+    const bool finite = (es.x + es.y) < 1e30f;
+    const bool range_ok = (hi01.x > 0.0f) & (lo01.x < k.range_hi);
+    const bool depth_pos = lo23.y > 0.0f;
+    const float q2hi = hi23.y * (1.0f + kCullSlack);
+    const bool u_ok = (hi01.y > -q2hi) & (lo01.y < k.img_wf * q2hi);
+    const bool v_ok = (hi23.x > -q2hi) & (lo23.x < k.img_hf * q2hi);
     return !finite | (range_ok & (!depth_pos | (u_ok & v_ok)));
 }
 
@@ -178,22 +208,24 @@ __device__ __forceinline__ bool precull_pass(const CullConsts& k, float x, float
 // Projection: q~ = M p with M = P T composed on the host (12 FMAs instead of 28).  Both q~ and the reference
 // chain q^ approximate the exact product within 8.1 u sum_j (|P||T|)_rj |x_j|, so |q~ - q^| <= e_r with
 // e_r = 64 u ((|P||T|)_r,xyz 3 B + (|P||T|)_r,w) for |x|,|y|,|z| < B (u = 2^-53; 4x safety factor).
-// With depth q~2 > 4 e_3:  |q~0/q~2 - q^0/q^2| <= (4/3)(e_1 + |u| e_3) / q~2.  The reciprocal (MUFU seed + two
+// With depth |q~2| > 4 e_3:  |q~0/q~2 - q^0/q^2| <= (4/3)(e_1 + |u| e_3) / |q~2|.  The reciprocal (MUFU seed + two
 // Newton steps) is good to 2^-45, the reference's own division to 2^-53.  Guard:
 //      g = (cg * r + c0),  cg = (4/3)(e_row + Umax e_3),  c0 = Umax 2^-44,  Umax = max(W, H) + 2.
 // The range test uses the velodyne x of the reference chain itself (same four operations), so it is exact.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double fast_rcp(double a) {
+    // MUFU.RCP64H seed (only the high word is used: good to at least 2^-8), three Newton steps square the
+    // error each time: 2^-8 -> 2^-16 -> 2^-32 -> 2^-64, i.e. limited by the roundings (a few 2^-53) < 2^-45
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    r = __fma_rn(r, __fma_rn(-a, r, 1.0), r);
     r = __fma_rn(r, __fma_rn(-a, r, 1.0), r);
     r = __fma_rn(r, __fma_rn(-a, r, 1.0), r);
     return r;
 }
 
-// floor of t when t is farther than `guard` from every integer; returns false when it is not (or t is not in
-// (-2, limit + 1), where the magic-number rounding below is valid and the answer may matter).
-// Caller has already established that a t outside (-2, limit + 1) means "out of range" for certain.
+// floor of t when t is farther than `guard` from every integer; returns false when it is not.
+// Valid for |t| < 2^31 (the callers check the range first).
 __device__ __forceinline__ bool certified_floor(double t, double guard, int& k) {
     const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
     const double rn = __dadd_rn(__dadd_rn(t, kMagic), -kMagic);
@@ -202,45 +234,67 @@ __device__ __forceinline__ bool certified_floor(double t, double guard, int& k) 
     return fabs(d) > guard;
 }
 
-// Fast version of project_point.  Returns 1 = kept (iu, iv valid), 0 = dropped, -1 = undecided (use project_point).
-__device__ __forceinline__ int fast_project(const FrameParams& f, double x, double y, double z, bool coords_ok,
-                                            int& iu, int& iv) {
-    const double vx = f.has_T ? dot4(f.T, x, y, z, 1.0) : x;   // the reference's own value
-    if (!((0.0 < vx) && (vx < f.range_max))) return 0;          // src/mapping_replay.py:235, exact
+// Decisions are returned packed in one int: >= 0: kept, value = (row << 16 | col) style payload built by the
+// caller; kDrop: dropped; kAsk: undecided, evaluate the reference chain.
+constexpr int kDrop = -1;
+constexpr int kAsk = -2;
+
+// Conservative cull in double precision: false only when the reference rule is CERTAIN to drop the point.
+// vx is the reference's own velodyne x (same four operations), so the range test is exact; the frustum test
+// uses q~ = M p and the error bounds e_r folded into clo_* / chi_* (see FrameParams).
+__device__ __forceinline__ bool cull_pass(const FrameParams& f, double x, double y, double z, bool coords_ok) {
+    const double vx = f.has_T ? dot4(f.T, x, y, z, 1.0) : x;
+    const bool in_front = (0.0 < vx) & (vx < f.range_max);          // src/mapping_replay.py:235, exact
     const double q0 = __fma_rn(f.M[0], x, __fma_rn(f.M[1], y, __fma_rn(f.M[2], z, f.M[3])));
     const double q1 = __fma_rn(f.M[4], x, __fma_rn(f.M[5], y, __fma_rn(f.M[6], z, f.M[7])));
     const double q2 = __fma_rn(f.M[8], x, __fma_rn(f.M[9], y, __fma_rn(f.M[10], z, f.M[11])));
-    if (!coords_ok || !(q2 > f.e3x4)) return -1;
+    const bool certain_depth = coords_ok & (q2 > f.e3x4);
+    const bool u_ok = (__fma_rn(q2, f.one_d, q0) > -f.clo_u) & (__fma_rn(q2, f.w_d, -q0) > -f.chi_u);
+    const bool v_ok = (__fma_rn(q2, f.one_d, q1) > -f.clo_v) & (__fma_rn(q2, f.h_d, -q1) > -f.chi_v);
+    // NaN anywhere: comparisons are false -> in_front false (NaN coordinate makes vx NaN) -> dropped, as the
+    // reference does; a huge-but-finite coordinate fails coords_ok and is passed on to the exact path
+    return in_front & (!certain_depth | (u_ok & v_ok));
+}
+
+// Fast version of project_point for a point that passed cull_pass.  Returns (iv << 16 | iu) >= 0 when kept
+// (images up to 32767 x 65535), kDrop, or kAsk.
+__device__ __forceinline__ int fast_project(const FrameParams& f, double x, double y, double z, bool coords_ok) {
+    const double vx = f.has_T ? dot4(f.T, x, y, z, 1.0) : x;   // the reference's own value
+    if (!((0.0 < vx) && (vx < f.range_max))) return kDrop;      // src/mapping_replay.py:235, exact
+    const double q0 = __fma_rn(f.M[0], x, __fma_rn(f.M[1], y, __fma_rn(f.M[2], z, f.M[3])));
+    const double q1 = __fma_rn(f.M[4], x, __fma_rn(f.M[5], y, __fma_rn(f.M[6], z, f.M[7])));
+    const double q2 = __fma_rn(f.M[8], x, __fma_rn(f.M[9], y, __fma_rn(f.M[10], z, f.M[11])));
+    // the bounds hold for either sign of the depth (the reference has no depth test: a point behind the image
+    // plane but in front of the LiDAR is projected like any other), as long as |q2| clears its own error
+    if (!coords_ok || !(fabs(q2) > f.e3x4)) return kAsk;
     const double r = fast_rcp(q2);
     const double tu = __dmul_rn(q0, r), tv = __dmul_rn(q1, r);
-    const double gu = __fma_rn(r, f.cgu, f.c0), gv = __fma_rn(r, f.cgv, f.c0);
-    if (!(gu < 0.25 && gv < 0.25)) return -1;
+    const double gu = __fma_rn(fabs(r), f.cgu, f.c0), gv = __fma_rn(fabs(r), f.cgv, f.c0);
+    if (!(gu < 0.25 && gv < 0.25)) return kAsk;
     // farther than 1 outside the image: dropped for certain (the guards are < 1/4)
-    if (!(tu > -2.0 && tu < f.img_wd + 1.0 && tv > -2.0 && tv < f.img_hd + 1.0)) return 0;
+    if (!(tu > -2.0 && tu < f.img_wd1 && tv > -2.0 && tv < f.img_hd1)) return kDrop;
     int ku, kv;
-    if (!certified_floor(tu, gu, ku) || !certified_floor(tv, gv, kv)) return -1;
-    if (ku < -1 || ku >= f.img_w || kv < -1 || kv >= f.img_h) return 0;
-    iu = ku < 0 ? 0 : ku;   // (-1, 0) truncates to 0
-    iv = kv < 0 ? 0 : kv;
-    return 1;
+    const bool su = certified_floor(tu, gu, ku), sv = certified_floor(tv, gv, kv);
+    if (!(su && sv)) return kAsk;
+    if (ku < -1 || ku >= f.img_w || kv < -1 || kv >= f.img_h) return kDrop;
+    return (max(kv, 0) << 16) | max(ku, 0);   // (-1, 0) truncates to 0
 }
 
 // Fast version of cell_xy: n = (x + off) - b0 exactly as the reference, then n * fl(1/res) instead of n / res
-// (they differ by at most 4 u |n / res|).  Returns 1 / 0 / -1 as above.
+// (they differ by at most 4 u |n / res| < 2^-19 for |n / res| < 2^31).  Returns the cell index, kDrop or kAsk.
 __device__ __forceinline__ int fast_cell(const GridParams& g, double x, double y, int& cx, int& cy) {
     const double nx = __dsub_rn(__dadd_rn(x, g.off_x), g.bx0);
     const double ny = __dsub_rn(__dadd_rn(y, g.off_y), g.by0);
     const double tx = __dmul_rn(nx, g.rinv), ty = __dmul_rn(ny, g.rinv);
-    if (!(tx > -2.0 && tx < (double)g.mh + 1.0 && ty > -2.0 && ty < (double)g.mw + 1.0))
-        return (tx == tx && ty == ty) ? 0 : -1;   // clearly off the grid; NaN: let the exact path decide
-    int kx, ky;
-    const double k50 = 8.8817841970012523e-16;  // 2^-50
-    if (!certified_floor(tx, __fma_rn(fabs(tx), k50, 1e-300), kx) || !certified_floor(ty, __fma_rn(fabs(ty), k50, 1e-300), ky))
-        return -1;
-    if (kx < -1 || kx >= g.mh || ky < -1 || ky >= g.mw) return 0;
-    cx = kx < 0 ? 0 : kx;
-    cy = ky < 0 ? 0 : ky;
-    return 1;
+    if (!(tx > -2.0 && tx < g.mh_d1 && ty > -2.0 && ty < g.mw_d1))
+        return (tx == tx && ty == ty) ? kDrop : kAsk;   // clearly off the grid; NaN: let the exact path decide
+    const double kGuard = 1.9073486328125e-06;          // 2^-19
+    const bool sx = certified_floor(tx, kGuard, cx), sy = certified_floor(ty, kGuard, cy);
+    if (!(sx && sy)) return kAsk;
+    if (cx < -1 || cx >= g.mh || cy < -1 || cy >= g.mw) return kDrop;
+    cx = max(cx, 0);
+    cy = max(cy, 0);
+    return 0;
 }
 
 template <int LAYOUT>

@@ -27,83 +27,72 @@ struct FrameBox {
 
 __device__ __forceinline__ void box_reset(int* b) { b[0] = 0x7fffffff; b[1] = -1; b[2] = 0x7fffffff; b[3] = -1; }
 
-// One frame of a batched launch.
-struct BatchFrame {
+// One frame = one launch of k_stream: every per-frame constant is then a kernel parameter at a fixed offset,
+// i.e. a constant-bank operand of the FP64 instructions (no register, no load).  A batched launch indexed by
+// blockIdx.y was tried: the run-time frame index turned every constant into a register-indexed LDC.
+struct StreamParams {
     FrameParams fp;
     const void* pts;
     const uint8_t* image;
     uint32_t* mask;       // this frame's mask slot (MH*MW words)
     int64_t n;
     int64_t ld;
-    uint32_t unit_begin;  // first work unit of this frame in the launch
-    uint32_t pad;
-};
-
-struct BatchParams {
-    int n_frames;
-    uint32_t n_units;
-    BatchFrame f[kMaxBatch];
 };
 
 // tuning knobs (overridable at compile time for the variant sweeps recorded in profiles/)
 #ifndef SMAP_STREAM_ROUND
 #define SMAP_STREAM_ROUND 4     // 32-point chunks per round: LDG.128 per lane in flight (x2 with the prefetch)
 #endif
-#ifndef SMAP_STREAM_ROUNDS
-#define SMAP_STREAM_ROUNDS 4    // rounds per work unit and warp
-#endif
 #ifndef SMAP_STREAM_MINB
 #define SMAP_STREAM_MINB 3      // resident blocks per SM the register allocation aims for
 #endif
 constexpr int kWarps = kThreads / 32;
 constexpr int kRound = SMAP_STREAM_ROUND;
-constexpr int kRounds = SMAP_STREAM_ROUNDS;
-constexpr int kRoundPts = 32 * kRound;
-constexpr int kWarpUnitPts = kRoundPts * kRounds;     // points of a unit owned by one warp
-constexpr int kUnitPts = kWarps * kWarpUnitPts;       // points per work unit (per block iteration)
+constexpr int kRoundPts = 32 * kRound;                // points a warp handles per round
+constexpr int kBlockRoundPts = kWarps * kRoundPts;    // points a block handles per round
 constexpr int kQueueCap = kRoundPts + 32;             // per-warp survivor stack: < 32 left over + one round
 
 template <int LAYOUT> struct QueueEntry { typedef float4 type; };
 template <> struct QueueEntry<1> { typedef uint32_t type; };
 
 // The reference's own rounding chain for one point; only reached when the certified fast path cannot decide.
-__device__ __noinline__ int exact_project_slow(const FrameParams* f, double x, double y, double z, int* iu, int* iv) {
-    int a, b;
-    const bool ok = project_point(*f, x, y, z, a, b);
-    *iu = a; *iv = b;
-    return ok ? 1 : 0;
+// Everything by value (a pointer to a caller's local would force it onto the stack in the hot loop).
+__device__ __noinline__ int exact_project_slow(const FrameParams* f, double x, double y, double z) {
+    int iu, iv;
+    if (!project_point(*f, x, y, z, iu, iv)) return kDrop;
+    return (iv << 16) | iu;
 }
 
-__device__ __noinline__ int exact_cell_slow(const GridParams* g, double x, double y, int* cx, int* cy) {
-    int a, b;
-    const bool ok = cell_xy(*g, x, y, a, b);
-    *cx = a; *cy = b;
-    return ok ? 1 : 0;
+__device__ __noinline__ long long exact_cell_slow(const GridParams* g, double x, double y) {
+    int cx, cy;
+    if (!cell_xy(*g, x, y, cx, cy)) return -1;
+    return ((long long)cx << 32) | (unsigned int)cy;
 }
 
 // ------------------------------------------------------------------------------------------------
 // K1+K2+K3a fused, persistent and warp-autonomous: project -> cull -> label lookup -> class bits -> cell ->
-// mask scatter for up to kMaxBatch frames per launch (src/mapping_replay.py:223-244, :261-277, :288-290).
+// mask scatter (src/mapping_replay.py:223-244, :261-277, :288-290).
 //
-// A block walks work units (kUnitPts consecutive points of one frame) round-robin; inside a unit every
-// warp owns a contiguous slice and never synchronises with the other warps:
+// One launch per frame (up to kMaxBatch frames, each with its own mask slot, are queued back to back before
+// one k_apply).  The blocks walk the cloud in rounds of kBlockRoundPts points; inside a round every warp owns
+// a contiguous slice and never synchronises with the other warps:
 //   stream   kRound coalesced LDG.128 per lane per round, the next round prefetched into registers before the
-//            current one is processed; float32 conservative cull (precull_pass); survivors (~35 %) pushed on
-//            the warp's private stack in shared memory (ballot + popc, no atomics);
+//            current one is processed; conservative float32 cull (precull_pass, constants straight from the
+//            parameter bank); survivors (~35 %)
+//            pushed on the warp's private stack in shared memory (ballot + popc, no atomics);
 //   drain    whenever >= 32 survivors are stacked, pop 32 - one per lane, all lanes busy: certified fast
 //            projection (exact fallback), label gather, class bits from the shared colour tables, certified
 //            fast cell index, one RED.OR into the frame's mask slot; lanes track the bounding box.
-// Stacks survive unit boundaries and are flushed (partial warps) only when the block moves to another frame.
 // ------------------------------------------------------------------------------------------------
 template <int LAYOUT>
 __global__ void __launch_bounds__(kThreads, SMAP_STREAM_MINB)
-k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridParams gp, FrameBox* __restrict__ boxes) {
+k_stream(const __grid_constant__ StreamParams F, const __grid_constant__ GridParams gp, FrameBox* __restrict__ box) {
     typedef typename QueueEntry<LAYOUT>::type Entry;
     __shared__ __align__(16) Entry s_queue[kWarps][kQueueCap];
     __shared__ uint32_t s_tab_r[256], s_tab_g[256];
-    __shared__ FrameParams s_fp;
     __shared__ int s_box[4];
 
+    const FrameParams& fp = F.fp;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -111,16 +100,17 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
 
     build_color_tables(gp, s_tab_r, s_tab_g);
     if (threadIdx.x == 0) box_reset(s_box);
+    __syncthreads();
+
+    const void* const f_pts = F.pts;
+    const uint8_t* const f_image = F.image;
+    uint32_t* const f_mask = F.mask;
+    const int64_t f_n = F.n, f_ld = F.ld;
+    // label image readable with aligned 32-bit loads (base aligned, size a multiple of 4)
+    const bool f_words = ((reinterpret_cast<uintptr_t>(f_image) & 3u) == 0u) && (((int64_t)fp.img_w * fp.img_h * 3) % 4 == 0);
 
     uint32_t qn = 0;       // entries on this warp's stack (warp-uniform)
     int bx0 = 0x7fffffff, bx1 = -1, by0 = 0x7fffffff, by1 = -1;
-
-    // frame-dependent values a lane keeps in registers
-    const void* f_pts = nullptr;
-    const uint8_t* f_image = nullptr;
-    uint32_t* f_mask = nullptr;
-    int64_t f_n = 0, f_ld = 0;
-    bool f_words = false;   // label image can be read with aligned 32-bit loads
 
     // ---- one batch of <= 32 stacked survivors, one per lane
     auto drain_batch = [&](uint32_t count) {
@@ -148,11 +138,10 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
         if (x == 1234.5) atomicOr(f_mask, (uint32_t)z);
         return;
 #endif
-        int iu = 0, iv = 0;
-        int vis = fast_project(s_fp, x, y, z, coords_ok, iu, iv);
-        if (vis < 0) vis = exact_project_slow(&s_fp, x, y, z, &iu, &iv);
-        if (!vis) return;
-        const uint32_t off = 3u * ((uint32_t)iv * (uint32_t)s_fp.img_w + (uint32_t)iu);
+        int pix = fast_project(fp, x, y, z, coords_ok);
+        if (pix == kAsk) pix = exact_project_slow(&fp, x, y, z);
+        if (pix < 0) return;
+        const uint32_t off = 3u * ((uint32_t)(pix >> 16) * (uint32_t)fp.img_w + (uint32_t)(pix & 0xffff));
         uint32_t r, g;
 #ifdef SMAP_ABL_NO_GATHER
         r = (off & 1u) ? 128u : 255u; g = (off & 1u) ? 64u : 255u;
@@ -160,9 +149,8 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
 #endif
         if (f_words) {
             // R and G sit in one aligned 32-bit word unless R is its last byte
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(f_image) + off;
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
-            const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+            const uint32_t sh = (off & 3u) * 8u;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(f_image) + (off >> 2);
             const uint32_t w0 = __ldg(wp);
             r = (w0 >> sh) & 0xffu;
             g = (sh == 24u) ? (__ldg(wp + 1) & 0xffu) : ((w0 >> (sh + 8u)) & 0xffu);
@@ -173,9 +161,14 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
         const uint32_t bits = class_bits_lut(gp, s_tab_r, s_tab_g, (uint8_t)r, (uint8_t)g, it);
         if (!bits) return;
         int cx = 0, cy = 0;
-        int on = fast_cell(gp, x, y, cx, cy);
-        if (on < 0) on = exact_cell_slow(&gp, x, y, &cx, &cy);
-        if (!on) return;
+        const int on = fast_cell(gp, x, y, cx, cy);
+        if (on == kAsk) {
+            const long long c2 = exact_cell_slow(&gp, x, y);
+            if (c2 < 0) return;
+            cx = (int)(c2 >> 32); cy = (int)(c2 & 0xffffffffll);
+        } else if (on == kDrop) {
+            return;
+        }
 #ifdef SMAP_ABL_NO_SCATTER
         if (cx == 0x7ffffff0) atomicOr(f_mask, bits);
         return;
@@ -184,120 +177,53 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
         bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
     };
 
-    // ---- work cursor: (unit, round) pairs, identical for all warps of the block
-    struct Cursor { uint32_t unit; int rd; int fi; };
-    auto frame_of = [&](uint32_t unit, int fi) {
-        while (fi + 1 < bp.n_frames && unit >= bp.f[fi + 1].unit_begin) ++fi;
-        return fi;
-    };
-    auto advance = [&](Cursor c) {
-        if (c.rd + 1 < kRounds) { c.rd += 1; return c; }
-        c.rd = 0; c.unit += gridDim.x;
-        if (c.unit < bp.n_units) c.fi = frame_of(c.unit, c.fi);
-        return c;
-    };
-    auto round_base = [&](const Cursor& c) {
-        return (int64_t)(c.unit - bp.f[c.fi].unit_begin) * kUnitPts + (int64_t)warp * kWarpUnitPts + (int64_t)c.rd * kRoundPts;
-    };
-    auto fetch = [&](const Cursor& c, float4 (&buf)[kRound]) {   // LAYOUT 0 only
+    // rounds of this block: r = blockIdx.x, blockIdx.x + gridDim.x, ...; this warp's slice of round r starts at
+    // r * kBlockRoundPts + warp * kRoundPts
+    const int64_t stride = (int64_t)gridDim.x * kBlockRoundPts;
+    int64_t rbase = (int64_t)blockIdx.x * kBlockRoundPts + (int64_t)warp * kRoundPts;
+
+    float4 buf[kRound];
+    if constexpr (LAYOUT == 0) {
         const float4* p4 = reinterpret_cast<const float4*>(f_pts);
-        const int64_t rbase = round_base(c);
 #pragma unroll
         for (int j = 0; j < kRound; ++j) {
             const int64_t k = rbase + j * 32 + lane;
             buf[j] = (k < f_n) ? __ldcs(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    };
-    auto enter_frame = [&](int fi) {   // all threads of the block; ends with the new constants visible
-        const BatchFrame& F = bp.f[fi];
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&F.fp);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_fp);
-        for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x) dst[i] = src[i];
-        f_pts = F.pts; f_image = F.image; f_mask = F.mask; f_n = F.n; f_ld = F.ld;
-        f_words = ((reinterpret_cast<uintptr_t>(F.image) & 3u) == 0u) && (((int64_t)F.fp.img_w * F.fp.img_h * 3) % 4 == 0);
-        __syncthreads();
-    };
-    auto leave_frame = [&](int fi) {   // flush the stacks and the bounding box of frame fi
-        while (qn) {
-            drain_batch(qn < 32u ? qn : 32u);
-            __syncwarp();
-        }
-        const bool any = bx1 >= bx0;
-        if (__any_sync(0xffffffffu, any)) {
-            const int a = __reduce_min_sync(0xffffffffu, bx0), b = __reduce_max_sync(0xffffffffu, bx1);
-            const int c = __reduce_min_sync(0xffffffffu, by0), d = __reduce_max_sync(0xffffffffu, by1);
-            if (lane == 0) {
-                atomicMin(&s_box[0], a); atomicMax(&s_box[1], b);
-                atomicMin(&s_box[2], c); atomicMax(&s_box[3], d);
-            }
-        }
-        bx0 = 0x7fffffff; bx1 = -1; by0 = 0x7fffffff; by1 = -1;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (s_box[1] >= s_box[0]) {
-                FrameBox* gb = boxes + fi;
-                atomicMin(&gb->x0, s_box[0]); atomicMax(&gb->x1, s_box[1]);
-                atomicMin(&gb->y0, s_box[2]); atomicMax(&gb->y1, s_box[3]);
-            }
-            box_reset(s_box);
-        }
-        // the next enter_frame's barrier orders this against later s_box / s_fp use
-    };
-
-    Cursor cur;
-    cur.unit = blockIdx.x; cur.rd = 0; cur.fi = 0;
-    if (cur.unit >= bp.n_units) return;
-    cur.fi = frame_of(cur.unit, 0);
-    __syncthreads();   // colour tables, s_box
-    enter_frame(cur.fi);
-
-    float4 buf[kRound];
-    if constexpr (LAYOUT == 0) fetch(cur, buf);
-
-    while (true) {
-        const Cursor nxt = advance(cur);
-        const bool has_next = nxt.unit < bp.n_units;
-        const bool same_frame = has_next && nxt.fi == cur.fi;
+    }
+    while (rbase < f_n) {
+        const int64_t nbase = rbase + stride;
         float4 pre[kRound];
-        if constexpr (LAYOUT == 0) {
-            if (same_frame) fetch(nxt, pre);   // in flight while this round is processed
-        }
-
-        // ---- cull the current round
-        {
-            CullConsts kc;
+        if constexpr (LAYOUT == 0) {   // next round in flight while this one is processed
+            const float4* p4 = reinterpret_cast<const float4*>(f_pts);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) kc.m[i] = s_fp.Mf[i];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                kc.ea[i] = s_fp.Ea[i];
-                kc.eb[i] = s_fp.Eb[i];
+            for (int j = 0; j < kRound; ++j) {
+                const int64_t k = nbase + j * 32 + lane;
+                pre[j] = (k < f_n) ? __ldcs(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            kc.range_hi = s_fp.range_hi;
-            kc.wf = s_fp.img_wf;
-            kc.hf = s_fp.img_hf;
-            const int64_t rbase = round_base(cur);
-            if constexpr (LAYOUT == 0) {
+        }
+        if constexpr (LAYOUT == 0) {
 #pragma unroll
-                for (int j = 0; j < kRound; ++j) {
-                    const int64_t k = rbase + j * 32 + lane;
-                    const bool pass = (k < f_n) & precull_pass(kc, buf[j].x, buf[j].y, buf[j].z);
-                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                    if (pass) *reinterpret_cast<float4*>(&queue[qn + __popc(ballot & lt_mask)]) = buf[j];
-                    qn += __popc(ballot);
-                }
-            } else {
-                const double* pd = reinterpret_cast<const double*>(f_pts);
+            for (int j = 0; j < kRound; ++j) {
+                const int64_t k = rbase + j * 32 + lane;
+                const float4 w = buf[j];
+                const bool pass = (k < f_n) & precull_pass_packed(fp, w.x, w.y, w.z);
+                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                if (pass) *reinterpret_cast<float4*>(&queue[qn + __popc(ballot & lt_mask)]) = w;
+                qn += __popc(ballot);
+            }
+        } else {
+            const double* pd = reinterpret_cast<const double*>(f_pts);
 #pragma unroll 2
-                for (int j = 0; j < kRound; ++j) {
-                    const int64_t k = rbase + j * 32 + lane;
-                    bool pass = false;
-                    if (k < f_n)
-                        pass = precull_pass(kc, (float)__ldg(pd + k), (float)__ldg(pd + f_ld + k), (float)__ldg(pd + 2 * f_ld + k));
-                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                    if (pass) *reinterpret_cast<uint32_t*>(&queue[qn + __popc(ballot & lt_mask)]) = (uint32_t)k;
-                    qn += __popc(ballot);
+            for (int j = 0; j < kRound; ++j) {
+                const int64_t k = rbase + j * 32 + lane;
+                bool pass = false;
+                if (k < f_n) {
+                    pass = precull_pass(fp, (float)__ldg(pd + k), (float)__ldg(pd + f_ld + k), (float)__ldg(pd + 2 * f_ld + k));
                 }
+                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                if (pass) *reinterpret_cast<uint32_t*>(&queue[qn + __popc(ballot & lt_mask)]) = (uint32_t)k;
+                qn += __popc(ballot);
             }
         }
         __syncwarp();
@@ -305,19 +231,30 @@ k_stream(const __grid_constant__ BatchParams bp, const __grid_constant__ GridPar
             drain_batch(32u);
             __syncwarp();
         }
-        if (!has_next) break;
-        if (!same_frame) {   // block-uniform
-            leave_frame(cur.fi);
-            enter_frame(nxt.fi);
-            if constexpr (LAYOUT == 0) fetch(nxt, pre);
-        }
         if constexpr (LAYOUT == 0) {
 #pragma unroll
             for (int j = 0; j < kRound; ++j) buf[j] = pre[j];
         }
-        cur = nxt;
+        rbase = nbase;
     }
-    leave_frame(cur.fi);
+    while (qn) {
+        drain_batch(qn < 32u ? qn : 32u);
+        __syncwarp();
+    }
+    // fold the lanes' bounding boxes: warp -> block (shared atomics) -> frame (4 global atomics per block)
+    if (__any_sync(0xffffffffu, bx1 >= bx0)) {
+        const int a = __reduce_min_sync(0xffffffffu, bx0), b = __reduce_max_sync(0xffffffffu, bx1);
+        const int c = __reduce_min_sync(0xffffffffu, by0), d = __reduce_max_sync(0xffffffffu, by1);
+        if (lane == 0) {
+            atomicMin(&s_box[0], a); atomicMax(&s_box[1], b);
+            atomicMin(&s_box[2], c); atomicMax(&s_box[3], d);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_box[1] >= s_box[0]) {
+        atomicMin(&box->x0, s_box[0]); atomicMax(&box->x1, s_box[1]);
+        atomicMin(&box->y0, s_box[2]); atomicMax(&box->y1, s_box[3]);
+    }
 }
 
 // Parity kernel for update_map (src/mapping_replay.py:261-277,:288-290): the scatter half from an already
@@ -360,7 +297,7 @@ struct ApplyParams {
     uint32_t* mask[kMaxBatch];
 };
 
-template <int NJ>
+template <int NJ, bool IDENTITY>
 __global__ void __launch_bounds__(kThreads)
 k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameBox* __restrict__ boxes,
         FrameBox* __restrict__ next_boxes, unsigned long long* __restrict__ touched_total,
@@ -388,42 +325,50 @@ k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameB
     unsigned int mine = 0;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t rr = (uint32_t)(t / ncols), cc = (uint32_t)(t - (uint64_t)rr * ncols);
-        const int cx = x0 + (int)rr, cy = y0 + (int)cc;
-        const uint32_t cell = (uint32_t)cx * (uint32_t)mw + (uint32_t)cy;
-        // pass 1: is the cell touched by any frame of the batch?  (independent coalesced loads)
-        uint32_t any = 0;
+        const uint32_t cell = (uint32_t)(x0 + (int)rr) * (uint32_t)mw + (uint32_t)(y0 + (int)cc);
+        // pass 1: which frames of the batch touched the cell?  Independent, coalesced loads; a slot is all
+        // zero outside its own frame's box, so no per-frame box test is needed inside the union.
+        uint32_t hit = 0;
 #pragma unroll
-        for (int f = 0; f < kMaxBatch; ++f) {
-            if (f < ap.n_frames && cx >= s_boxes[f].x0 && cx <= s_boxes[f].x1 && cy >= s_boxes[f].y0 && cy <= s_boxes[f].y1)
-                any |= __ldcg(ap.mask[f] + cell);
-        }
-        if (!any) continue;
-        // pass 2: replay the frames in order on the row held in registers
+        for (int f = 0; f < kMaxBatch; ++f)
+            if (f < ap.n_frames) hit |= (__ldcg(ap.mask[f] + cell) != 0u) ? (1u << f) : 0u;
+        if (!hit) continue;
+        // pass 2: replay those frames in order on the row held in registers
         double* row = map + (size_t)cell * c;
         double acc[8 * NJ];
 #pragma unroll
         for (int j = 0; j < 8 * NJ; ++j) acc[j] = (j < c) ? row[j] : 0.0;
-#pragma unroll 1
-        for (int f = 0; f < ap.n_frames; ++f) {
-            if (!(cx >= s_boxes[f].x0 && cx <= s_boxes[f].x1 && cy >= s_boxes[f].y0 && cy <= s_boxes[f].y1)) continue;
+        while (hit) {
+            const int f = __ffs(hit) - 1;
+            hit &= hit - 1u;
             uint32_t* wp = ap.mask[f] + cell;
-            const uint32_t w = __ldcg(wp);
-            if (!w) continue;
-            ++mine;
+            const uint32_t w = *wp;
             *wp = 0u;
-#pragma unroll 1
-            for (int i = 0; i < c; ++i) {
-                if (!((w >> i) & 1u)) continue;
-                const double* col = s_cm + i * c;
+            ++mine;
+            if (IDENTITY) {   // CM = np.eye(C): column i is the unit vector e_i (adding its zeros changes nothing)
 #pragma unroll
                 for (int j = 0; j < 8 * NJ; ++j)
-                    if (j < c) acc[j] = __dadd_rn(acc[j], col[j]);
-                if (i == lane_cls && (w & boost)) {
-                    // written with a bit test per (compile-time) j so that acc[] is never indexed dynamically
+                    if ((w >> j) & 1u & (j < c)) acc[j] = __dadd_rn(acc[j], 1.0);
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < c; ++i) {
+                    if (!((w >> i) & 1u)) continue;
+                    const double* col = s_cm + i * c;
 #pragma unroll
                     for (int j = 0; j < 8 * NJ; ++j)
-                        if ((lane_bit >> j) & 1u) acc[j] = __dadd_rn(acc[j], 2.0);
+                        if (j < c) acc[j] = __dadd_rn(acc[j], col[j]);
+                    if (i == lane_cls && (w & boost)) {
+                        // written with a bit test per (compile-time) j so that acc[] is never indexed dynamically
+#pragma unroll
+                        for (int j = 0; j < 8 * NJ; ++j)
+                            if ((lane_bit >> j) & 1u) acc[j] = __dadd_rn(acc[j], 2.0);
+                    }
                 }
+            }
+            if (IDENTITY && (w & boost) && (w & lane_bit)) {
+#pragma unroll
+                for (int j = 0; j < 8 * NJ; ++j)
+                    if ((lane_bit >> j) & 1u) acc[j] = __dadd_rn(acc[j], 2.0);
             }
         }
 #pragma unroll
