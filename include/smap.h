@@ -68,6 +68,8 @@ typedef struct smap_config {
     double origin_offset_y;  /* 562.84814453125 */
     double range_max;        /* cfg.MAPPING.PCD.RANGE_MAX */
     void *map_dev;           /* caller-owned grid (MH*MW*C doubles) or NULL: the handle allocates it */
+    int32_t map_is_zero;     /* caller-owned grid is all zeros right now (enables the atomic count update, below) */
+    int32_t reserved;
 } smap_config;
 
 /* One frame of the batched fused path. */
@@ -133,7 +135,12 @@ SMAP_API int smap_update(smap_handle *h, double *map_dev, const double *pcd_dev,
  * (src/mapping_replay.py:184-192 loop body).  Bit-exact with the reference for any update matrix (count or
  * log-likelihood): a streaming kernel ORs the frame's class bits into a per-frame cell mask (the per-frame
  * (cell, class) de-duplication), a second kernel adds the matrix columns to the touched cells in ascending
- * class order and clears the mask. */
+ * class order and clears the mask.
+ * Count update shortcut: when the matrix is exactly np.eye(C) AND the grid is known to hold integer-valued
+ * counts (zero-initialised -- by the handle, by smap_clear, or declared with cfg.map_is_zero -- and since then
+ * only updated by count updates of this handle), the streaming kernel adds 1.0 per newly observed (cell, class)
+ * and 2.0 per lane boost with float64 atomics: sums of small integers, exact in any order, so the result is
+ * the same bits.  smap_upload / smap_notify_map_modified switch back to the ordered update. */
 SMAP_API int smap_integrate(smap_handle *h, const smap_frame *frame, void *stream);
 
 /* Same rule for n_frames frames IN ORDER.  Up to 16 frames share one pair of launches: each frame scatters
@@ -164,6 +171,9 @@ SMAP_API int smap_render_thresholds(const double *map_dev, int mh, int mw, int c
 /* ---- grid access ------------------------------------------------------------------------------- */
 SMAP_API int smap_map_ptr(smap_handle *h, double **map_dev, int64_t *n_elements);
 SMAP_API int smap_clear(smap_handle *h, void *stream);            /* self.map = np.zeros(...)  src/mapping_replay.py:181 */
+/* The caller wrote into the grid through its own pointer (map_dev / smap_map_ptr): the grid may no longer hold
+ * integer-valued counts, use the ordered update from now on. */
+SMAP_API int smap_notify_map_modified(smap_handle *h);
 SMAP_API int smap_download(smap_handle *h, double *map_host);     /* synchronises */
 SMAP_API int smap_upload(smap_handle *h, const double *map_host); /* synchronises */
 SMAP_API int smap_get_stats(smap_handle *h, smap_stats *out);     /* synchronises the handle's last stream */

@@ -26,10 +26,14 @@ def dev(a):
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-@pytest.mark.parametrize("layout", ["f32x4", "f64soa"])
-def test_fused_path_matches_reference_golden(name, layout):
+@pytest.mark.parametrize("layout,ordered", [("f32x4", False), ("f64soa", False), ("f32x4", True)])
+def test_fused_path_matches_reference_golden(name, layout, ordered):
+    """ordered=True forces the two-kernel ordered update also for the count update (which otherwise adds its
+    increments with float64 atomics when the grid holds integer counts)."""
     case = Case(name)
     dm = make_mapper(case)
+    if ordered:
+        dm.notify_map_modified()
     for f, out in enumerate(case.spec["frames_out"]):
         pcd, points, image, T = case.frame(f)
         cloud = dev(points) if layout == "f32x4" else dev(pcd)
@@ -123,8 +127,9 @@ def test_filter_borders(shape):
     assert np.array_equal(renderer.apply_filter(dev(src)).cpu().numpy(), c_oracle.apply_filter(src))
 
 
-@pytest.mark.parametrize("full19,log_cm", [(False, False), (True, False), (True, True)])
-def test_full_size_frame_against_oracle(full19, log_cm):
+@pytest.mark.parametrize("full19,log_cm,ordered", [(False, False, False), (True, False, False), (True, False, True),
+                                                  (True, True, True)])
+def test_full_size_frame_against_oracle(full19, log_cm, ordered):
     """BASELINE.json configs[1] shape: 2M-point cloud + 1920x1440 frame, checked in full against the oracle,
     plus size-independent properties (linearity of the count grid in the number of replays)."""
     labels, names, colors = syn.class_setup(full19)
@@ -138,6 +143,8 @@ def test_full_size_frame_against_oracle(full19, log_cm):
     boundary, res, mh, mw = [[100, 300], [800, 1000]], 0.1, 2000, 2000
     lane = names.index("lane")
     dm = DeviceMapper(mh, mw, colors, cm, boundary, res, 100.0, True, lane, cameras=[cam], device=0)
+    if ordered:
+        dm.notify_map_modified()
     ref = np.zeros((mh, mw, c))
     for f in range(2):
         fr = syn.synthetic_frame(1000, f, 2000000, blocky=(f == 1))
@@ -186,12 +193,15 @@ def _oracle_grid(case, frames):
     return ref
 
 
-@pytest.mark.parametrize("name", ["cfg1_c5_count", "cfg1_c19_count", "cfg1_c19_log"])
-def test_batched_launch_equals_sequential_frames(name):
+@pytest.mark.parametrize("name,ordered", [("cfg1_c5_count", False), ("cfg1_c19_count", False), ("cfg1_c19_count", True),
+                                          ("cfg1_c19_log", True)])
+def test_batched_launch_equals_sequential_frames(name, ordered):
     """Up to 16 frames share one launch (one mask slot each); repeating a frame inside a batch must count it
     twice, and 37 frames exercise full batches plus a ragged tail."""
     case = Case(name)
     dm = make_mapper(case)
+    if ordered:
+        dm.notify_map_modified()
     base = [case.frame(f) for f in range(3)]
     order = [0, 1, 2, 2, 0, 1, 1] * 5 + [2, 0]
     frames_dev, keep = [], []

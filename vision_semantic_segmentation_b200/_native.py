@@ -19,7 +19,7 @@ EXPORTS = [
     "smap_abi_version", "smap_last_error", "smap_device_count", "smap_device_info", "smap_create",
     "smap_destroy", "smap_set_camera", "smap_set_classes", "smap_project", "smap_update", "smap_integrate",
     "smap_integrate_batch", "smap_integrate_host", "smap_apply_filter", "smap_render", "smap_filter_render",
-    "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_download", "smap_upload", "smap_get_stats",
+    "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_notify_map_modified", "smap_download", "smap_upload", "smap_get_stats",
 ]
 
 
@@ -29,7 +29,7 @@ class SmapConfig(ctypes.Structure):
         ("use_intensity", ctypes.c_int32), ("lane_index", ctypes.c_int32), ("device", ctypes.c_int32),
         ("boundary_x_min", ctypes.c_double), ("boundary_y_min", ctypes.c_double), ("resolution", ctypes.c_double),
         ("origin_offset_x", ctypes.c_double), ("origin_offset_y", ctypes.c_double), ("range_max", ctypes.c_double),
-        ("map_dev", ctypes.c_void_p),
+        ("map_dev", ctypes.c_void_p), ("map_is_zero", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 
@@ -105,6 +105,8 @@ def load():
     L.smap_map_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     L.smap_clear.restype = i32
     L.smap_clear.argtypes = [vp, vp]
+    L.smap_notify_map_modified.restype = i32
+    L.smap_notify_map_modified.argtypes = [vp]
     L.smap_download.restype = i32
     L.smap_download.argtypes = [vp, vp]
     L.smap_upload.restype = i32

@@ -10,6 +10,10 @@
 #include "../../include/smap.h"
 #include "smap_kernels.cuh"
 
+#ifndef SMAP_AUX_STREAMS
+#define SMAP_AUX_STREAMS 2
+#endif
+
 using namespace smap;
 
 namespace {
@@ -55,12 +59,20 @@ struct smap_handle {
     // per-frame cell masks: n_slots slots of `cells` words, all zero between launches
     uint32_t* mask = nullptr;
     int n_slots = 0;
+    int64_t slot_words = 0;   // cells rounded up to a multiple of 4: k_apply reads the slots with 16-byte loads
     // double-buffered per-slot bounding boxes + touched counters (k_stream writes [parity], k_apply resets [parity^1])
     FrameBox* boxes = nullptr;                // [2][kMaxBatch]
     unsigned long long* touched = nullptr;    // [2]
     int parity = 0;
     int sm_count = 148;
-    bool identity_cm = false;   // update matrix is exactly np.eye(C): k_apply adds unit vectors
+    bool identity_cm = false;   // update matrix is exactly np.eye(C): the count update
+    bool integer_grid = false;  // the grid is known to hold integer-valued counts (zeroed by us, then only count updates)
+    // k_stream launches of one batch alternate over a few internal streams (fork / join with events around the
+    // batch): the frames are independent, so the ramp-up and tail of one launch overlap the next one's body
+    static constexpr int kAux = SMAP_AUX_STREAMS;
+    cudaStream_t aux[kAux > 0 ? kAux : 1] = {};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[kAux > 0 ? kAux : 1] = {};
     // class tables
     double* cm_dev = nullptr;
     uint8_t colors[SMAP_MAX_CLASSES * 3];
@@ -194,7 +206,7 @@ int ensure_scratch(smap_handle* h, int64_t n) {
 int ensure_slots(smap_handle* h, int want) {
     if (want <= h->n_slots) return SMAP_OK;
     uint32_t* fresh = nullptr;
-    const size_t slot_bytes = sizeof(uint32_t) * (size_t)h->cells;
+    const size_t slot_bytes = sizeof(uint32_t) * (size_t)h->slot_words;
     CK(cudaDeviceSynchronize());
     CK(cudaMalloc(&fresh, slot_bytes * want));
     CK(cudaMemset(fresh, 0, slot_bytes * want));
@@ -208,12 +220,12 @@ int ensure_slots(smap_handle* h, int want) {
 }
 
 // K3b launch: ordered apply of the `n_slots_used` mask slots whose boxes are boxes[parity]; flips parity.
-int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st) {
+int launch_apply(smap_handle* h, double* map, int n_slots_used, bool clear_only, cudaStream_t st) {
     const int c = h->cfg.num_classes;
     ApplyParams ap;
     memset(&ap, 0, sizeof ap);
     ap.n_frames = n_slots_used;
-    for (int i = 0; i < n_slots_used; ++i) ap.mask[i] = h->mask + (size_t)i * h->cells;
+    for (int i = 0; i < n_slots_used; ++i) ap.mask[i] = h->mask + (size_t)i * h->slot_words;
     const size_t smem = sizeof(double) * c * c;
     FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch;
     FrameBox* next_boxes = h->boxes + (size_t)(h->parity ^ 1) * kMaxBatch;
@@ -223,7 +235,7 @@ int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st)
     const int lane = h->cfg.lane_index, mw = h->cfg.map_width;
 #define SMAP_LAUNCH_APPLY(NJ)                                                                                          \
     do {                                                                                                              \
-        if (h->identity_cm) k_apply<NJ, true><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw); \
+        if (clear_only) k_apply<1, true><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw); \
         else k_apply<NJ, false><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw); \
     } while (0)
     if (c <= 8) SMAP_LAUNCH_APPLY(1);
@@ -239,18 +251,33 @@ int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st)
 
 // Queue one k_stream launch per non-empty frame; frame i of the non-empty ones scatters into mask slot i.
 // Returns the number of slots used in *slots_used.
-int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, cudaStream_t st,
-                  int* slots_used) {
+int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, bool count_atomics,
+                  cudaStream_t st, int* slots_used) {
     const int layout = frames[0].layout;
     int used = 0;
+    int n_nonempty = 0;
+    for (int i = 0; i < n_frames; ++i) n_nonempty += frames[i].n_points > 0;
+    const bool fork = smap_handle::kAux > 0 && n_nonempty > 1;
+    if (fork) {
+        if (!h->ev_fork) {
+            CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            for (int a = 0; a < smap_handle::kAux; ++a) {
+                CK(cudaStreamCreateWithFlags(&h->aux[a], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming));
+            }
+        }
+        CK(cudaEventRecord(h->ev_fork, st));
+        for (int a = 0; a < smap_handle::kAux; ++a) CK(cudaStreamWaitEvent(h->aux[a], h->ev_fork, 0));
+    }
     for (int i = 0; i < n_frames; ++i) {
         if (frames[i].n_points == 0) continue;
         if (frames[i].layout != layout) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
+        cudaStream_t ls = fork ? h->aux[used % smap_handle::kAux] : st;
         StreamParams sp;
         sp.fp = fps[i];
         sp.pts = frames[i].points_dev;
         sp.image = frames[i].image_dev;
-        sp.mask = h->mask + (size_t)used * h->cells;
+        sp.mask = h->mask + (size_t)used * h->slot_words;
         sp.n = frames[i].n_points;
         sp.ld = frames[i].ld;
         // persistent grid: as many blocks as stay resident, never more than the cloud has rounds
@@ -258,11 +285,22 @@ int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* f
         const int64_t rounds = ceil_div(sp.n, kBlockRoundPts);
         if (grid > rounds) grid = rounds;
         FrameBox* box = h->boxes + (size_t)h->parity * kMaxBatch + used;
-        if (layout == SMAP_PTS_F32X4) k_stream<SMAP_PTS_F32X4><<<(unsigned)grid, kThreads, 0, st>>>(sp, h->gp, box);
-        else k_stream<SMAP_PTS_F64_SOA><<<(unsigned)grid, kThreads, 0, st>>>(sp, h->gp, box);
+        if (layout == SMAP_PTS_F32X4) {
+            if (count_atomics) k_stream<SMAP_PTS_F32X4, 1><<<(unsigned)grid, kThreads, 0, ls>>>(sp, h->gp, box, h->map);
+            else k_stream<SMAP_PTS_F32X4, 0><<<(unsigned)grid, kThreads, 0, ls>>>(sp, h->gp, box, h->map);
+        } else {
+            if (count_atomics) k_stream<SMAP_PTS_F64_SOA, 1><<<(unsigned)grid, kThreads, 0, ls>>>(sp, h->gp, box, h->map);
+            else k_stream<SMAP_PTS_F64_SOA, 0><<<(unsigned)grid, kThreads, 0, ls>>>(sp, h->gp, box, h->map);
+        }
         CK(cudaGetLastError());
         h->stats.kernel_launches += 1;
         ++used;
+    }
+    if (fork) {
+        for (int a = 0; a < smap_handle::kAux; ++a) {
+            CK(cudaEventRecord(h->ev_join[a], h->aux[a]));
+            CK(cudaStreamWaitEvent(st, h->ev_join[a], 0));
+        }
     }
     *slots_used = used;
     return SMAP_OK;
@@ -358,12 +396,15 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     cudaError_t e = cudaSuccess;
     if (cfg->map_dev) {
         h->map = static_cast<double*>(cfg->map_dev);
+        h->integer_grid = cfg->map_is_zero != 0;
     } else {
         e = cudaMalloc(&h->map, map_bytes);
         if (e == cudaSuccess) { h->own_map = true; e = cudaMemset(h->map, 0, map_bytes); }
+        h->integer_grid = true;
     }
-    if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->cells);
-    if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->cells);
+    h->slot_words = (h->cells + 3) / 4 * 4;
+    if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->slot_words);
+    if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->slot_words);
     if (e == cudaSuccess) h->n_slots = 1;
     if (e == cudaSuccess) e = cudaMalloc(&h->boxes, sizeof(FrameBox) * 2 * kMaxBatch);
     if (e == cudaSuccess) {
@@ -394,6 +435,13 @@ int smap_destroy(smap_handle* h) {
     if (h->own_map) cudaFree(h->map);
     cudaFree(h->mask); cudaFree(h->boxes); cudaFree(h->touched); cudaFree(h->cm_dev); cudaFree(h->total_dev);
     cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
+    if (h->ev_fork) {
+        cudaEventDestroy(h->ev_fork);
+        for (int a = 0; a < smap_handle::kAux; ++a) {
+            cudaEventDestroy(h->ev_join[a]);
+            cudaStreamDestroy(h->aux[a]);
+        }
+    }
     for (int i = 0; i < smap_handle::kStages; ++i) {
         cudaFree(h->stage_pts[i]);
         cudaFree(h->stage_img[i]);
@@ -483,7 +531,8 @@ int smap_update(smap_handle* h, double* map_dev, const double* pcd, int64_t ld, 
     CK(cudaGetLastError());
     h->stats.kernel_launches += 1;
     h->last_stream = st;
-    return launch_apply(h, map_dev ? map_dev : h->map, 1, st);
+    if (!map_dev || map_dev == h->map) h->integer_grid = h->integer_grid && h->identity_cm;
+    return launch_apply(h, map_dev ? map_dev : h->map, 1, false, st);
 }
 
 int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames, void* stream) {
@@ -502,10 +551,14 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
             h->stats.frames += 1;
             h->stats.points += frames[begin + i].n_points;
         }
+        // the count update on a grid of integer-valued counts may add its increments with float64 atomics (exact
+        // in any order); everything else goes through the ordered apply
+        const bool count_atomics = h->identity_cm && h->integer_grid;
+        if (!h->identity_cm) h->integer_grid = false;
         int rc = ensure_slots(h, chunk);
         int used = 0;
-        if (!rc) rc = launch_stream(h, frames + begin, fps, chunk, st, &used);
-        if (!rc && used > 0) rc = launch_apply(h, h->map, used, st);
+        if (!rc) rc = launch_stream(h, frames + begin, fps, chunk, count_atomics, st, &used);
+        if (!rc && used > 0) rc = launch_apply(h, h->map, used, count_atomics, st);
         if (rc) return rc;
         begin += chunk;
     }
@@ -618,7 +671,14 @@ int smap_clear(smap_handle* h, void* stream) {
     CK(cudaMemsetAsync(h->map, 0, sizeof(double) * (size_t)h->cells * h->cfg.num_classes, static_cast<cudaStream_t>(stream)));
     h->stats.frames = 0;
     h->stats.points = 0;
+    h->integer_grid = true;
     h->last_stream = static_cast<cudaStream_t>(stream);
+    return SMAP_OK;
+}
+
+int smap_notify_map_modified(smap_handle* h) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    h->integer_grid = false;
     return SMAP_OK;
 }
 
@@ -635,6 +695,7 @@ int smap_upload(smap_handle* h, const double* map_host) {
     DeviceGuard guard(h->cfg.device);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h->map, map_host, sizeof(double) * (size_t)h->cells * h->cfg.num_classes, cudaMemcpyHostToDevice));
+    h->integer_grid = false;
     return SMAP_OK;
 }
 

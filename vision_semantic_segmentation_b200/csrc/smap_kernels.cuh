@@ -84,9 +84,15 @@ __device__ __noinline__ long long exact_cell_slow(const GridParams* g, double x,
 //            projection (exact fallback), label gather, class bits from the shared colour tables, certified
 //            fast cell index, one RED.OR into the frame's mask slot; lanes track the bounding box.
 // ------------------------------------------------------------------------------------------------
-template <int LAYOUT>
+// MODE 0: masks only -- k_apply adds the update-matrix columns in frame and class order (any matrix, any grid).
+// MODE 1: count update (matrix == np.eye(C)) on a grid that holds integer-valued counts: the atomicOr returns
+//         what the frame had already put in the cell, and every NEWLY set class bit adds 1.0 to map[cell, class]
+//         (a newly set boost bit 2.0 to map[cell, lane]) with a float64 RED.  Sums of small integers are exact in
+//         any order, so the grid is bit-identical to the ordered update; k_apply then only clears the masks.
+template <int LAYOUT, int MODE>
 __global__ void __launch_bounds__(kThreads, SMAP_STREAM_MINB)
-k_stream(const __grid_constant__ StreamParams F, const __grid_constant__ GridParams gp, FrameBox* __restrict__ box) {
+k_stream(const __grid_constant__ StreamParams F, const __grid_constant__ GridParams gp, FrameBox* __restrict__ box,
+         double* __restrict__ map) {
     typedef typename QueueEntry<LAYOUT>::type Entry;
     __shared__ __align__(16) Entry s_queue[kWarps][kQueueCap];
     __shared__ uint32_t s_tab_r[256], s_tab_g[256];
@@ -173,7 +179,22 @@ k_stream(const __grid_constant__ StreamParams F, const __grid_constant__ GridPar
         if (cx == 0x7ffffff0) atomicOr(f_mask, bits);
         return;
 #endif
-        atomicOr(f_mask + (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy, bits);   // result unused: RED.OR
+        const uint32_t cell = (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy;
+        if (MODE == 0) {
+            atomicOr(f_mask + cell, bits);   // result unused: RED.OR, nothing waits for it
+        } else {
+            uint32_t fresh = bits & ~atomicOr(f_mask + cell, bits);
+            double* row = map + (size_t)cell * gp.c;
+            if (fresh >> gp.c) {   // boost bit newly set: +2 on the lane class (src/mapping_replay.py:294)
+                atomicAdd(row + gp.lane, 2.0);
+                fresh &= (1u << gp.c) - 1u;
+            }
+            while (fresh) {
+                const int i = __ffs(fresh) - 1;
+                fresh &= fresh - 1u;
+                atomicAdd(row + i, 1.0);
+            }
+        }
         bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
     };
 
@@ -182,32 +203,35 @@ k_stream(const __grid_constant__ StreamParams F, const __grid_constant__ GridPar
     const int64_t stride = (int64_t)gridDim.x * kBlockRoundPts;
     int64_t rbase = (int64_t)blockIdx.x * kBlockRoundPts + (int64_t)warp * kRoundPts;
 
+    // a round that lies completely inside the cloud (all but the last one) needs no per-lane bounds checks
+    auto load_round = [&](int64_t base, float4 (&dst)[kRound]) {
+        const float4* p = reinterpret_cast<const float4*>(f_pts) + base + lane;
+        if (base + kRoundPts <= f_n) {
+#pragma unroll
+            for (int j = 0; j < kRound; ++j) dst[j] = __ldcs(p + j * 32);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kRound; ++j)
+                dst[j] = (base + j * 32 + lane < f_n) ? __ldcs(p + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
     float4 buf[kRound];
     if constexpr (LAYOUT == 0) {
-        const float4* p4 = reinterpret_cast<const float4*>(f_pts);
-#pragma unroll
-        for (int j = 0; j < kRound; ++j) {
-            const int64_t k = rbase + j * 32 + lane;
-            buf[j] = (k < f_n) ? __ldcs(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        if (rbase < f_n) load_round(rbase, buf);
     }
     while (rbase < f_n) {
         const int64_t nbase = rbase + stride;
         float4 pre[kRound];
         if constexpr (LAYOUT == 0) {   // next round in flight while this one is processed
-            const float4* p4 = reinterpret_cast<const float4*>(f_pts);
-#pragma unroll
-            for (int j = 0; j < kRound; ++j) {
-                const int64_t k = nbase + j * 32 + lane;
-                pre[j] = (k < f_n) ? __ldcs(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            if (nbase < f_n) load_round(nbase, pre);
         }
         if constexpr (LAYOUT == 0) {
+            const bool full = rbase + kRoundPts <= f_n;
 #pragma unroll
             for (int j = 0; j < kRound; ++j) {
-                const int64_t k = rbase + j * 32 + lane;
                 const float4 w = buf[j];
-                const bool pass = (k < f_n) & precull_pass_packed(fp, w.x, w.y, w.z);
+                bool pass = precull_pass_packed(fp, w.x, w.y, w.z);
+                if (!full) pass &= (rbase + j * 32 + lane < f_n);
                 const unsigned ballot = __ballot_sync(0xffffffffu, pass);
                 if (pass) *reinterpret_cast<float4*>(&queue[qn + __popc(ballot & lt_mask)]) = w;
                 qn += __popc(ballot);
@@ -284,12 +308,13 @@ k_update_scatter(const double* __restrict__ pcd, int64_t ld, const uint8_t* __re
 
 // ------------------------------------------------------------------------------------------------
 // K3b: ordered apply for up to kMaxBatch frame slots in one pass.
-// One thread per cell of the union of the frames' bounding boxes.  It reads the cell's word in every slot
-// whose box contains it (coalesced along the row), and if any is non-zero it loads the C-element grid row
-// once, replays the frames IN ORDER -- for each frame the classes in ascending order, "row += CM[:, i]" and
-// the lane boost, exactly the statements at src/mapping_replay.py:281 and :294 -- stores the row once and
-// zeroes the words.  Bit-exact for any update matrix; the grid row traffic is shared by all frames of the batch.
-// NJ = ceil(C / 8): the row lives in 8*NJ registers.
+// The union of the frames' bounding boxes is walked two horizontally adjacent cells per thread, so that a
+// thread reads the two mask words of a slot with ONE 8-byte load and only from the slots whose row span covers
+// the cell (a slot is all zero outside its own frame's box).  For each cell touched by any frame the C-element
+// grid row is loaded once, the frames are replayed IN ORDER -- for each frame the classes in ascending order,
+// "row += CM[:, i]" and the lane boost, exactly the statements at src/mapping_replay.py:281 and :294 -- the row
+// is stored once and the words are zeroed.  Bit-exact for any update matrix; the grid traffic is shared by
+// all frames of the batch.  NJ = ceil(C / 8).
 // ------------------------------------------------------------------------------------------------
 struct ApplyParams {
     int n_frames;
@@ -297,16 +322,40 @@ struct ApplyParams {
     uint32_t* mask[kMaxBatch];
 };
 
-template <int NJ, bool IDENTITY>
+template <int V> struct MaskVec;
+template <> struct MaskVec<4> { typedef uint4 type; };
+template <> struct MaskVec<2> { typedef uint2 type; };
+template <> struct MaskVec<1> { typedef uint32_t type; };
+
+template <int V> __device__ __forceinline__ void mask_vec_load(const uint32_t* p, uint32_t (&w)[V]);
+template <> __device__ __forceinline__ void mask_vec_load<4>(const uint32_t* p, uint32_t (&w)[4]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+}
+template <> __device__ __forceinline__ void mask_vec_load<2>(const uint32_t* p, uint32_t (&w)[2]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    w[0] = v.x; w[1] = v.y;
+}
+template <> __device__ __forceinline__ void mask_vec_load<1>(const uint32_t* p, uint32_t (&w)[1]) { w[0] = *p; }
+
+// CLEAR_ONLY: the grid was already updated by k_stream MODE 1; only count and zero the touched words.
+template <int NJ, bool CLEAR_ONLY>
 __global__ void __launch_bounds__(kThreads)
 k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameBox* __restrict__ boxes,
         FrameBox* __restrict__ next_boxes, unsigned long long* __restrict__ touched_total,
-        unsigned long long* __restrict__ next_touched_total, const double* __restrict__ cm, int c, int lane_cls, int mw) {
+        unsigned long long* __restrict__ next_touched_total, const double* __restrict__ cm, int c, int lane_cls,
+        int mw) {
+    constexpr int V = 2;
     extern __shared__ double s_cm[];  // C x C, transposed: s_cm[i * c + j] = cm[j * c + i] (column i contiguous)
     __shared__ FrameBox s_boxes[kMaxBatch];
     __shared__ unsigned int s_count;
     for (int e = threadIdx.x; e < c * c; e += blockDim.x) s_cm[(e % c) * c + e / c] = cm[e];
-    if (threadIdx.x < ap.n_frames) s_boxes[threadIdx.x] = boxes[threadIdx.x];
+    if (threadIdx.x < kMaxBatch) {
+        FrameBox b;
+        box_reset(&b.x0);
+        if (threadIdx.x < ap.n_frames) b = boxes[threadIdx.x];
+        s_boxes[threadIdx.x] = b;
+    }
     if (threadIdx.x == 0) s_count = 0;
     if (blockIdx.x == 0 && threadIdx.x < kMaxBatch) box_reset(&next_boxes[threadIdx.x].x0);
     if (blockIdx.x == 0 && threadIdx.x == 0) *next_touched_total = 0ull;
@@ -317,63 +366,87 @@ k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameB
         x0 = min(x0, s_boxes[f].x0); x1 = max(x1, s_boxes[f].x1);
         y0 = min(y0, s_boxes[f].y0); y1 = max(y1, s_boxes[f].y1);
     }
-    if (x1 < x0) return;   // block-uniform
-    const uint32_t ncols = (uint32_t)(y1 - y0 + 1);
-    const uint64_t total = (uint64_t)(x1 - x0 + 1) * ncols;
+    if (x1 < x0) return;   // block-uniform: nothing was touched
+    // a thread owns V = 2 horizontally adjacent cells whose linear index is even, so that the two words of a
+    // slot come with one 8-byte load; columns outside [y0, y1] that such a pair drags in are ignored
+    const uint32_t gcols = (uint32_t)(y1 - y0 + 1) / V + 2u;          // pairs per row, generous
+    const uint64_t total = (uint64_t)(x1 - x0 + 1) * gcols;
     const uint32_t boost = 1u << c;
     const uint32_t lane_bit = lane_cls >= 0 ? (1u << lane_cls) : 0u;
     unsigned int mine = 0;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t rr = (uint32_t)(t / ncols), cc = (uint32_t)(t - (uint64_t)rr * ncols);
-        const uint32_t cell = (uint32_t)(x0 + (int)rr) * (uint32_t)mw + (uint32_t)(y0 + (int)cc);
-        // pass 1: which frames of the batch touched the cell?  Independent, coalesced loads; a slot is all
-        // zero outside its own frame's box, so no per-frame box test is needed inside the union.
-        uint32_t hit = 0;
+        const uint32_t rr = (uint32_t)(t / gcols), gc = (uint32_t)(t - (uint64_t)rr * gcols);
+        const int cx = x0 + (int)rr;
+        const uint32_t row0 = (uint32_t)cx * (uint32_t)mw;
+        const uint32_t cell0 = ((row0 + (uint32_t)y0) & ~1u) + gc * V;   // even linear index
+        // valid cells of the pair: inside this row's [y0, y1]
+        bool valid[V];
+        bool anyvalid = false;
 #pragma unroll
-        for (int f = 0; f < kMaxBatch; ++f)
-            if (f < ap.n_frames) hit |= (__ldcg(ap.mask[f] + cell) != 0u) ? (1u << f) : 0u;
-        if (!hit) continue;
-        // pass 2: replay those frames in order on the row held in registers
-        double* row = map + (size_t)cell * c;
-        double acc[8 * NJ];
+        for (int v = 0; v < V; ++v) {
+            const uint32_t cell = cell0 + v;
+            valid[v] = cell >= row0 + (uint32_t)y0 && cell <= row0 + (uint32_t)y1;
+            anyvalid |= valid[v];
+        }
+        if (!anyvalid) continue;
+        // all mask words of the pair, every frame whose box covers it: up to 16 independent loads in flight
+        uint32_t w[kMaxBatch][V];
+        uint32_t any = 0;
 #pragma unroll
-        for (int j = 0; j < 8 * NJ; ++j) acc[j] = (j < c) ? row[j] : 0.0;
-        while (hit) {
-            const int f = __ffs(hit) - 1;
-            hit &= hit - 1u;
-            uint32_t* wp = ap.mask[f] + cell;
-            const uint32_t w = *wp;
-            *wp = 0u;
-            ++mine;
-            if (IDENTITY) {   // CM = np.eye(C): column i is the unit vector e_i (adding its zeros changes nothing)
+        for (int f = 0; f < kMaxBatch; ++f) {
 #pragma unroll
-                for (int j = 0; j < 8 * NJ; ++j)
-                    if ((w >> j) & 1u & (j < c)) acc[j] = __dadd_rn(acc[j], 1.0);
-            } else {
+            for (int v = 0; v < V; ++v) w[f][v] = 0;
+            if (f < ap.n_frames && cx >= s_boxes[f].x0 && cx <= s_boxes[f].x1) mask_vec_load<V>(ap.mask[f] + cell0, w[f]);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                if (!valid[v]) w[f][v] = 0;
+                any |= w[f][v];
+            }
+        }
+        if (!any) continue;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            uint32_t anyv = 0;
+#pragma unroll
+            for (int f = 0; f < kMaxBatch; ++f) anyv |= w[f][v];
+            if (!anyv) continue;
+            const uint32_t cell = cell0 + v;
+            if (CLEAR_ONLY) {
+#pragma unroll
+                for (int f = 0; f < kMaxBatch; ++f)
+                    if (w[f][v]) { ap.mask[f][cell] = 0u; ++mine; }
+                continue;
+            }
+            double* row = map + (size_t)cell * c;
+            double acc[8 * NJ];
+#pragma unroll
+            for (int j = 0; j < 8 * NJ; ++j) acc[j] = (j < c) ? row[j] : 0.0;
+            // replay the frames in order on the row held in registers
+#pragma unroll
+            for (int f = 0; f < kMaxBatch; ++f) {
+                const uint32_t wf = w[f][v];
+                if (!wf) continue;
+                ap.mask[f][cell] = 0u;
+                ++mine;
 #pragma unroll 1
                 for (int i = 0; i < c; ++i) {
-                    if (!((w >> i) & 1u)) continue;
+                    if (!((wf >> i) & 1u)) continue;
                     const double* col = s_cm + i * c;
 #pragma unroll
                     for (int j = 0; j < 8 * NJ; ++j)
                         if (j < c) acc[j] = __dadd_rn(acc[j], col[j]);
-                    if (i == lane_cls && (w & boost)) {
-                        // written with a bit test per (compile-time) j so that acc[] is never indexed dynamically
+                    if (i == lane_cls && (wf & boost)) {
+                        // a bit test per (compile-time) j: acc[] must never be indexed dynamically
 #pragma unroll
                         for (int j = 0; j < 8 * NJ; ++j)
                             if ((lane_bit >> j) & 1u) acc[j] = __dadd_rn(acc[j], 2.0);
                     }
                 }
             }
-            if (IDENTITY && (w & boost) && (w & lane_bit)) {
 #pragma unroll
-                for (int j = 0; j < 8 * NJ; ++j)
-                    if ((lane_bit >> j) & 1u) acc[j] = __dadd_rn(acc[j], 2.0);
-            }
+            for (int j = 0; j < 8 * NJ; ++j)
+                if (j < c) row[j] = acc[j];
         }
-#pragma unroll
-        for (int j = 0; j < 8 * NJ; ++j)
-            if (j < c) row[j] = acc[j];
     }
     if (mine) atomicAdd(&s_count, mine);
     __syncthreads();

@@ -43,6 +43,7 @@ class DeviceMapper(object):
         cfg.origin_offset_x, cfg.origin_offset_y = float(origin_offset[0]), float(origin_offset[1])
         cfg.range_max = float(range_max)
         cfg.map_dev = self.map.data_ptr()
+        cfg.map_is_zero = 1   # torch.zeros above: the handle may use the atomic count update (include/smap.h)
         handle = ctypes.c_void_p()
         _native.check(self._lib.smap_create(ctypes.byref(cfg), ctypes.byref(handle)))
         self._h = handle
@@ -170,6 +171,11 @@ class DeviceMapper(object):
         _native.check(self._lib.smap_update(self._h, target.data_ptr(), pcd.data_ptr(), pcd.stride(0) if m else 0,
                                             label.data_ptr(), label.stride(0) if m else 0, m, self._stream()))
         return target
+
+    def notify_map_modified(self):
+        """Call after writing into ``self.map`` from outside (``copy_``, arithmetic, ...): the grid may no longer hold
+        integer-valued counts, so the handle switches from the atomic count update to the ordered update."""
+        _native.check(self._lib.smap_notify_map_modified(self._h))
 
     def clear(self):
         _native.check(self._lib.smap_clear(self._h, self._stream()))

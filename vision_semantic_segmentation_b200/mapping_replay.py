@@ -133,6 +133,7 @@ class SemanticMapping(object):
                 cameras=[self.cam1, self.cam6], device=self._device_arg)
             if self._host_map is not None:
                 self._dev.map.copy_(_native.require_cuda().from_numpy(self._host_map))
+                self._dev.notify_map_modified()
                 self._host_map = None
         return self._dev
 
@@ -158,10 +159,12 @@ class SemanticMapping(object):
             return
         if _is_torch(value):
             self.device_mapper.map.copy_(value)
+            self._dev.notify_map_modified()
         elif self._dev is None:
             self._host_map = np.ascontiguousarray(value, dtype=np.float64)
         else:
             self._dev.map.copy_(_native.require_cuda().from_numpy(np.ascontiguousarray(value, dtype=np.float64)))
+            self._dev.notify_map_modified()
         self._map_valid = True
 
     _map_valid = False
@@ -257,6 +260,7 @@ class SemanticMapping(object):
 
         color_map, filtered = filter_and_render(dm.map, self.label_colors, return_filtered=True)
         dm.map.copy_(filtered)  # self.map = apply_filter(self.map)
+        dm.notify_map_modified()
         color_map = color_map.cpu().numpy()
 
         if write_image and rank == 0:
