@@ -8,6 +8,8 @@ fraction of the HBM roofline, next to the CPU path timed on the same box).
 A "step" is one frame of BASELINE.json configs[1]: a 2M-point local cloud + one 1920x1440
 19-class label image, count-based update into the default 2000x2000 BEV grid.  Inputs are a ring of
 distinct frames resident in HBM (ring >> L2), so every step streams its cloud and image from DRAM.
+Frames are handed to the C ABI 16 at a time (smap_integrate_batch: one streaming kernel per frame, one
+apply/clear kernel per batch).
 N > 1: one process per GPU (torchrun), frames sharded by rank (weak scaling: every rank integrates K
 frames), one NCCL all-reduce of the grids at the end of the timed region.
 """
@@ -266,20 +268,26 @@ def run_b200(args):
     ms = float(t.item())
     value = world * args.steps * n_pts / (ms * 1e-3)
 
-    # ---- dominant kernel alone (roofline): same launches, events around the scatter kernel's share
-    # The step is two kernels (k_integrate, k_apply); the roofline is reported for the whole fused
-    # project->lookup->update step (both kernels), which is what BASELINE.json's target names.
+    # ---- roofline of the dominant kernel (k_stream: project + cull + lookup + update of one frame).
+    # Its launch duration is measured live with CUDA events recorded by the library on the launching stream
+    # (smap_set_profiling: the per-frame launches are then serialised on that stream); the algorithmic bytes are
+    # SURVEY.md 8d's  16 N + 3 M + 2*8 U  per frame with N, M, U measured above on the device path.
     dm.clear()
-    device_loop(3, False)
+    device_loop(min(16, args.warmup + 3), False)
     torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
+    dm.set_profiling(True)
     device_loop(args.steps, False)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / args.steps
+    st = dm.stats()
+    dm.set_profiling(False)
+    kernel_ms = st["stream_kernel_ms"] / max(st["profiled_frames"], 1)
+    apply_ms = st["apply_kernel_ms"] / max(st["profiled_frames"], 1)
     peak, peak_src = peaks()
     achieved = bytes_per_frame / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")   # from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("k_stream_c%d" % args.classes)
 
     # ---- end to end through the host-buffer entry point: H2D of cloud + image and a D2H read every step
     e2e = None
@@ -333,8 +341,10 @@ def run_b200(args):
             "frames_per_sec": value / n_pts,
             "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_fuse (project+cull+lookup+update, %d frames per launch)" % min(args.batch, args.ring),
-                         "kernel_ms": kernel_ms,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k_stream<float4, count> (project+cull+lookup+update, one frame per launch)",
+                         "kernel_ms": kernel_ms, "apply_kernel_ms_per_frame": apply_ms,
+                         "step_frac": bytes_per_frame / (ms / args.steps * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_frame": bytes_per_frame,
                          "N": n_pts, "M": M, "K_cells": Kc, "U_elements": U},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

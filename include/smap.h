@@ -93,6 +93,11 @@ typedef struct smap_stats {
     int64_t points;          /* points read */
     int64_t touched_cells;   /* (cell, frame) pairs updated by the most recent launch: K for a single frame */
     int64_t kernel_launches; /* kernels launched by this handle */
+    /* filled while smap_set_profiling(h, 1) is active: device time (CUDA events on the caller's stream, launches
+     * serialised on it) of the streaming kernels and of the apply kernels, and the frames they covered */
+    int64_t profiled_frames;
+    double stream_kernel_ms;
+    double apply_kernel_ms;
 } smap_stats;
 
 SMAP_API int smap_abi_version(void);
@@ -177,6 +182,9 @@ SMAP_API int smap_notify_map_modified(smap_handle *h);
 SMAP_API int smap_download(smap_handle *h, double *map_host);     /* synchronises */
 SMAP_API int smap_upload(smap_handle *h, const double *map_host); /* synchronises */
 SMAP_API int smap_get_stats(smap_handle *h, smap_stats *out);     /* synchronises the handle's last stream */
+/* on != 0: time the kernels of every smap_integrate* call with CUDA events (the per-frame launches are then
+ * issued on the caller's stream only, not over the internal streams); read the totals with smap_get_stats. */
+SMAP_API int smap_set_profiling(smap_handle *h, int on);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ EXPORTS = [
     "smap_abi_version", "smap_last_error", "smap_device_count", "smap_device_info", "smap_create",
     "smap_destroy", "smap_set_camera", "smap_set_classes", "smap_project", "smap_update", "smap_integrate",
     "smap_integrate_batch", "smap_integrate_host", "smap_apply_filter", "smap_render", "smap_filter_render",
-    "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_notify_map_modified", "smap_download", "smap_upload", "smap_get_stats",
+    "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_notify_map_modified", "smap_download", "smap_upload", "smap_get_stats", "smap_set_profiling",
 ]
 
 
@@ -44,7 +44,8 @@ class SmapFrame(ctypes.Structure):
 
 class SmapStats(ctypes.Structure):
     _fields_ = [("frames", ctypes.c_int64), ("points", ctypes.c_int64), ("touched_cells", ctypes.c_int64),
-                ("kernel_launches", ctypes.c_int64)]
+                ("kernel_launches", ctypes.c_int64), ("profiled_frames", ctypes.c_int64),
+                ("stream_kernel_ms", ctypes.c_double), ("apply_kernel_ms", ctypes.c_double)]
 
 
 class SmapError(RuntimeError):
@@ -105,6 +106,8 @@ def load():
     L.smap_map_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     L.smap_clear.restype = i32
     L.smap_clear.argtypes = [vp, vp]
+    L.smap_set_profiling.restype = i32
+    L.smap_set_profiling.argtypes = [vp, i32]
     L.smap_notify_map_modified.restype = i32
     L.smap_notify_map_modified.argtypes = [vp]
     L.smap_download.restype = i32

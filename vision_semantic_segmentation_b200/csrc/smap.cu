@@ -95,6 +95,11 @@ struct smap_handle {
     size_t stage_img_cap[kStages] = {};
     cudaEvent_t stage_done[kStages] = {};
     int stage_next = 0;
+    // profiling (smap_set_profiling): three events per smap_integrate_batch chunk, harvested lazily
+    bool profiling = false;
+    struct ProfRec { cudaEvent_t e[3]; int frames; };
+    ProfRec prof_pending[64];
+    int n_prof_pending = 0;
     // bookkeeping
     smap_stats stats = {};
     cudaStream_t last_stream = nullptr;
@@ -257,7 +262,7 @@ int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* f
     int used = 0;
     int n_nonempty = 0;
     for (int i = 0; i < n_frames; ++i) n_nonempty += frames[i].n_points > 0;
-    const bool fork = smap_handle::kAux > 0 && n_nonempty > 1;
+    const bool fork = smap_handle::kAux > 0 && n_nonempty > 1 && !h->profiling;
     if (fork) {
         if (!h->ev_fork) {
             CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -303,6 +308,22 @@ int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* f
         }
     }
     *slots_used = used;
+    return SMAP_OK;
+}
+
+int harvest_profile(smap_handle* h) {
+    for (int i = 0; i < h->n_prof_pending; ++i) {
+        smap_handle::ProfRec& r = h->prof_pending[i];
+        CK(cudaEventSynchronize(r.e[2]));
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, r.e[0], r.e[1]));
+        CK(cudaEventElapsedTime(&b, r.e[1], r.e[2]));
+        h->stats.stream_kernel_ms += a;
+        h->stats.apply_kernel_ms += b;
+        h->stats.profiled_frames += r.frames;
+        for (int k = 0; k < 3; ++k) cudaEventDestroy(r.e[k]);
+    }
+    h->n_prof_pending = 0;
     return SMAP_OK;
 }
 
@@ -432,6 +453,7 @@ int smap_destroy(smap_handle* h) {
     if (!h) return SMAP_OK;
     DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
+    harvest_profile(h);
     if (h->own_map) cudaFree(h->map);
     cudaFree(h->mask); cudaFree(h->boxes); cudaFree(h->touched); cudaFree(h->cm_dev); cudaFree(h->total_dev);
     cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
@@ -557,8 +579,20 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
         if (!h->identity_cm) h->integer_grid = false;
         int rc = ensure_slots(h, chunk);
         int used = 0;
+        smap_handle::ProfRec* pr = nullptr;
+        if (!rc && h->profiling) {
+            if (h->n_prof_pending == 64) rc = harvest_profile(h);
+            if (!rc) {
+                pr = &h->prof_pending[h->n_prof_pending++];
+                pr->frames = 0;
+                for (int k = 0; k < 3; ++k) CK(cudaEventCreate(&pr->e[k]));
+                CK(cudaEventRecord(pr->e[0], st));
+            }
+        }
         if (!rc) rc = launch_stream(h, frames + begin, fps, chunk, count_atomics, st, &used);
+        if (pr) { pr->frames = used; CK(cudaEventRecord(pr->e[1], st)); }
         if (!rc && used > 0) rc = launch_apply(h, h->map, used, count_atomics, st);
+        if (pr) CK(cudaEventRecord(pr->e[2], st));
         if (rc) return rc;
         begin += chunk;
     }
@@ -676,6 +710,16 @@ int smap_clear(smap_handle* h, void* stream) {
     return SMAP_OK;
 }
 
+int smap_set_profiling(smap_handle* h, int on) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    DeviceGuard guard(h->cfg.device);
+    int rc = harvest_profile(h);
+    if (rc) return rc;
+    h->profiling = on != 0;
+    if (on) { h->stats.profiled_frames = 0; h->stats.stream_kernel_ms = 0.0; h->stats.apply_kernel_ms = 0.0; }
+    return SMAP_OK;
+}
+
 int smap_notify_map_modified(smap_handle* h) {
     if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
     h->integer_grid = false;
@@ -703,6 +747,10 @@ int smap_get_stats(smap_handle* h, smap_stats* out) {
     if (!h || !out) return fail(SMAP_ERR_INVALID, "NULL argument");
     DeviceGuard guard(h->cfg.device);
     CK(cudaStreamSynchronize(h->last_stream));
+    {
+        int rc = harvest_profile(h);
+        if (rc) return rc;
+    }
     // after launch_apply flipped the parity, the finished launch's counter sits in touched[parity ^ 1]
     unsigned long long k = 0;
     CK(cudaMemcpy(&k, h->touched + (h->parity ^ 1), sizeof k, cudaMemcpyDeviceToHost));

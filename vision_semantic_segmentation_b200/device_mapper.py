@@ -184,4 +184,9 @@ class DeviceMapper(object):
         s = SmapStats()
         _native.check(self._lib.smap_get_stats(self._h, ctypes.byref(s)))
         return {"frames": s.frames, "points": s.points, "touched_cells": s.touched_cells,
-                "kernel_launches": s.kernel_launches}
+                "kernel_launches": s.kernel_launches, "profiled_frames": s.profiled_frames,
+                "stream_kernel_ms": s.stream_kernel_ms, "apply_kernel_ms": s.apply_kernel_ms}
+
+    def set_profiling(self, on=True):
+        """Time the streaming / apply kernels with CUDA events (see include/smap.h); totals come back in stats()."""
+        _native.check(self._lib.smap_set_profiling(self._h, int(bool(on))))
