@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ordered", action="store_true",
+                    help="dev switch: force the ordered update (cell masks + k_apply) although the matrix is np.eye(C)")
     return ap.parse_args()
 
 
@@ -205,6 +207,15 @@ def run_b200(args):
     c = len(labels)
     cam, cm, lane = camera_setup_1(), np.eye(c), names.index("lane")
     dm = DeviceMapper(MAP_H, MAP_W, colors, cm, BOUNDARY, RESOLUTION, RANGE_MAX, True, lane, cameras=[cam], device=local_rank)
+
+    if args.ordered:   # smap_clear re-arms the count update: undo that after every clear
+        plain_clear = dm.clear
+
+        def ordered_clear():
+            plain_clear()
+            dm.notify_map_modified()
+        dm.clear = ordered_clear
+        dm.notify_map_modified()
 
     ring_host = make_ring(args, rank)
     ring_dev, ring_pinned = [], []

@@ -91,7 +91,8 @@ typedef struct smap_frame {
 typedef struct smap_stats {
     int64_t frames;          /* frames integrated since create / clear */
     int64_t points;          /* points read */
-    int64_t touched_cells;   /* (cell, frame) pairs updated by the most recent launch: K for a single frame */
+    int64_t touched_cells;   /* (cell, frame) pairs updated by the most recent ORDERED update launch (K for a single
+                              * frame); -1 after a count update of a float4 cloud (tags, nothing is replayed) */
     int64_t kernel_launches; /* kernels launched by this handle */
     /* filled while smap_set_profiling(h, 1) is active: device time (CUDA events on the caller's stream, launches
      * serialised on it) of the streaming kernels and of the apply kernels, and the frames they covered */

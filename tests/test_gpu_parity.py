@@ -152,7 +152,8 @@ def test_full_size_frame_against_oracle(full19, log_cm, ordered):
         dm.integrate(dm.make_frame(dev(fr["points"]), dev(fr["semantic_image"]), T, 0))
         mp, lab, _, _ = c_oracle.project_pcd(fr["pcd"], T, cam.P, fr["semantic_image"], 100.0)
         st = c_oracle.update_map(ref, mp, lab, colors, cm, boundary, res, True, lane)
-        assert dm.stats()["touched_cells"] == st[1]
+        # K is counted by the ordered apply; the tagged count update of a float4 cloud replays nothing
+        assert dm.stats()["touched_cells"] == (st[1] if ordered else -1)
         assert np.array_equal(dm.map.cpu().numpy(), ref), "frame %d" % f
     if not log_cm:
         # replaying the same two frames again doubles every count exactly

@@ -180,7 +180,8 @@ for f in range(n_frames):
 assert np.array_equal(t.numpy(), full), "sharded sum differs from the sequential grid"
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank %%d ok\n" %% rank)   # one write per rank: the two ranks share a pipe
+sys.stdout.flush()
 '''
 
 

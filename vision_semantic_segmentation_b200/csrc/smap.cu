@@ -9,10 +9,7 @@
 
 #include "../../include/smap.h"
 #include "smap_kernels.cuh"
-
-#ifndef SMAP_AUX_STREAMS
-#define SMAP_AUX_STREAMS 2
-#endif
+#include "smap_fuse.cuh"
 
 using namespace smap;
 
@@ -59,6 +56,13 @@ struct smap_handle {
     // per-frame cell masks: n_slots slots of `cells` words, all zero between launches
     uint32_t* mask = nullptr;
     int n_slots = 0;
+    // count update (k_fuse MODE 1): one plane of (cells, C + 1) uint32 tags per launching stream; a frame's tag is
+    // larger than every tag written before it in its plane
+    uint32_t* tags = nullptr;
+    int n_tag_planes = 0;
+    uint32_t frame_tag = 0;
+    bool fuse_attr_set = false;
+    bool last_update_counted = true;   // the most recent update went through k_apply (which counts touched cells)
     int64_t slot_words = 0;   // cells rounded up to a multiple of 4: k_apply reads the slots with 16-byte loads
     // double-buffered per-slot bounding boxes + touched counters (k_stream writes [parity], k_apply resets [parity^1])
     FrameBox* boxes = nullptr;                // [2][kMaxBatch]
@@ -67,12 +71,9 @@ struct smap_handle {
     int sm_count = 148;
     bool identity_cm = false;   // update matrix is exactly np.eye(C): the count update
     bool integer_grid = false;  // the grid is known to hold integer-valued counts (zeroed by us, then only count updates)
-    // k_stream launches of one batch alternate over a few internal streams (fork / join with events around the
-    // batch): the frames are independent, so the ramp-up and tail of one launch overlap the next one's body
-    static constexpr int kAux = SMAP_AUX_STREAMS;
-    cudaStream_t aux[kAux > 0 ? kAux : 1] = {};
-    cudaEvent_t ev_fork = nullptr;
-    cudaEvent_t ev_join[kAux > 0 ? kAux : 1] = {};
+    // batched k_fuse launch: parameter block (13 KB, rebuilt per launch) and the per-frame block-completion counters
+    FuseBatch fuse_batch;
+    unsigned int* frames_done = nullptr;      // [kMaxBatch]
     // class tables
     double* cm_dev = nullptr;
     uint8_t colors[SMAP_MAX_CLASSES * 3];
@@ -140,11 +141,6 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
             fp.Ea[r] = nextafterf(kCullSlack * a, INFINITY);
             fp.Eb[r] = nextafterf(kCullSlack * fabsf(fp.Mf[4 * r + 3]), INFINITY);
         }
-        for (int p = 0; p < 2; ++p) {
-            for (int j = 0; j < 4; ++j) fp.Mc[p][j] = make_float2(fp.Mf[(2 * p) * 4 + j], fp.Mf[(2 * p + 1) * 4 + j]);
-            fp.Eac[p] = make_float2(fp.Ea[2 * p], fp.Ea[2 * p + 1]);
-            fp.Ebc[p] = make_float2(fp.Eb[2 * p], fp.Eb[2 * p + 1]);
-        }
         fp.range_hi = (float)fp.range_max * (1.0f + kCullSlack);
         fp.img_wf = (float)f->image_width;
         fp.img_hf = (float)f->image_height;
@@ -173,13 +169,6 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
         fp.img_hd = (double)f->image_height;
         fp.img_wd1 = fp.img_wd + 1.0;
         fp.img_hd1 = fp.img_hd + 1.0;
-        fp.one_d = 1.0 + 9.094947017729282e-13;  // 1 + 2^-40
-        fp.w_d = fp.img_wd * fp.one_d;
-        fp.h_d = fp.img_hd * fp.one_d;
-        fp.clo_u = e[0] + fp.one_d * e[2];
-        fp.chi_u = e[0] + fp.w_d * e[2];
-        fp.clo_v = e[1] + fp.one_d * e[2];
-        fp.chi_v = e[1] + fp.h_d * e[2];
         // non-finite bounds (absurd matrices) switch the fast path off: q2 > inf never holds
         if (!(fp.cgu == fp.cgu) || !(fp.cgv == fp.cgv) || !(fp.e3x4 == fp.e3x4)) fp.e3x4 = INFINITY;
     }
@@ -188,6 +177,168 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
     fp.img_h = f->image_height;
     fp.pad = 0;
     return SMAP_OK;
+}
+
+// float next above / below (the thresholds of the float32 path are rounded away from the certified side)
+inline float f_up(double v) {
+    float f = (float)v;
+    if ((double)f < v) f = nextafterf(f, INFINITY);
+    return f;
+}
+inline float f_down(double v) {
+    float f = (float)v;
+    if ((double)f > v) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+// Constants of the float32 path of k_fuse (error analysis: header of smap_fuse.cuh).  Everything is composed in
+// double here; whenever a precondition of the analysis cannot be met (absurd matrices, a vehicle millions of cells
+// away from the grid, ...) the float32 decisions are switched off (coord_l < 0): every survivor of the cull is then
+// decided by the float64 path, which is always valid.
+void fill_fast32(const smap_handle* h, const smap_frame* f, const FrameParams& fp, Fast32& k) {
+    memset(&k, 0, sizeof k);
+    const double u53 = 1.1102230246251565e-16, p21 = 4.76837158203125e-07 /* 2^-21 */, slack = 1.0 + 9.765625e-4;
+    const double p22 = 0.5 * p21, p23 = 0.25 * p21;
+    double Tm[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (f->has_transform) memcpy(Tm, f->world_to_velodyne, sizeof Tm);
+    // rows: 0..2 = M = P T, 3 = velodyne x (row 0 of T); abs = |P| |T| resp. |T row 0|
+    double row[4][4], arow[4][4];
+    for (int r = 0; r < 3; ++r)
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0, aabs = 0.0;
+            for (int q = 0; q < 4; ++q) {
+                acc += fp.P[4 * r + q] * Tm[4 * q + j];
+                aabs += fabs(fp.P[4 * r + q]) * fabs(Tm[4 * q + j]);
+            }
+            row[r][j] = acc;
+            arow[r][j] = aabs;
+        }
+    for (int j = 0; j < 4; ++j) { row[3][j] = Tm[j]; arow[3][j] = fabs(Tm[j]); }
+    const double W = (double)f->image_width, H = (double)f->image_height, R = fp.range_max;
+    const double umax = (W > H ? W : H) + 2.0;
+    const bool r_ok = (R == R) && fabs(R) < 1e30;
+
+    // re-centring point: the velodyne origin in world coordinates (any float32 point is valid; this one keeps
+    // the local coordinates small)
+    float cf[3] = {0.f, 0.f, 0.f};
+    if (f->has_transform)
+        for (int j = 0; j < 3; ++j) {
+            double c = 0.0;
+            for (int i = 0; i < 3; ++i) c -= Tm[4 * i + j] * Tm[4 * i + 3];
+            const float cc = (float)c;
+            cf[j] = (cc == cc && fabsf(cc) < 1e30f) ? cc : 0.f;
+        }
+    const double cd[3] = {(double)cf[0], (double)cf[1], (double)cf[2]};
+    const double cmax = fmax(fmax(fabs(cd[0]), fabs(cd[1])), fabs(cd[2]));
+
+    // ---------------- conservative cull in world coordinates, constant error bounds for |x|,|y|,|z| <= bw
+    {
+        k.c_bw = f_down(cmax + 1024.0);
+        const double bw = (double)k.c_bw * (1.0 + 1e-6);
+        double S[4], E[4];
+        for (int r = 0; r < 4; ++r) {
+            double s = fabs(row[r][3]), sa = arow[r][3];
+            for (int j = 0; j < 3; ++j) { s += fabs(row[r][j]) * bw; sa += arow[r][j] * bw; }
+            S[r] = s;
+            E[r] = (p21 * s + 64.0 * u53 * sa) * slack;
+        }
+        for (int j = 0; j < 4; ++j) {
+            k.c_dc[j] = make_float2((float)row[3][j], (float)row[2][j]);
+            k.c_ab[j] = make_float2((float)row[0][j], (float)row[1][j]);
+        }
+        k.c_wh = make_float2((float)W, (float)H);
+        k.c_depth = f_up(E[2]);
+        k.c_lo_u = f_down(-((E[0] + E[2]) + p23 * (S[0] + S[2])) * slack);
+        k.c_hi_u = f_down(-((E[0] + W * E[2]) + p23 * (S[0] + W * S[2])) * slack);
+        k.c_lo_v = f_down(-((E[1] + E[2]) + p23 * (S[1] + S[2])) * slack);
+        k.c_hi_v = f_down(-((E[1] + H * E[2]) + p23 * (S[1] + H * S[2])) * slack);
+        if (r_ok) {
+            k.c_rh = (float)(0.5 * R);
+            k.c_rthr = f_up((0.5 * R + E[3] + p22 * fabs(R) + p23 * S[3]) * slack);
+        } else {   // non-finite RANGE_MAX: no range cull here, the float64 path applies the reference's own test
+            k.c_rh = 0.f;
+            k.c_rthr = (R == R) ? INFINITY : NAN;
+        }
+        // a bound that is not finite cannot certify anything: let every point through
+        const double chk = E[0] + E[1] + W * E[2] + H * E[2] + E[3];
+        if (!(chk == chk) || chk > 1e30) {
+            k.c_bw = -1.f;
+        }
+    }
+
+    // ---------------- certified float32 decisions in re-centred coordinates
+    const double L = 512.0;
+    const double pE = 0.75 * p21;   // 6 u: the row bound of the analysis is 5.03 u (1 + 3 u)
+    k.n_ctr_xy = make_float2(-cf[0], -cf[1]);
+    k.n_ctr_z = -cf[2];
+    bool ok = r_ok;
+    {
+        const double bloc = cmax + L;
+        // local rows: 0 = q0 - q2/2, 1 = q1 - q2/2, 2 = q2, 3 = velodyne x;  beta = row . (c, 1)
+        double A[4][3], beta[4], e[4], amax[4];
+        for (int r = 0; r < 4; ++r) {
+            double rr[4], ra[4];
+            for (int j = 0; j < 4; ++j) {
+                rr[j] = row[r][j]; ra[j] = arow[r][j];
+                if (r < 2) { rr[j] -= 0.5 * row[2][j]; ra[j] += 0.5 * arow[2][j]; }
+            }
+            double b = rr[3], sa = ra[3];
+            amax[r] = 0.0;
+            for (int j = 0; j < 3; ++j) {
+                A[r][j] = rr[j];
+                b += rr[j] * cd[j];
+                sa += ra[j] * bloc;
+                amax[r] = fmax(amax[r], fabs(rr[j]));
+            }
+            beta[r] = b;
+            e[r] = 128.0 * u53 * sa;   // reference chain + host composition of beta
+        }
+        for (int j = 0; j < 3; ++j) {
+            k.d_uv[j] = make_float2((float)A[0][j], (float)A[1][j]);
+            k.d_cd[j] = make_float2((float)A[2][j], (float)A[3][j]);
+        }
+        k.d_uv[3] = make_float2((float)beta[0], (float)beta[1]);
+        k.d_cd[3] = make_float2((float)beta[2], (float)beta[3]);
+        const double k1 = (4.0 / 3.0) * pE * (fmax(amax[0], amax[1]) + umax * amax[2]) * slack;
+        const double k0 = (4.0 / 3.0) * (fmax(pE * fabs(beta[0]) + e[0], pE * fabs(beta[1]) + e[1]) +
+                                         umax * (pE * fabs(beta[2]) + e[2])) * slack;
+        const double c0 = umax * p21 + 2.0 * p21;
+        k.g_k1 = f_up(k1);
+        k.g_k0 = f_up(k0);
+        k.g_hc = f_down(0.5 - c0);
+        k.r_h = (float)(0.5 * R);
+        k.r_kd = f_up(pE * amax[3] * slack);
+        k.r_thr0 = f_down((0.5 * R - (pE * fabs(beta[3]) + e[3] + 2.0 * p21 * fabs(R))) * (1.0 - 1e-6));
+        k.mid_uv = make_float2((float)(0.5 * (W - 2.0)), (float)(0.5 * (H - 2.0)));
+        k.half_uv = make_float2((float)(0.5 * W), (float)(0.5 * H));
+        if (!(k1 < 1e10) || !(k0 < 1e10) || !(c0 < 0.25)) ok = false;   // also keeps MUFU.RCP away from flush-to-zero
+    }
+    {
+        const smap_config& c = h->cfg;
+        const double rinv = 1.0 / c.resolution;
+        const double g0[2] = {((cd[0] + c.origin_offset_x) - c.boundary_x_min) / c.resolution,
+                              ((cd[1] + c.origin_offset_y) - c.boundary_y_min) / c.resolution};
+        const double i0[2] = {rint(g0[0]), rint(g0[1])};
+        const double dims[2] = {(double)c.map_height, (double)c.map_width};
+        const double lim = 2097152.0;   // 2^21
+        if (!(fabs(i0[0]) < lim && fabs(i0[1]) < lim && L * fabs(rinv) < lim && dims[0] < lim && dims[1] < lim)) ok = false;
+        const double span = cmax + L + fabs(c.origin_offset_x) + fabs(c.origin_offset_y) + fabs(c.boundary_x_min) + fabs(c.boundary_y_min);
+        const double cc = p22 + 9.094947017729282e-13 * (span * fabs(rinv) + 1.0);
+        k.cell_rf = (float)rinv;
+        k.cell_kc = f_up(0.875 * p22 * fabs(rinv) * slack);   // 3.5 u: the analysis gives 3.1 u (1 + 3 u)
+        k.cell_hg0 = f_down(0.5 - cc - p22);
+        if (!(cc < 0.25)) ok = false;
+        if (ok) {
+            k.cell_f0 = make_float2((float)(g0[0] - i0[0] - 0.5), (float)(g0[1] - i0[1] - 0.5));
+            k.mid_c = make_float2((float)(0.5 * (dims[0] - 2.0) - i0[0]), (float)(0.5 * (dims[1] - 2.0) - i0[1]));
+            k.half_c = make_float2((float)(0.5 * dims[0]), (float)(0.5 * dims[1]));
+            k.clamp_c = make_float2((float)(12582912.0 - i0[0]), (float)(12582912.0 - i0[1]));
+            const int64_t mb = 0x4B400000ll;   // bit pattern of 1.5 * 2^23
+            k.cell_k = (uint32_t)(uint64_t)(((int64_t)i0[0] - mb) * (int64_t)c.map_width + ((int64_t)i0[1] - mb));
+            k.pix_k = (uint32_t)(uint64_t)(-mb * (int64_t)f->image_width - mb);
+        }
+    }
+    k.coord_l = ok ? (float)L : -1.f;
 }
 
 int ensure_scratch(smap_handle* h, int64_t n) {
@@ -225,7 +376,7 @@ int ensure_slots(smap_handle* h, int want) {
 }
 
 // K3b launch: ordered apply of the `n_slots_used` mask slots whose boxes are boxes[parity]; flips parity.
-int launch_apply(smap_handle* h, double* map, int n_slots_used, bool clear_only, cudaStream_t st) {
+int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st) {
     const int c = h->cfg.num_classes;
     ApplyParams ap;
     memset(&ap, 0, sizeof ap);
@@ -238,11 +389,7 @@ int launch_apply(smap_handle* h, double* map, int n_slots_used, bool clear_only,
     unsigned long long* ntt = h->touched + (h->parity ^ 1);
     const unsigned grid = (unsigned)h->sm_count * 8;
     const int lane = h->cfg.lane_index, mw = h->cfg.map_width;
-#define SMAP_LAUNCH_APPLY(NJ)                                                                                          \
-    do {                                                                                                              \
-        if (clear_only) k_apply<1, true><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw); \
-        else k_apply<NJ, false><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw); \
-    } while (0)
+#define SMAP_LAUNCH_APPLY(NJ) k_apply<NJ><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw)
     if (c <= 8) SMAP_LAUNCH_APPLY(1);
     else if (c <= 16) SMAP_LAUNCH_APPLY(2);
     else if (c <= 24) SMAP_LAUNCH_APPLY(3);
@@ -254,30 +401,14 @@ int launch_apply(smap_handle* h, double* map, int n_slots_used, bool clear_only,
     return SMAP_OK;
 }
 
-// Queue one k_stream launch per non-empty frame; frame i of the non-empty ones scatters into mask slot i.
-// Returns the number of slots used in *slots_used.
-int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, bool count_atomics,
-                  cudaStream_t st, int* slots_used) {
-    const int layout = frames[0].layout;
+// Queue one k_stream_soa launch per non-empty (4, N) float64 frame; frame i of the non-empty ones scatters into
+// mask slot i.  Returns the number of slots used in *slots_used.
+int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, cudaStream_t st,
+                  int* slots_used) {
     int used = 0;
-    int n_nonempty = 0;
-    for (int i = 0; i < n_frames; ++i) n_nonempty += frames[i].n_points > 0;
-    const bool fork = smap_handle::kAux > 0 && n_nonempty > 1 && !h->profiling;
-    if (fork) {
-        if (!h->ev_fork) {
-            CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-            for (int a = 0; a < smap_handle::kAux; ++a) {
-                CK(cudaStreamCreateWithFlags(&h->aux[a], cudaStreamNonBlocking));
-                CK(cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming));
-            }
-        }
-        CK(cudaEventRecord(h->ev_fork, st));
-        for (int a = 0; a < smap_handle::kAux; ++a) CK(cudaStreamWaitEvent(h->aux[a], h->ev_fork, 0));
-    }
     for (int i = 0; i < n_frames; ++i) {
         if (frames[i].n_points == 0) continue;
-        if (frames[i].layout != layout) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
-        cudaStream_t ls = fork ? h->aux[used % smap_handle::kAux] : st;
+        if (frames[i].layout != SMAP_PTS_F64_SOA) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
         StreamParams sp;
         sp.fp = fps[i];
         sp.pts = frames[i].points_dev;
@@ -289,25 +420,85 @@ int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* f
         int64_t grid = (int64_t)h->sm_count * SMAP_STREAM_MINB;
         const int64_t rounds = ceil_div(sp.n, kBlockRoundPts);
         if (grid > rounds) grid = rounds;
-        FrameBox* box = h->boxes + (size_t)h->parity * kMaxBatch + used;
-        if (layout == SMAP_PTS_F32X4) {
-            if (count_atomics) k_stream<SMAP_PTS_F32X4, 1><<<(unsigned)grid, kThreads, 0, ls>>>(sp, h->gp, box, h->map);
-            else k_stream<SMAP_PTS_F32X4, 0><<<(unsigned)grid, kThreads, 0, ls>>>(sp, h->gp, box, h->map);
-        } else {
-            if (count_atomics) k_stream<SMAP_PTS_F64_SOA, 1><<<(unsigned)grid, kThreads, 0, ls>>>(sp, h->gp, box, h->map);
-            else k_stream<SMAP_PTS_F64_SOA, 0><<<(unsigned)grid, kThreads, 0, ls>>>(sp, h->gp, box, h->map);
-        }
+        k_stream_soa<<<(unsigned)grid, kThreads, 0, st>>>(sp, h->gp, h->boxes + (size_t)h->parity * kMaxBatch + used);
         CK(cudaGetLastError());
         h->stats.kernel_launches += 1;
         ++used;
     }
-    if (fork) {
-        for (int a = 0; a < smap_handle::kAux; ++a) {
-            CK(cudaEventRecord(h->ev_join[a], h->aux[a]));
-            CK(cudaStreamWaitEvent(st, h->ev_join[a], 0));
+    *slots_used = used;
+    return SMAP_OK;
+}
+
+// Tag planes of the count update (k_fuse MODE 1): zero = "never written"; frame tags start at 1.
+int ensure_tags(smap_handle* h, int planes) {
+    if (planes <= h->n_tag_planes) return SMAP_OK;
+    const size_t plane_bytes = sizeof(uint32_t) * (size_t)h->cells * (size_t)(h->cfg.num_classes + 1);
+    CK(cudaDeviceSynchronize());
+    if (h->tags) CK(cudaFree(h->tags));
+    h->tags = nullptr;
+    h->n_tag_planes = 0;
+    CK(cudaMalloc(&h->tags, plane_bytes * planes));
+    CK(cudaMemset(h->tags, 0, plane_bytes * planes));
+    h->n_tag_planes = planes;
+    h->frame_tag = 0;
+    return SMAP_OK;
+}
+
+// One k_fuse launch for all the non-empty float4 frames of a batch (frame = blockIdx.y).  Count update: nothing
+// else to do afterwards; otherwise frame i of the non-empty ones scatters into mask slot i and *slots_used tells
+// k_apply how many there are.
+int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, bool count_atomics,
+                cudaStream_t st, int* slots_used) {
+    int used = 0;
+    if (count_atomics) {
+        int rc = ensure_tags(h, 2);
+        if (rc) return rc;
+        if (h->frame_tag > 0xffffffffu - (uint32_t)n_frames - 1u) {   // tag space exhausted: start over
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemset(h->tags, 0, sizeof(uint32_t) * (size_t)h->cells * (size_t)(h->cfg.num_classes + 1) * h->n_tag_planes));
+            h->frame_tag = 0;
         }
     }
+    if (!h->fuse_attr_set) {   // the per-warp TMA stages + stacks need more than the default 48 KB
+        CK(cudaFuncSetAttribute(k_fuse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFBlockSmem));
+        CK(cudaFuncSetAttribute(k_fuse<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFBlockSmem));
+        h->fuse_attr_set = true;
+    }
+    const size_t plane_words = (size_t)h->cells * (size_t)(h->cfg.num_classes + 1);
+    FuseBatch* fb = &h->fuse_batch;
+    int64_t n_max = 0;
+    for (int i = 0; i < n_frames; ++i) {
+        if (frames[i].n_points == 0) continue;
+        if (frames[i].layout != SMAP_PTS_F32X4) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
+        FuseFrame& f = fb->f[used];
+        f.fp = fps[i];
+        fill_fast32(h, frames + i, fps[i], f.fk);
+        f.pts = static_cast<const float4*>(frames[i].points_dev);
+        f.image = frames[i].image_dev;
+        f.fk.tag = ++h->frame_tag;
+        f.mask = count_atomics ? nullptr : h->mask + (size_t)used * h->slot_words;
+        // consecutive frames alternate between the two tag planes; k_fuse makes frame f + 2 wait for frame f
+        f.tags = count_atomics ? h->tags + plane_words * (f.fk.tag & 1u) : nullptr;
+        f.n = frames[i].n_points;
+        if (f.n > n_max) n_max = f.n;
+        ++used;
+    }
     *slots_used = used;
+    if (used == 0) return SMAP_OK;
+    // one full wave of resident blocks per frame (fewer for a small cloud): at most two frames are then in flight
+    int64_t gx = (int64_t)h->sm_count * SMAP_FUSE_MINB;
+    const int64_t rounds = ceil_div(n_max, kFBlockRoundPts);
+    if (gx > rounds) gx = rounds;
+    const dim3 grid((unsigned)gx, (unsigned)used);
+    FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch;
+    if (count_atomics) {
+        CK(cudaMemsetAsync(h->frames_done, 0, sizeof(unsigned int) * kMaxBatch, st));
+        k_fuse<1><<<grid, kThreads, kFBlockSmem, st>>>(*fb, h->gp, boxes, h->map, h->frames_done);
+    } else {
+        k_fuse<0><<<grid, kThreads, kFBlockSmem, st>>>(*fb, h->gp, boxes, h->map, h->frames_done);
+    }
+    CK(cudaGetLastError());
+    h->stats.kernel_launches += 1;
     return SMAP_OK;
 }
 
@@ -438,6 +629,7 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     if (e == cudaSuccess) e = cudaMalloc(&h->cm_dev, sizeof(double) * SMAP_MAX_CLASSES * SMAP_MAX_CLASSES);
     if (e == cudaSuccess) e = cudaMalloc(&h->total_dev, sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&h->frames_done, sizeof(unsigned int) * kMaxBatch);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         fail(e == cudaErrorMemoryAllocation ? SMAP_ERR_NOMEM : SMAP_ERR_CUDA, "smap_create: %s", cudaGetErrorString(e));
@@ -455,15 +647,9 @@ int smap_destroy(smap_handle* h) {
     cudaDeviceSynchronize();
     harvest_profile(h);
     if (h->own_map) cudaFree(h->map);
-    cudaFree(h->mask); cudaFree(h->boxes); cudaFree(h->touched); cudaFree(h->cm_dev); cudaFree(h->total_dev);
+    cudaFree(h->mask); cudaFree(h->tags); cudaFree(h->boxes); cudaFree(h->touched); cudaFree(h->cm_dev); cudaFree(h->total_dev);
     cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
-    if (h->ev_fork) {
-        cudaEventDestroy(h->ev_fork);
-        for (int a = 0; a < smap_handle::kAux; ++a) {
-            cudaEventDestroy(h->ev_join[a]);
-            cudaStreamDestroy(h->aux[a]);
-        }
-    }
+    cudaFree(h->frames_done);
     for (int i = 0; i < smap_handle::kStages; ++i) {
         cudaFree(h->stage_pts[i]);
         cudaFree(h->stage_img[i]);
@@ -554,7 +740,8 @@ int smap_update(smap_handle* h, double* map_dev, const double* pcd, int64_t ld, 
     h->stats.kernel_launches += 1;
     h->last_stream = st;
     if (!map_dev || map_dev == h->map) h->integer_grid = h->integer_grid && h->identity_cm;
-    return launch_apply(h, map_dev ? map_dev : h->map, 1, false, st);
+    h->last_update_counted = true;
+    return launch_apply(h, map_dev ? map_dev : h->map, 1, st);
 }
 
 int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames, void* stream) {
@@ -575,9 +762,12 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
         }
         // the count update on a grid of integer-valued counts may add its increments with float64 atomics (exact
         // in any order); everything else goes through the ordered apply
-        const bool count_atomics = h->identity_cm && h->integer_grid;
+        const bool f4 = frames[begin].layout == SMAP_PTS_F32X4;
+        // (the tag planes index (cell, class) elements with 32 bits)
+        const bool count_atomics = f4 && h->identity_cm && h->integer_grid &&
+                                   h->cells * (int64_t)(h->cfg.num_classes + 1) < ((int64_t)1 << 32);
         if (!h->identity_cm) h->integer_grid = false;
-        int rc = ensure_slots(h, chunk);
+        int rc = count_atomics ? SMAP_OK : ensure_slots(h, chunk);
         int used = 0;
         smap_handle::ProfRec* pr = nullptr;
         if (!rc && h->profiling) {
@@ -589,9 +779,11 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
                 CK(cudaEventRecord(pr->e[0], st));
             }
         }
-        if (!rc) rc = launch_stream(h, frames + begin, fps, chunk, count_atomics, st, &used);
+        if (!rc) rc = f4 ? launch_fuse(h, frames + begin, fps, chunk, count_atomics, st, &used)
+                         : launch_stream(h, frames + begin, fps, chunk, st, &used);
         if (pr) { pr->frames = used; CK(cudaEventRecord(pr->e[1], st)); }
-        if (!rc && used > 0) rc = launch_apply(h, h->map, used, count_atomics, st);
+        if (!rc && used > 0 && !count_atomics) rc = launch_apply(h, h->map, used, st);
+        h->last_update_counted = !count_atomics;
         if (pr) CK(cudaEventRecord(pr->e[2], st));
         if (rc) return rc;
         begin += chunk;
@@ -743,6 +935,17 @@ int smap_upload(smap_handle* h, const double* map_host) {
     return SMAP_OK;
 }
 
+#ifdef SMAP_FUSE_STATS
+// diagnostic builds only: read and reset the routing counters of k_fuse
+__attribute__((visibility("default"))) int smap_debug_fuse_stats(unsigned long long out[4]) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out, g_fuse_stats, sizeof(unsigned long long) * 4));
+    unsigned long long zero[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyToSymbol(g_fuse_stats, zero, sizeof zero));
+    return SMAP_OK;
+}
+#endif
+
 int smap_get_stats(smap_handle* h, smap_stats* out) {
     if (!h || !out) return fail(SMAP_ERR_INVALID, "NULL argument");
     DeviceGuard guard(h->cfg.device);
@@ -754,7 +957,7 @@ int smap_get_stats(smap_handle* h, smap_stats* out) {
     // after launch_apply flipped the parity, the finished launch's counter sits in touched[parity ^ 1]
     unsigned long long k = 0;
     CK(cudaMemcpy(&k, h->touched + (h->parity ^ 1), sizeof k, cudaMemcpyDeviceToHost));
-    h->stats.touched_cells = (int64_t)k;
+    h->stats.touched_cells = h->last_update_counted ? (int64_t)k : -1;
     *out = h->stats;
     return SMAP_OK;
 }

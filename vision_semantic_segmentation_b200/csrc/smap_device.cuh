@@ -26,20 +26,12 @@ struct FrameParams {
     double c0;         // guard offset: Umax * 2^-44
     double img_wd, img_hd;
     double img_wd1, img_hd1;   // W + 1, H + 1
-    // ---- conservative cull in double (cull_pass): a point can only be kept if
-    //   q0 + (1+d) q2 > -clo_u,  W(1+d) q2 - q0 > -chi_u   (and the same for v) whenever q2 > e3x4
-    double one_d;      // 1 + 2^-40
-    double w_d, h_d;   // W (1 + 2^-40), H (1 + 2^-40)
-    double clo_u, chi_u, clo_v, chi_v;
     // ---- float32 pre-cull (see precull_pass): row 0 = T row 0 (velodyne x), rows 1..3 = rows of P*T
     float Mf[16];
     float Ea[4];       // kCullSlack * max(|m_r0|, |m_r1|, |m_r2|)   error bound of row r = Ea[r] * (|x|+|y|+|z|) + Eb[r]
     float Eb[4];       // kCullSlack * |m_r3|
     float range_hi;    // range_max * (1 + kCullSlack)
     float img_wf, img_hf;
-    // the same constants paired by rows -- {row 0, row 1} and {row 2, row 3} -- as operands of the packed
-    // FFMA2 / FADD2 instructions: Mc[p][j] = {Mf[(2p)*4 + j], Mf[(2p+1)*4 + j]}
-    float2 Mc[2][4], Eac[2], Ebc[2];
     int has_T;         // 0: cloud already in the velodyne frame
     int img_w, img_h;  // image.shape[1], image.shape[0]
     int pad;
@@ -175,30 +167,6 @@ __device__ __forceinline__ bool precull_pass(const FrameParams& k, float x, floa
     return !finite | (range_ok & (!depth_pos | (u_ok & v_ok)));
 }
 
-// The same test with Blackwell's packed float32 pipe (FFMA2 / FADD2, sm_100+): rows 0,1 and rows 2,3 of the
-// pre-cull matrix are evaluated as float2 pairs, so 20 FFMA + 8 FADD become 8 FFMA2 + 4 FADD2.  That matters
-// because this kernel is issue-bound, not FP32-bound.  Every operation is the same IEEE round-to-nearest
-// operation as in precull_pass, so the two agree bit for bit (except the order of the 4-term sum that only
-// feeds the "is it finite" test).
-__device__ __forceinline__ bool precull_pass_packed(const FrameParams& k, float x, float y, float z) {
-    const float s = fabsf(x) + fabsf(y) + fabsf(z);
-    const float2 xx = make_float2(x, x), yy = make_float2(y, y), zz = make_float2(z, z), ss = make_float2(s, s);
-    const float2 neg1 = make_float2(-1.0f, -1.0f);
-    const float2 v01 = __ffma2_rn(k.Mc[0][0], xx, __ffma2_rn(k.Mc[0][1], yy, __ffma2_rn(k.Mc[0][2], zz, k.Mc[0][3])));
-    const float2 v23 = __ffma2_rn(k.Mc[1][0], xx, __ffma2_rn(k.Mc[1][1], yy, __ffma2_rn(k.Mc[1][2], zz, k.Mc[1][3])));
-    const float2 e01 = __ffma2_rn(k.Eac[0], ss, k.Ebc[0]), e23 = __ffma2_rn(k.Eac[1], ss, k.Ebc[1]);
-    const float2 hi01 = __fadd2_rn(v01, e01), hi23 = __fadd2_rn(v23, e23);
-    const float2 lo01 = __ffma2_rn(e01, neg1, v01), lo23 = __ffma2_rn(e23, neg1, v23);   // v - e, one rounding
-    const float2 es = __fadd2_rn(e01, e23);
-    const bool finite = (es.x + es.y) < 1e30f;
-    const bool range_ok = (hi01.x > 0.0f) & (lo01.x < k.range_hi);
-    const bool depth_pos = lo23.y > 0.0f;
-    const float q2hi = hi23.y * (1.0f + kCullSlack);
-    const bool u_ok = (hi01.y > -q2hi) & (lo01.y < k.img_wf * q2hi);
-    const bool v_ok = (hi23.x > -q2hi) & (lo23.x < k.img_hf * q2hi);
-    return !finite | (range_ok & (!depth_pos | (u_ok & v_ok)));
-}
-
 // ------------------------------------------------------------------------------------------------
 // Certified fast path ("filtered predicate"): the integer results the reference produces -- keep / drop,
 // pixel (iu, iv), cell (cx, cy) -- are floors of real quantities; a cheaper evaluation with a rigorous error
@@ -239,24 +207,7 @@ __device__ __forceinline__ bool certified_floor(double t, double guard, int& k) 
 constexpr int kDrop = -1;
 constexpr int kAsk = -2;
 
-// Conservative cull in double precision: false only when the reference rule is CERTAIN to drop the point.
-// vx is the reference's own velodyne x (same four operations), so the range test is exact; the frustum test
-// uses q~ = M p and the error bounds e_r folded into clo_* / chi_* (see FrameParams).
-__device__ __forceinline__ bool cull_pass(const FrameParams& f, double x, double y, double z, bool coords_ok) {
-    const double vx = f.has_T ? dot4(f.T, x, y, z, 1.0) : x;
-    const bool in_front = (0.0 < vx) & (vx < f.range_max);          // src/mapping_replay.py:235, exact
-    const double q0 = __fma_rn(f.M[0], x, __fma_rn(f.M[1], y, __fma_rn(f.M[2], z, f.M[3])));
-    const double q1 = __fma_rn(f.M[4], x, __fma_rn(f.M[5], y, __fma_rn(f.M[6], z, f.M[7])));
-    const double q2 = __fma_rn(f.M[8], x, __fma_rn(f.M[9], y, __fma_rn(f.M[10], z, f.M[11])));
-    const bool certain_depth = coords_ok & (q2 > f.e3x4);
-    const bool u_ok = (__fma_rn(q2, f.one_d, q0) > -f.clo_u) & (__fma_rn(q2, f.w_d, -q0) > -f.chi_u);
-    const bool v_ok = (__fma_rn(q2, f.one_d, q1) > -f.clo_v) & (__fma_rn(q2, f.h_d, -q1) > -f.chi_v);
-    // NaN anywhere: comparisons are false -> in_front false (NaN coordinate makes vx NaN) -> dropped, as the
-    // reference does; a huge-but-finite coordinate fails coords_ok and is passed on to the exact path
-    return in_front & (!certain_depth | (u_ok & v_ok));
-}
-
-// Fast version of project_point for a point that passed cull_pass.  Returns (iv << 16 | iu) >= 0 when kept
+// Fast version of project_point.  Returns (iv << 16 | iu) >= 0 when kept
 // (images up to 32767 x 65535), kDrop, or kAsk.
 __device__ __forceinline__ int fast_project(const FrameParams& f, double x, double y, double z, bool coords_ok) {
     const double vx = f.has_T ? dot4(f.T, x, y, z, 1.0) : x;   // the reference's own value

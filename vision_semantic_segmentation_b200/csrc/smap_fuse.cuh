@@ -1,0 +1,524 @@
+// k_fuse: the fused project -> cull -> label lookup -> cell -> update kernel for float4 clouds (sm_100a).
+//
+// Same per-point rule as k_stream (SURVEY.md section 9 = src/mapping_replay.py:214-301), but every point is first
+// decided in FLOAT32 with a rigorous error bound ("filtered predicate"), because the kernel is bound by
+// instruction issue, not by HBM: the integers the reference produces -- keep / drop, pixel (iu, iv), cell
+// (cx, cy) -- are floors of real quantities, and a float32 evaluation in coordinates re-centred on the vehicle
+// yields the same integers unless a quantity lies within its error bound of an integer.  Those points (~1 %)
+// are set aside on a second per-warp stack and decided by the float64 certified path of smap_device.cuh
+// (fast_project / fast_cell, themselves backed by the reference's own rounding chain), 32 at a time.
+// The results are therefore bit-identical to the reference by construction; the float32 arithmetic only
+// decides how a point is ROUTED.
+//
+// Error analysis (u = 2^-24; all constants are composed in double on the host, see fill_fast32 in smap.cu).
+//   re-centring   xl = fl(x - cx) = D (1 + d), |d| <= u  (D = x - cx exactly; x and cx are float32 values)
+//   row r         q~ = fma(a0, xl, fma(a1, yl, fma(a2, zl, b))) with a_j = fl32(A_j), b = fl32(beta); against the
+//                 exact Q = sum A_j D_j + beta:  |q~ - Q| <= 5.1 u (sum |A_j| |D_j| + |beta|)
+//                 -> E_r(rho) = 6 u (amax_r rho + |beta_r|) + e_ref_r,   rho = |xl| + |yl| + |zl|
+//                 (e_ref_r: what the reference's own float64 chain and the host's composition may differ from Q)
+//   quotient      us = q0' r~ (kept unrounded inside two FMAs), r~ = MUFU.RCP(q2~) (<= 2 ulp), q0' = q0 - q2 / 2 so that us ~ u - 1/2 and
+//                 RN(us) = floor(u) away from the integers.  With |q2~| > 4 E_2:
+//                 |us - (u_ref - 1/2)| <= (4/3)(E_0' + Umax E_2) |r~| + Umax 2^-21  =: g
+//                 certified  <=>  |us - RN(us)| < 1/2 - g   (implies |q2~| > 4 E_2, see smap.cu)
+//   range         |d~ - vx_ref| <= E_d(rho);  certified inside  <=>  |d~ - R/2| < R/2 - E_d
+//   cell          ts = fma(xl, fl32(1/res), f0) ~ gx_ref - I0 - 1/2,  |ts - ...| <= 3.5 u rho / res + c
+// ------------------------------------------------------------------------------------------------
+#pragma once
+#include "smap_kernels.cuh"
+
+namespace smap {
+
+// Per-frame constants of the float32 path.  float2 members are operand pairs of the packed FFMA2 / FADD2
+// instructions (two rows per instruction); as kernel parameters they live in the constant bank and reach the
+// packed instructions through uniform registers.
+struct Fast32 {
+    // ---- conservative cull, world coordinates: rows {velodyne x, q2} and {q0, q1}, columns x, y, z, 1
+    float2 c_dc[4];
+    float2 c_ab[4];
+    float2 c_wh;           // {W, H}
+    float c_bw;            // a coordinate beyond this magnitude: not culled here (decided downstream)
+    float c_rh, c_rthr;    // R / 2,  R / 2 + E_d
+    float c_depth;         // q2 above this: depth certainly positive
+    float c_lo_u, c_hi_u, c_lo_v, c_hi_v;   // pass iff  a + c > c_lo_u,  W c - a > c_hi_u, ... (all <= 0)
+    // ---- certified float32 decisions, coordinates re-centred on the vehicle
+    float2 n_ctr_xy;       // {-cx, -cy}
+    float n_ctr_z;         // -cz
+    float coord_l;         // rho must stay below this (<= 0 switches the float32 path off)
+    float2 d_uv[4];        // rows {q0 - q2 / 2, q1 - q2 / 2}
+    float2 d_cd[4];        // rows {q2, velodyne x}
+    float g_k1, g_k0, g_hc;        // 1/2 - g = fma(-(fma(g_k1, rho, g_k0)), |r|, g_hc)
+    float r_h, r_kd, r_thr0;       // |d - r_h| < fma(-r_kd, rho, r_thr0)
+    float2 mid_uv, half_uv;        // |RN - mid| <= half  <=>  floor in [-1, W - 1] (resp. H - 1)
+    float2 cell_f0;                // fractional parts of the centre's cell coordinate, minus 1/2
+    float cell_rf;                 // fl32(1 / res)
+    float cell_kc, cell_hg0;       // 1/2 - g_cell = fma(-cell_kc, rho, cell_hg0)
+    float2 mid_c, half_c;          // floor + I0 in [-1, MH - 1] (resp. MW - 1)
+    float2 clamp_c;                // magic - I0: lower clamp of the magic-shifted cell coordinate (cell >= 0)
+    uint32_t pix_k;                // pixel = bits(tv) * W + bits(tu) + pix_k    (mod 2^32)
+    uint32_t cell_k;               // cell  = bits(tx) * MW + bits(ty) + cell_k  (mod 2^32)
+    uint32_t tag;                  // count update: this frame's tag (strictly increasing per tag plane)
+    uint32_t pad;
+};
+
+constexpr float kMagic32 = 12582912.0f;   // 1.5 * 2^23: adding it rounds |t| < 2^22 to the nearest integer
+
+// One frame of a batched launch.
+struct FuseFrame {
+    FrameParams fp;        // float64 constants (deferred points only)
+    Fast32 fk;
+    const float4* pts;
+    const uint8_t* image;
+    uint32_t* mask;        // MODE 0: this frame's mask slot
+    uint32_t* tags;        // MODE 1: (cells, C + 1) uint32 tag plane of this frame (two planes alternate)
+    int64_t n;
+};
+
+// Kernel parameter of k_fuse: up to kMaxBatch frames, frame = blockIdx.y.  One launch per batch: the blocks of
+// frame f + 1 start as the blocks of frame f retire, so the ramp-up and tail of consecutive frames overlap and
+// there is no launch gap between frames (a launch per frame on alternating streams left 4 us of each 20 us idle).
+// The per-frame constants are read from the constant bank with the (block-uniform) frame index.
+struct FuseBatch {
+    FuseFrame f[kMaxBatch];
+};
+
+#ifndef SMAP_FUSE_ROUND
+#define SMAP_FUSE_ROUND 2
+#endif
+#ifndef SMAP_FUSE_MINB
+#define SMAP_FUSE_MINB 4
+#endif
+constexpr int kFRound = SMAP_FUSE_ROUND;
+constexpr int kFRoundPts = 32 * kFRound;
+constexpr int kFBlockRoundPts = kWarps * kFRoundPts;
+constexpr int kFQueueCap = kFRoundPts + 32;
+constexpr int kFDeferCap = 64;
+constexpr uint32_t kNone = 0xffffffffu;
+
+#ifdef SMAP_FUSE_STATS   // diagnostic builds only (tools/fuse_stats.py): how the points were routed
+__device__ unsigned long long g_fuse_stats[4];   // survivors of the cull, deferred to float64, float32-accepted, unused
+#endif
+
+// The conservative cull: false only when the reference rule is CERTAIN to drop the point.
+__device__ __forceinline__ bool cull32(const Fast32& k, float x, float y, float z) {
+    const float2 xx = make_float2(x, x), yy = make_float2(y, y), zz = make_float2(z, z);
+    const float2 dc = __ffma2_rn(k.c_dc[0], xx, __ffma2_rn(k.c_dc[1], yy, __ffma2_rn(k.c_dc[2], zz, k.c_dc[3])));
+    const float2 ab = __ffma2_rn(k.c_ab[0], xx, __ffma2_rn(k.c_ab[1], yy, __ffma2_rn(k.c_ab[2], zz, k.c_ab[3])));
+    const float2 cc = make_float2(dc.y, dc.y);
+    const float2 lo = __fadd2_rn(ab, cc);                                       // a + c, b + c
+    const float2 hi = __ffma2_rn(k.c_wh, cc, make_float2(-ab.x, -ab.y));        // W c - a, H c - b
+    bool p = (lo.x > k.c_lo_u) & (hi.x > k.c_hi_u) & (lo.y > k.c_lo_v) & (hi.y > k.c_hi_v);
+    p |= !(dc.y > k.c_depth);                                                   // depth not certainly positive
+    p &= fabsf(dc.x - k.c_rh) < k.c_rthr;                                       // NaN: dropped, as the reference does
+    p |= fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > k.c_bw;
+    return p;
+}
+
+// A deferred point: the float64 certified path (fast_project / fast_cell, exact chain behind them).  Returns
+// {pixel index, cell index}; cell == kNone: dropped.  About 3 % of the cull's survivors come here.
+__device__ __noinline__ uint2 fuse_decide64(const FrameParams* fp, const GridParams* gp, float4 w) {
+    const double x = (double)w.x, y = (double)w.y, z = (double)w.z;
+    const bool coords_ok = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fabsf(w.z)) < (float)kCoordBound;
+    int pix = fast_project(*fp, x, y, z, coords_ok);
+    if (pix == kAsk) pix = exact_project_slow(fp, x, y, z);
+    if (pix < 0) return make_uint2(0u, kNone);
+    int cx = 0, cy = 0;
+    const int on = fast_cell(*gp, x, y, cx, cy);
+    if (on == kAsk) {
+        const long long c2 = exact_cell_slow(gp, x, y);
+        if (c2 < 0) return make_uint2(0u, kNone);
+        cx = (int)(c2 >> 32); cy = (int)(c2 & 0xffffffffll);
+    } else if (on == kDrop) {
+        return make_uint2(0u, kNone);
+    }
+    return make_uint2((uint32_t)(pix >> 16) * (uint32_t)fp->img_w + (uint32_t)(pix & 0xffff),
+                      (uint32_t)cx * (uint32_t)gp->mw + (uint32_t)cy);
+}
+
+// ---- TMA (bulk async copy) + mbarrier plumbing of the per-warp cloud pipeline
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// (the bulk copies themselves -- cp.async.bulk global -> shared, 16-byte granular, completion counted in bytes on
+// the stage's mbarrier, evict-first in L2 because the cloud is read once -- are issued inline in k_fuse)
+
+#ifndef SMAP_FUSE_STAGES
+#define SMAP_FUSE_STAGES 2
+#endif
+constexpr int kFStages = SMAP_FUSE_STAGES;
+#ifndef SMAP_FUSE_GATHER
+#define SMAP_FUSE_GATHER 2
+#endif
+constexpr int kFGather = SMAP_FUSE_GATHER;         // records per lane in one label-lookup + update pass
+constexpr int kFRecCap = 32 * kFGather + 64;       // record stack: < 32 * kFGather left over + 32 (float32) + 32 (float64)
+// dynamic shared memory of k_fuse, per warp: kFStages cloud stages, the survivor stack, the deferred stack, the
+// record stack, the stages' mbarriers; then the two colour tables of the block
+constexpr int kFWarpSmem = (kFStages * kFRoundPts + kFQueueCap + kFDeferCap) * 16 + kFRecCap * 8 + (kFStages * 8 + 15) / 16 * 16;
+constexpr int kFBlockSmem = kWarps * kFWarpSmem + 2 * 256 * 4;
+
+// ------------------------------------------------------------------------------------------------
+// MODE 0: masks only (RED.OR into the frame's slot, bounding box) -- k_apply replays the frames in order.
+// MODE 1: count update (matrix == np.eye(C), grid of integer-valued counts): one uint32 tag per (cell, class)
+//         and one per (cell, boost); ATOM.MAX with the frame's tag returns an older tag exactly once per frame,
+//         and that lane adds 1.0 (boost: 2.0 on the lane class; src/mapping_replay.py:281,294) with a float64 RED.
+//         Sums of small integers are exact in any order.  Nothing to clear, no second kernel.
+//
+// Every warp is autonomous (no block barrier after the prologue) and owns a contiguous, equally sized slice of the
+// cloud, which it walks in rounds of kFRoundPts points:
+//   cloud     a private ring of kFStages shared-memory stages filled by TMA bulk copies (cp.async.bulk +
+//             mbarrier complete_tx): kFStages - 1 rounds are always in flight per warp, no registers and no
+//             scoreboards are tied up by the stream (the register-prefetched version stalled on exactly those);
+//   cull      one LDS.128 per point, conservative float32 test (cull32), survivors (~36 %) pushed on the warp's
+//             stack (ballot + popc);
+//   drain     whenever >= 32 survivors are stacked, pop 32 -- one per lane, all lanes busy -- through a software
+//             pipeline of three batches, so that no lane waits for its own loads or atomics:
+//               stage A (batch k)    float32 decisions (deferred points: float64), label bytes requested
+//               stage B (batch k-1)  label bytes -> class bits (shared colour tables) -> ATOM.MAX / RED.OR issued
+//               stage C (batch k-2)  returned tags -> RED.ADD
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, SMAP_FUSE_MINB)
+k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams gp, FrameBox* __restrict__ boxes,
+       double* __restrict__ map, unsigned int* __restrict__ frames_done) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ int s_box[4];
+
+    const FuseFrame& F = B.f[blockIdx.y];
+    const Fast32& fk = F.fk;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned char* const wbase = s_dyn + (size_t)warp * kFWarpSmem;
+    float4* const stages = reinterpret_cast<float4*>(wbase);
+    float4* const queue = stages + kFStages * kFRoundPts;
+    float4* const defer = queue + kFQueueCap;
+    uint2* const recs = reinterpret_cast<uint2*>(defer + kFDeferCap);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(recs + kFRecCap);
+    uint32_t* const s_tab_r = reinterpret_cast<uint32_t*>(s_dyn + (size_t)kWarps * kFWarpSmem);
+    uint32_t* const s_tab_g = s_tab_r + 256;
+
+    // this warp's slice of the cloud: [w_begin, w_end), the same size (+-1 round-up) for every warp of the frame
+    const int64_t f_n = F.n;
+    const int64_t n_warps = (int64_t)gridDim.x * kWarps;
+    const int64_t per = (f_n + n_warps - 1) / n_warps;
+    const int64_t w_begin = ((int64_t)blockIdx.x * kWarps + warp) * per;
+    const int64_t w_end = (w_begin + per < f_n) ? w_begin + per : f_n;
+    const int w_pts = (w_end > w_begin) ? (int)(w_end - w_begin) : 0;      // < 2^31: a frame has < 2^31 * n_warps points
+    const int n_rounds = (w_pts + kFRoundPts - 1) / kFRoundPts;
+
+    // TMA producer state (meaningful in lane 0): next round to issue, its source, the points left to issue
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    const uint32_t stg0 = smem_u32(stages), bar0 = smem_u32(bars);
+    const float4* i_src = F.pts + w_begin;
+    int i_left = w_pts;
+    uint32_t i_st = 0;
+    auto issue_round = [&]() {   // one elected lane; no-op when the slice is exhausted
+        if (lane == 0 && i_left > 0) {
+            const uint32_t bytes = (uint32_t)(i_left < kFRoundPts ? i_left : kFRoundPts) * 16u;
+            const uint32_t bar = bar0 + i_st * 8u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(stg0 + i_st * (uint32_t)(kFRoundPts * 16)), "l"(i_src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+        }
+        i_src += kFRoundPts;
+        i_left -= kFRoundPts;
+        i_st = (i_st + 1u) % (uint32_t)kFStages;
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kFStages; ++s) mbar_init(bars + s, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kFStages - 1; ++r) issue_round();   // round kFStages - 1 is issued in the first loop turn
+    // the first rounds are on their way while the block builds its colour tables
+    build_color_tables(gp, s_tab_r, s_tab_g);
+    if (threadIdx.x == 0) {
+        box_reset(s_box);
+        if (MODE == 1 && blockIdx.y >= 2) {
+            // the tag plane of this frame was last used by frame blockIdx.y - 2: all its blocks must have retired
+            // (they were dispatched before this one, so the wait cannot deadlock; normally it is already true)
+            const volatile unsigned int* d = frames_done + (blockIdx.y - 2);
+            while (*d < gridDim.x) {}
+            __threadfence();
+        }
+    }
+    __syncthreads();
+
+    const uint8_t* const f_image = F.image;
+    const uint32_t c1 = (uint32_t)gp.c + 1u;
+    const uint32_t lane_bit = (gp.use_intensity && gp.lane >= 0) ? (1u << gp.lane) : 0u;
+
+    uint32_t qn = 0, dn = 0, rn = 0;   // entries on the survivor / deferred / record stacks (warp-uniform)
+    // MODE 0 bounding box: magic-shifted floats on the float32 path (monotone in the cell coordinates), ints for
+    // the deferred points
+    float fbx0 = 3.0e38f, fbx1 = -3.0e38f, fby0 = 3.0e38f, fby1 = -3.0e38f;
+    int ibx0 = 0x7fffffff, ibx1 = -1, iby0 = 0x7fffffff, iby1 = -1;
+
+    // a decided point -> record stack: {pixel index, cell index | intensity flag << 31}
+    auto push_record = [&](bool have, uint32_t pix, uint32_t cell, float it) {
+        const unsigned ballot = __ballot_sync(0xffffffffu, have);
+        if (have) {
+            const uint32_t extreme = (it < 2.0f || it > 14.0f) ? 0x80000000u : 0u;   // src/mapping_replay.py:290
+            recs[rn + __popc(ballot & lt_mask)] = make_uint2(pix, cell | extreme);
+        }
+        rn += __popc(ballot);
+    };
+
+    // float32 decisions for up to 32 stacked survivors, one per lane
+    auto decide32 = [&](uint32_t count) {
+        const uint32_t first = qn - count;
+        qn = first;
+        bool defer_me = false, have = false;
+        uint32_t pix = 0, cell = 0;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef SMAP_ABL_NO_DRAIN   // ablation builds (profiles/): streaming + cull + stack traffic alone
+        if ((uint32_t)lane < count) {
+            w = queue[first + lane];
+            if (w.x == 1234.5f) atomicOr(F.mask, (uint32_t)w.z);
+        }
+        count = 0;
+#endif
+        if ((uint32_t)lane < count) {
+            w = queue[first + lane];
+            const float2 lxy = __fadd2_rn(make_float2(w.x, w.y), fk.n_ctr_xy);
+            const float lz = w.z + fk.n_ctr_z;
+            const float rho = fabsf(lxy.x) + fabsf(lxy.y) + fabsf(lz);
+            const float2 xx = make_float2(lxy.x, lxy.x), yy = make_float2(lxy.y, lxy.y), zz = make_float2(lz, lz);
+            const float2 uv = __ffma2_rn(fk.d_uv[0], xx, __ffma2_rn(fk.d_uv[1], yy, __ffma2_rn(fk.d_uv[2], zz, fk.d_uv[3])));
+            const float2 cd = __ffma2_rn(fk.d_cd[0], xx, __ffma2_rn(fk.d_cd[1], yy, __ffma2_rn(fk.d_cd[2], zz, fk.d_cd[3])));
+            float rc;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(cd.x));
+            // us = uv * rc is never rounded on its own: both uses are fused (one rounding each), which the error
+            // bound covers either way.  (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under
+            // -fmad=false, so the fusion is spelled out instead of being left to the compiler.)
+            const float2 rc2 = make_float2(rc, rc);
+            const float hg = fmaf(-fmaf(fk.g_k1, rho, fk.g_k0), fabsf(rc), fk.g_hc);
+            const float2 mg = make_float2(kMagic32, kMagic32), nmg = make_float2(-kMagic32, -kMagic32);
+            float2 tp = __ffma2_rn(uv, rc2, mg);                               // RN(us) + magic
+            const float2 rp = __fadd2_rn(tp, nmg);                             // RN(us), exact
+            const float2 dp = __ffma2_rn(uv, rc2, make_float2(-rp.x, -rp.y));  // us - RN(us)
+            const float2 op = __fadd2_rn(rp, make_float2(-fk.mid_uv.x, -fk.mid_uv.y));
+            // cell
+            const float2 ts = __ffma2_rn(lxy, make_float2(fk.cell_rf, fk.cell_rf), fk.cell_f0);
+            const float hgc = fmaf(-fk.cell_kc, rho, fk.cell_hg0);
+            float2 tc = __fadd2_rn(ts, mg);
+            const float2 rcl = __fadd2_rn(tc, nmg);
+            const float2 dcl = __fadd2_rn(ts, make_float2(-rcl.x, -rcl.y));
+            const float2 oc = __fadd2_rn(rcl, make_float2(-fk.mid_c.x, -fk.mid_c.y));
+            // every comparison is written so that a NaN anywhere means "not certified"
+            bool cert = rho < fk.coord_l;
+            cert &= fabsf(cd.y - fk.r_h) < fmaf(-fk.r_kd, rho, fk.r_thr0);
+            cert &= (fabsf(dp.x) < hg) & (fabsf(dp.y) < hg);
+            cert &= (fabsf(dcl.x) < hgc) & (fabsf(dcl.y) < hgc);
+            const bool inside = (fabsf(op.x) <= fk.half_uv.x) & (fabsf(op.y) <= fk.half_uv.y) &
+                                (fabsf(oc.x) <= fk.half_c.x) & (fabsf(oc.y) <= fk.half_c.y);
+            defer_me = !cert;
+            have = cert & inside;
+            tp.x = fmaxf(tp.x, kMagic32); tp.y = fmaxf(tp.y, kMagic32);              // floor -1 -> pixel 0
+            tc.x = fmaxf(tc.x, fk.clamp_c.x); tc.y = fmaxf(tc.y, fk.clamp_c.y);      // floor -1 -> cell 0
+            pix = __float_as_uint(tp.y) * (uint32_t)F.fp.img_w + __float_as_uint(tp.x) + fk.pix_k;
+            cell = __float_as_uint(tc.x) * (uint32_t)gp.mw + __float_as_uint(tc.y) + fk.cell_k;
+            if (MODE == 0 && have) {
+                fbx0 = fminf(fbx0, tc.x); fbx1 = fmaxf(fbx1, tc.x);
+                fby0 = fminf(fby0, tc.y); fby1 = fmaxf(fby1, tc.y);
+            }
+        }
+        push_record(have, pix, cell, w.w);
+        const unsigned dballot = __ballot_sync(0xffffffffu, defer_me);
+#ifdef SMAP_FUSE_STATS
+        {
+            const unsigned aballot = __ballot_sync(0xffffffffu, have);
+            if (lane == 0) {
+                atomicAdd(&g_fuse_stats[0], (unsigned long long)count);
+                atomicAdd(&g_fuse_stats[1], (unsigned long long)__popc(dballot));
+                atomicAdd(&g_fuse_stats[2], (unsigned long long)__popc(aballot));
+            }
+        }
+#endif
+#ifndef SMAP_ABL_NO_DEFER   // ablation builds: deferred points are dropped (wrong results, timing only)
+        if (dballot) {
+            if (defer_me) defer[dn + __popc(dballot & lt_mask)] = w;
+            dn += __popc(dballot);
+        }
+#endif
+    };
+
+    // float64 decisions for up to 32 deferred points
+    auto decide64 = [&](uint32_t count) {
+        const uint32_t first = dn - count;
+        dn = first;
+        bool have = false;
+        uint2 pc = make_uint2(0u, kNone);
+        float it = 0.f;
+        if ((uint32_t)lane < count) {
+            const float4 w = defer[first + lane];
+            it = w.w;
+            pc = fuse_decide64(&F.fp, &gp, w);
+            have = pc.y != kNone;
+            if (MODE == 0 && have) {
+                const int cx = (int)(pc.y / (uint32_t)gp.mw), cy = (int)(pc.y - (uint32_t)cx * (uint32_t)gp.mw);
+                ibx0 = min(ibx0, cx); ibx1 = max(ibx1, cx); iby0 = min(iby0, cy); iby1 = max(iby1, cy);
+            }
+        }
+        push_record(have, pc.x, pc.y, it);
+    };
+
+    // label lookup + update for up to 32 * kFGather records, kFGather per lane, in straight-line code: all the label
+    // bytes are requested before the first one is used, then all the tag atomics are issued before the first
+    // result is used -- the two memory round trips are paid once per 32 * kFGather records.  (A software pipeline that
+    // carried loads and atomics across loop iterations was tried first: ptxas puts every carried operation on one
+    // scoreboard and waits for it at the loop head, which serialised everything.)
+    auto gather = [&](uint32_t count) {
+        const uint32_t first = rn - count;
+        rn = first;
+        uint32_t cellf[kFGather], lr[kFGather], lg[kFGather];
+#pragma unroll
+        for (int k = 0; k < kFGather; ++k) {
+            const uint32_t i = (uint32_t)(k * 32 + lane);
+            cellf[k] = kNone;
+            lr[k] = 0; lg[k] = 0;
+            if (i < count) {
+                const uint2 rec = recs[first + i];
+                cellf[k] = rec.y;
+#ifdef SMAP_ABL_NO_GATHER
+                lr[k] = (rec.x & 1u) ? 128u : 255u; lg[k] = (rec.x & 1u) ? 64u : 255u;
+#else
+                const uint8_t* px = f_image + (size_t)rec.x * 3u;
+                lr[k] = __ldg(px);
+                lg[k] = __ldg(px + 1);
+#endif
+            }
+        }
+        uint32_t bits[kFGather], old0[kFGather], old1[kFGather];
+#pragma unroll
+        for (int k = 0; k < kFGather; ++k) {
+            bits[k] = (cellf[k] != kNone) ? (s_tab_r[lr[k]] & s_tab_g[lg[k]]) : 0u;
+            old0[k] = fk.tag; old1[k] = fk.tag;
+#ifdef SMAP_ABL_NO_SCATTER
+            if (bits[k] && cellf[k] == 0x7ffffff0u) atomicOr(F.mask, bits[k]);
+            bits[k] = 0;
+#endif
+            if (!bits[k]) continue;
+            const uint32_t cell = cellf[k] & 0x7fffffffu;
+            const bool boost = (bits[k] & lane_bit) && (cellf[k] >> 31);
+            if (MODE == 0) {
+                atomicOr(F.mask + cell, boost ? (bits[k] | (1u << gp.c)) : bits[k]);   // result unused: RED.OR
+                bits[k] = 0;
+            } else {
+                uint32_t* trow = F.tags + cell * c1;   // element indices fit 32 bits (checked by the host)
+                if (bits[k] & (bits[k] - 1u)) {
+                    // several classes share this pixel's (R, G): rare, done in place
+                    double* row = map + cell * (uint32_t)gp.c;
+                    uint32_t b = bits[k];
+                    while (b) {
+                        const int i = __ffs(b) - 1;
+                        b &= b - 1u;
+                        if (atomicMax(trow + i, fk.tag) != fk.tag) atomicAdd(row + i, 1.0);
+                    }
+                    if (boost && atomicMax(trow + gp.c, fk.tag) != fk.tag) atomicAdd(row + gp.lane, 2.0);
+                    bits[k] = 0;
+                } else {
+                    const uint32_t cls = (uint32_t)__ffs(bits[k]) - 1u;
+                    old0[k] = atomicMax(trow + cls, fk.tag);
+                    if (boost) old1[k] = atomicMax(trow + gp.c, fk.tag);
+                    bits[k] = cell * (uint32_t)gp.c + cls;   // from here on: the grid element
+                }
+            }
+        }
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < kFGather; ++k) {
+                if (old0[k] != fk.tag) atomicAdd(map + bits[k], 1.0);
+                if (old1[k] != fk.tag) atomicAdd(map + bits[k], 2.0);
+            }
+        }
+    };
+
+    auto drain = [&](uint32_t count) {
+        decide32(count);
+        __syncwarp();
+        if (dn >= 32u) {
+            decide64(32u);
+            __syncwarp();
+        }
+        if (rn >= 32u * kFGather) {
+            gather(32u * kFGather);
+            __syncwarp();
+        }
+    };
+
+    for (int r = 0; r < n_rounds; ++r) {
+        // keep kFStages - 1 rounds in flight: the next one goes into the stage that round r - 1 used (every lane
+        // has consumed its reads of that stage, and the warp has re-converged since)
+        issue_round();
+        const int st = r % kFStages;
+        const uint32_t parity = (uint32_t)(r / kFStages) & 1u;
+        while (!mbar_try_wait(bars + st, parity)) {}
+        const int left = w_pts - r * kFRoundPts;
+        const int pts = left < kFRoundPts ? left : kFRoundPts;
+        const float4* sp = stages + st * kFRoundPts + lane;
+#pragma unroll
+        for (int j = 0; j < kFRound; ++j) {
+            const float4 w = sp[j * 32];
+            const bool pass = cull32(fk, w.x, w.y, w.z) & (j * 32 + lane < pts);
+            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+            if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
+            qn += __popc(ballot);
+        }
+        __syncwarp();
+        while (qn >= 32u) drain(32u);
+    }
+    // flush: the partial batch of survivors, the deferred points, the records
+    if (qn) drain(qn);
+    if (dn) {
+        decide64(dn);
+        __syncwarp();
+    }
+    while (rn) {
+        gather(rn < 32u * kFGather ? rn : 32u * kFGather);
+        __syncwarp();
+    }
+
+    if (MODE == 1) {
+        // frame blockIdx.y + 2 reuses this frame's tag plane: publish "this block's atomics are performed"
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(frames_done + blockIdx.y, 1u);
+    }
+    if (MODE == 0) {
+        FrameBox* box = boxes + blockIdx.y;
+        // fold the bounding boxes: lane -> warp -> block (shared atomics) -> frame (4 global atomics per block)
+        int bx0 = ibx0, bx1 = ibx1, by0 = iby0, by1 = iby1;
+        if (fbx1 >= fbx0) {
+            // magic-shifted float -> cell coordinate: bits - (bits(magic) - I0); clamp_c = magic - I0
+            const int ox = (int)__float_as_uint(fk.clamp_c.x), oy = (int)__float_as_uint(fk.clamp_c.y);
+            bx0 = min(bx0, (int)__float_as_uint(fbx0) - ox); bx1 = max(bx1, (int)__float_as_uint(fbx1) - ox);
+            by0 = min(by0, (int)__float_as_uint(fby0) - oy); by1 = max(by1, (int)__float_as_uint(fby1) - oy);
+        }
+        if (__any_sync(0xffffffffu, bx1 >= bx0)) {
+            const int a = __reduce_min_sync(0xffffffffu, bx0), b = __reduce_max_sync(0xffffffffu, bx1);
+            const int c = __reduce_min_sync(0xffffffffu, by0), d = __reduce_max_sync(0xffffffffu, by1);
+            if (lane == 0) {
+                atomicMin(&s_box[0], a); atomicMax(&s_box[1], b);
+                atomicMin(&s_box[2], c); atomicMax(&s_box[3], d);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_box[1] >= s_box[0]) {
+            atomicMin(&box->x0, s_box[0]); atomicMax(&box->x1, s_box[1]);
+            atomicMin(&box->y0, s_box[2]); atomicMax(&box->y1, s_box[3]);
+        }
+    }
+}
+
+}  // namespace smap

@@ -17,7 +17,8 @@ constexpr int kThreads = 256;
 // (cell, class) de-duplication of the reference's fancy-index "+=" (src/mapping_replay.py:281,294).  The
 // scatter only issues fire-and-forget RED.OR (no returned atomics); k_apply reads the words inside the
 // frame's bounding box, adds the update-matrix columns in frame and class order, and writes the words back
-// to zero, so a slot is always clean between launches.
+// to zero, so a slot is always clean between launches.  (The count update on float4 clouds does not use the
+// masks at all: k_fuse MODE 1, smap_fuse.cuh.)
 // ------------------------------------------------------------------------------------------------
 
 // Bounding box (in cells, inclusive) of everything a frame touched; written by the scatter kernels.
@@ -27,9 +28,9 @@ struct FrameBox {
 
 __device__ __forceinline__ void box_reset(int* b) { b[0] = 0x7fffffff; b[1] = -1; b[2] = 0x7fffffff; b[3] = -1; }
 
-// One frame = one launch of k_stream: every per-frame constant is then a kernel parameter at a fixed offset,
-// i.e. a constant-bank operand of the FP64 instructions (no register, no load).  A batched launch indexed by
-// blockIdx.y was tried: the run-time frame index turned every constant into a register-indexed LDC.
+// One frame = one launch: every per-frame constant is then a kernel parameter at a fixed offset, i.e. a
+// constant-bank operand of the FP64 instructions (no register, no load).  A batched launch indexed by blockIdx.y
+// was tried: the run-time frame index turned every constant into a register-indexed LDC.
 struct StreamParams {
     FrameParams fp;
     const void* pts;
@@ -41,7 +42,7 @@ struct StreamParams {
 
 // tuning knobs (overridable at compile time for the variant sweeps recorded in profiles/)
 #ifndef SMAP_STREAM_ROUND
-#define SMAP_STREAM_ROUND 4     // 32-point chunks per round: LDG.128 per lane in flight (x2 with the prefetch)
+#define SMAP_STREAM_ROUND 4     // 32-point chunks per round
 #endif
 #ifndef SMAP_STREAM_MINB
 #define SMAP_STREAM_MINB 3      // resident blocks per SM the register allocation aims for
@@ -51,9 +52,6 @@ constexpr int kRound = SMAP_STREAM_ROUND;
 constexpr int kRoundPts = 32 * kRound;                // points a warp handles per round
 constexpr int kBlockRoundPts = kWarps * kRoundPts;    // points a block handles per round
 constexpr int kQueueCap = kRoundPts + 32;             // per-warp survivor stack: < 32 left over + one round
-
-template <int LAYOUT> struct QueueEntry { typedef float4 type; };
-template <> struct QueueEntry<1> { typedef uint32_t type; };
 
 // The reference's own rounding chain for one point; only reached when the certified fast path cannot decide.
 // Everything by value (a pointer to a caller's local would force it onto the stack in the hot loop).
@@ -70,31 +68,22 @@ __device__ __noinline__ long long exact_cell_slow(const GridParams* g, double x,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1+K2+K3a fused, persistent and warp-autonomous: project -> cull -> label lookup -> class bits -> cell ->
-// mask scatter (src/mapping_replay.py:223-244, :261-277, :288-290).
+// k_stream_soa: the fused path for the reference's own cloud layout, (4, N) float64 rows
+// (project -> cull -> label lookup -> class bits -> cell -> mask scatter; src/mapping_replay.py:223-244,
+// :261-277, :288-290).  float4 clouds -- the fast path -- go through k_fuse (smap_fuse.cuh).
 //
-// One launch per frame (up to kMaxBatch frames, each with its own mask slot, are queued back to back before
-// one k_apply).  The blocks walk the cloud in rounds of kBlockRoundPts points; inside a round every warp owns
-// a contiguous slice and never synchronises with the other warps:
-//   stream   kRound coalesced LDG.128 per lane per round, the next round prefetched into registers before the
-//            current one is processed; conservative float32 cull (precull_pass, constants straight from the
-//            parameter bank); survivors (~35 %)
-//            pushed on the warp's private stack in shared memory (ballot + popc, no atomics);
-//   drain    whenever >= 32 survivors are stacked, pop 32 - one per lane, all lanes busy: certified fast
+// Persistent and warp-autonomous: the blocks walk the cloud in rounds of kBlockRoundPts points; inside a round
+// every warp owns a contiguous slice and never synchronises with the other warps:
+//   stream   conservative float32 cull (precull_pass) on the coordinates rounded to float; the indices of the
+//            survivors (~35 %) go on the warp's private stack in shared memory (ballot + popc, no atomics);
+//   drain    whenever >= 32 survivors are stacked, pop 32 - one per lane, all lanes busy: float64 certified fast
 //            projection (exact fallback), label gather, class bits from the shared colour tables, certified
 //            fast cell index, one RED.OR into the frame's mask slot; lanes track the bounding box.
+// k_apply then replays the masks of the batch in frame and class order (any update matrix, any grid).
 // ------------------------------------------------------------------------------------------------
-// MODE 0: masks only -- k_apply adds the update-matrix columns in frame and class order (any matrix, any grid).
-// MODE 1: count update (matrix == np.eye(C)) on a grid that holds integer-valued counts: the atomicOr returns
-//         what the frame had already put in the cell, and every NEWLY set class bit adds 1.0 to map[cell, class]
-//         (a newly set boost bit 2.0 to map[cell, lane]) with a float64 RED.  Sums of small integers are exact in
-//         any order, so the grid is bit-identical to the ordered update; k_apply then only clears the masks.
-template <int LAYOUT, int MODE>
 __global__ void __launch_bounds__(kThreads, SMAP_STREAM_MINB)
-k_stream(const __grid_constant__ StreamParams F, const __grid_constant__ GridParams gp, FrameBox* __restrict__ box,
-         double* __restrict__ map) {
-    typedef typename QueueEntry<LAYOUT>::type Entry;
-    __shared__ __align__(16) Entry s_queue[kWarps][kQueueCap];
+k_stream_soa(const __grid_constant__ StreamParams F, const __grid_constant__ GridParams gp, FrameBox* __restrict__ box) {
+    __shared__ uint32_t s_queue[kWarps][kQueueCap];
     __shared__ uint32_t s_tab_r[256], s_tab_g[256];
     __shared__ int s_box[4];
 
@@ -102,18 +91,16 @@ k_stream(const __grid_constant__ StreamParams F, const __grid_constant__ GridPar
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    Entry* const queue = s_queue[warp];
+    uint32_t* const queue = s_queue[warp];
 
     build_color_tables(gp, s_tab_r, s_tab_g);
     if (threadIdx.x == 0) box_reset(s_box);
     __syncthreads();
 
-    const void* const f_pts = F.pts;
+    const double* const pd = reinterpret_cast<const double*>(F.pts);
     const uint8_t* const f_image = F.image;
     uint32_t* const f_mask = F.mask;
     const int64_t f_n = F.n, f_ld = F.ld;
-    // label image readable with aligned 32-bit loads (base aligned, size a multiple of 4)
-    const bool f_words = ((reinterpret_cast<uintptr_t>(f_image) & 3u) == 0u) && (((int64_t)fp.img_w * fp.img_h * 3) % 4 == 0);
 
     uint32_t qn = 0;       // entries on this warp's stack (warp-uniform)
     int bx0 = 0x7fffffff, bx1 = -1, by0 = 0x7fffffff, by1 = -1;
@@ -123,47 +110,18 @@ k_stream(const __grid_constant__ StreamParams F, const __grid_constant__ GridPar
         const uint32_t first = qn - count;
         qn = first;
         if ((uint32_t)lane >= count) return;
-        double x, y, z;
-        float it;
-        bool coords_ok;
-        if (LAYOUT == 0) {
-            const float4 w = *reinterpret_cast<const float4*>(&queue[first + lane]);
-            coords_ok = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fabsf(w.z)) < (float)kCoordBound;
-            x = (double)w.x; y = (double)w.y; z = (double)w.z; it = w.w;
-        } else {
-            const double* pd = reinterpret_cast<const double*>(f_pts);
-            const int64_t k = (int64_t)*reinterpret_cast<const uint32_t*>(&queue[first + lane]);
-            x = __ldg(pd + k); y = __ldg(pd + f_ld + k); z = __ldg(pd + 2 * f_ld + k);
-            coords_ok = fmax(fmax(fabs(x), fabs(y)), fabs(z)) < kCoordBound;
-            // the boost test compares the float64 intensity with 2 and 14; rounding to float32 could move a
-            // value across them, so map the double onto a float on the same side (NaN: neither)
-            const double itd = __ldg(pd + 3 * f_ld + k);
-            it = (itd < 2.0) ? 0.0f : ((itd > 14.0) ? 15.0f : 8.0f);
-        }
-#ifdef SMAP_ABL_NO_DRAIN   // ablation builds (profiles/): the streaming + cull alone
-        if (x == 1234.5) atomicOr(f_mask, (uint32_t)z);
-        return;
-#endif
+        const int64_t k = (int64_t)queue[first + lane];
+        const double x = __ldg(pd + k), y = __ldg(pd + f_ld + k), z = __ldg(pd + 2 * f_ld + k);
+        const bool coords_ok = fmax(fmax(fabs(x), fabs(y)), fabs(z)) < kCoordBound;
+        // the boost test compares the float64 intensity with 2 and 14; rounding to float32 could move a
+        // value across them, so map the double onto a float on the same side (NaN: neither)
+        const double itd = __ldg(pd + 3 * f_ld + k);
+        const float it = (itd < 2.0) ? 0.0f : ((itd > 14.0) ? 15.0f : 8.0f);
         int pix = fast_project(fp, x, y, z, coords_ok);
         if (pix == kAsk) pix = exact_project_slow(&fp, x, y, z);
         if (pix < 0) return;
-        const uint32_t off = 3u * ((uint32_t)(pix >> 16) * (uint32_t)fp.img_w + (uint32_t)(pix & 0xffff));
-        uint32_t r, g;
-#ifdef SMAP_ABL_NO_GATHER
-        r = (off & 1u) ? 128u : 255u; g = (off & 1u) ? 64u : 255u;
-        if (false)
-#endif
-        if (f_words) {
-            // R and G sit in one aligned 32-bit word unless R is its last byte
-            const uint32_t sh = (off & 3u) * 8u;
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(f_image) + (off >> 2);
-            const uint32_t w0 = __ldg(wp);
-            r = (w0 >> sh) & 0xffu;
-            g = (sh == 24u) ? (__ldg(wp + 1) & 0xffu) : ((w0 >> (sh + 8u)) & 0xffu);
-        } else {
-            r = __ldg(f_image + off);
-            g = __ldg(f_image + off + 1);
-        }
+        const size_t off = 3u * ((size_t)(pix >> 16) * (size_t)fp.img_w + (size_t)(pix & 0xffff));
+        const uint32_t r = __ldg(f_image + off), g = __ldg(f_image + off + 1);
         const uint32_t bits = class_bits_lut(gp, s_tab_r, s_tab_g, (uint8_t)r, (uint8_t)g, it);
         if (!bits) return;
         int cx = 0, cy = 0;
@@ -175,91 +133,30 @@ k_stream(const __grid_constant__ StreamParams F, const __grid_constant__ GridPar
         } else if (on == kDrop) {
             return;
         }
-#ifdef SMAP_ABL_NO_SCATTER
-        if (cx == 0x7ffffff0) atomicOr(f_mask, bits);
-        return;
-#endif
         const uint32_t cell = (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy;
-        if (MODE == 0) {
-            atomicOr(f_mask + cell, bits);   // result unused: RED.OR, nothing waits for it
-        } else {
-            uint32_t fresh = bits & ~atomicOr(f_mask + cell, bits);
-            double* row = map + (size_t)cell * gp.c;
-            if (fresh >> gp.c) {   // boost bit newly set: +2 on the lane class (src/mapping_replay.py:294)
-                atomicAdd(row + gp.lane, 2.0);
-                fresh &= (1u << gp.c) - 1u;
-            }
-            while (fresh) {
-                const int i = __ffs(fresh) - 1;
-                fresh &= fresh - 1u;
-                atomicAdd(row + i, 1.0);
-            }
-        }
+        atomicOr(f_mask + cell, bits);   // result unused: RED.OR, nothing waits for it
         bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
     };
 
-    // rounds of this block: r = blockIdx.x, blockIdx.x + gridDim.x, ...; this warp's slice of round r starts at
-    // r * kBlockRoundPts + warp * kRoundPts
     const int64_t stride = (int64_t)gridDim.x * kBlockRoundPts;
-    int64_t rbase = (int64_t)blockIdx.x * kBlockRoundPts + (int64_t)warp * kRoundPts;
-
-    // a round that lies completely inside the cloud (all but the last one) needs no per-lane bounds checks
-    auto load_round = [&](int64_t base, float4 (&dst)[kRound]) {
-        const float4* p = reinterpret_cast<const float4*>(f_pts) + base + lane;
-        if (base + kRoundPts <= f_n) {
-#pragma unroll
-            for (int j = 0; j < kRound; ++j) dst[j] = __ldcs(p + j * 32);
-        } else {
-#pragma unroll
-            for (int j = 0; j < kRound; ++j)
-                dst[j] = (base + j * 32 + lane < f_n) ? __ldcs(p + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    float4 buf[kRound];
-    if constexpr (LAYOUT == 0) {
-        if (rbase < f_n) load_round(rbase, buf);
-    }
-    while (rbase < f_n) {
-        const int64_t nbase = rbase + stride;
-        float4 pre[kRound];
-        if constexpr (LAYOUT == 0) {   // next round in flight while this one is processed
-            if (nbase < f_n) load_round(nbase, pre);
-        }
-        if constexpr (LAYOUT == 0) {
-            const bool full = rbase + kRoundPts <= f_n;
-#pragma unroll
-            for (int j = 0; j < kRound; ++j) {
-                const float4 w = buf[j];
-                bool pass = precull_pass_packed(fp, w.x, w.y, w.z);
-                if (!full) pass &= (rbase + j * 32 + lane < f_n);
-                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                if (pass) *reinterpret_cast<float4*>(&queue[qn + __popc(ballot & lt_mask)]) = w;
-                qn += __popc(ballot);
-            }
-        } else {
-            const double* pd = reinterpret_cast<const double*>(f_pts);
+    for (int64_t rbase = (int64_t)blockIdx.x * kBlockRoundPts + (int64_t)warp * kRoundPts; rbase < f_n; rbase += stride) {
 #pragma unroll 2
-            for (int j = 0; j < kRound; ++j) {
-                const int64_t k = rbase + j * 32 + lane;
-                bool pass = false;
-                if (k < f_n) {
-                    pass = precull_pass(fp, (float)__ldg(pd + k), (float)__ldg(pd + f_ld + k), (float)__ldg(pd + 2 * f_ld + k));
-                }
-                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                if (pass) *reinterpret_cast<uint32_t*>(&queue[qn + __popc(ballot & lt_mask)]) = (uint32_t)k;
-                qn += __popc(ballot);
+        for (int j = 0; j < kRound; ++j) {
+            const int64_t k = rbase + j * 32 + lane;
+            bool pass = false;
+            if (k < f_n) {
+                // a coordinate that is not float32-representable only moves by one rounding: covered by kCullSlack
+                pass = precull_pass(fp, (float)__ldg(pd + k), (float)__ldg(pd + f_ld + k), (float)__ldg(pd + 2 * f_ld + k));
             }
+            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+            if (pass) queue[qn + __popc(ballot & lt_mask)] = (uint32_t)k;
+            qn += __popc(ballot);
         }
         __syncwarp();
         while (qn >= 32u) {
             drain_batch(32u);
             __syncwarp();
         }
-        if constexpr (LAYOUT == 0) {
-#pragma unroll
-            for (int j = 0; j < kRound; ++j) buf[j] = pre[j];
-        }
-        rbase = nbase;
     }
     while (qn) {
         drain_batch(qn < 32u ? qn : 32u);
@@ -338,8 +235,7 @@ template <> __device__ __forceinline__ void mask_vec_load<2>(const uint32_t* p, 
 }
 template <> __device__ __forceinline__ void mask_vec_load<1>(const uint32_t* p, uint32_t (&w)[1]) { w[0] = *p; }
 
-// CLEAR_ONLY: the grid was already updated by k_stream MODE 1; only count and zero the touched words.
-template <int NJ, bool CLEAR_ONLY>
+template <int NJ>
 __global__ void __launch_bounds__(kThreads)
 k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameBox* __restrict__ boxes,
         FrameBox* __restrict__ next_boxes, unsigned long long* __restrict__ touched_total,
@@ -411,12 +307,6 @@ k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameB
             for (int f = 0; f < kMaxBatch; ++f) anyv |= w[f][v];
             if (!anyv) continue;
             const uint32_t cell = cell0 + v;
-            if (CLEAR_ONLY) {
-#pragma unroll
-                for (int f = 0; f < kMaxBatch; ++f)
-                    if (w[f][v]) { ap.mask[f][cell] = 0u; ++mine; }
-                continue;
-            }
             double* row = map + (size_t)cell * c;
             double acc[8 * NJ];
 #pragma unroll
