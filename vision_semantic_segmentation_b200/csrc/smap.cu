@@ -11,6 +11,16 @@
 #include "smap_kernels.cuh"
 #include "smap_fuse.cuh"
 
+#ifndef SMAP_AUX_STREAMS
+#define SMAP_AUX_STREAMS 2      // internal streams the per-frame k_fuse launches of a batch alternate over
+#endif
+#ifndef SMAP_FUSE_GRID_DIV
+#define SMAP_FUSE_GRID_DIV 1    // > 1: a frame's launch fills only 1/DIV of the resident block slots, so that the
+#endif                          // launches of DIV frames (on different internal streams) run side by side
+#ifndef SMAP_FUSE_PERSISTENT
+#define SMAP_FUSE_PERSISTENT 0  // 1: one persistent k_fuse launch per batch (measured alternative, see smap_fuse.cuh)
+#endif
+
 using namespace smap;
 
 namespace {
@@ -71,9 +81,14 @@ struct smap_handle {
     int sm_count = 148;
     bool identity_cm = false;   // update matrix is exactly np.eye(C): the count update
     bool integer_grid = false;  // the grid is known to hold integer-valued counts (zeroed by us, then only count updates)
-    // batched k_fuse launch: parameter block (13 KB, rebuilt per launch) and the per-frame block-completion counters
-    FuseBatch fuse_batch;
-    unsigned int* frames_done = nullptr;      // [kMaxBatch]
+    // k_fuse launches of one batch alternate over a few internal streams (fork / join with events around the
+    // batch): the frames are independent, so the ramp-up and tail of one launch overlap the next one's body
+    static constexpr int kAux = SMAP_AUX_STREAMS;
+    cudaStream_t aux[kAux > 0 ? kAux : 1] = {};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[kAux > 0 ? kAux : 1] = {};
+    FuseBatchT<1> fuse_one;               // parameter block of the next k_fuse launch
+    FuseBatchT<kMaxBatch> fuse_batch;     // the same for the persistent variant (about 14 KB)
     // class tables
     double* cm_dev = nullptr;
     uint8_t colors[SMAP_MAX_CLASSES * 3];
@@ -429,14 +444,17 @@ int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* f
     return SMAP_OK;
 }
 
-// Tag planes of the count update (k_fuse MODE 1): zero = "never written"; frame tags start at 1.
-int ensure_tags(smap_handle* h, int planes) {
-    if (planes <= h->n_tag_planes) return SMAP_OK;
+// Tag planes of the count update (k_fuse MODE 1); zero = "never written", frame tags start at 1.
+//   one launch per frame:  one plane per internal stream (launches on one stream are serialised)
+//   persistent launch:     one plane per frame of a launch, interleaved per element; as many as a batch has frames when
+//                          memory allows (a quarter of what is free at the first call), never fewer than one
+int ensure_tags(smap_handle* h, int want) {
+    if (h->n_tag_planes > 0) return SMAP_OK;
     const size_t plane_bytes = sizeof(uint32_t) * (size_t)h->cells * (size_t)(h->cfg.num_classes + 1);
-    CK(cudaDeviceSynchronize());
-    if (h->tags) CK(cudaFree(h->tags));
-    h->tags = nullptr;
-    h->n_tag_planes = 0;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    int planes = want;
+    while (planes > 1 && plane_bytes * (size_t)planes > free_b / 4) planes /= 2;
     CK(cudaMalloc(&h->tags, plane_bytes * planes));
     CK(cudaMemset(h->tags, 0, plane_bytes * planes));
     h->n_tag_planes = planes;
@@ -444,14 +462,45 @@ int ensure_tags(smap_handle* h, int planes) {
     return SMAP_OK;
 }
 
-// One k_fuse launch for all the non-empty float4 frames of a batch (frame = blockIdx.y).  Count update: nothing
-// else to do afterwards; otherwise frame i of the non-empty ones scatters into mask slot i and *slots_used tells
-// k_apply how many there are.
+int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp, bool count_atomics, int slot, FuseFrame& f) {
+    if (fr->layout != SMAP_PTS_F32X4) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
+    if ((int64_t)fr->image_width * fr->image_height >= ((int64_t)1 << kFidShift))
+        return fail(SMAP_ERR_INVALID, "label image has 2^28 pixels or more");
+    f.fp = fp;
+    fill_fast32(h, fr, fp, f.fk);
+    f.pts = static_cast<const float4*>(fr->points_dev);
+    f.image = fr->image_dev;
+    f.mask = count_atomics ? nullptr : h->mask + (size_t)slot * h->slot_words;
+    f.fk.tag = ++h->frame_tag;   // larger than every tag written to this frame's plane before
+    f.n = fr->n_points;
+    f.img64 = ((reinterpret_cast<uintptr_t>(fr->image_dev) & 7u) == 0u &&
+               ((int64_t)fr->image_width * fr->image_height * 3) % 8 == 0) ? 1 : 0;
+    return SMAP_OK;
+}
+
+// persistent grid: as many blocks as stay resident, never more than the largest cloud has block-rounds
+int fuse_grid(const smap_handle* h, FuseFrame* f, int n, int64_t* gx_out) {
+    int64_t n_max = 0;
+    for (int k = 0; k < n; ++k) n_max = f[k].n > n_max ? f[k].n : n_max;
+    int64_t gx = (int64_t)h->sm_count * SMAP_FUSE_MINB / SMAP_FUSE_GRID_DIV;
+    const int64_t rounds = ceil_div(n_max, kFBlockRoundPts);
+    if (gx > rounds) gx = rounds;
+    for (int k = 0; k < n; ++k) {
+        const int64_t per = ceil_div(f[k].n, gx * kWarps);
+        if (per >= ((int64_t)1 << 31)) return fail(SMAP_ERR_INVALID, "cloud too large for one launch");
+        f[k].per_warp = (int32_t)per;
+    }
+    *gx_out = gx;
+    return SMAP_OK;
+}
+
+// Queue the float4 frames of a batch.  Count update: nothing else to do afterwards; otherwise frame i of the
+// non-empty ones scatters into mask slot i and *slots_used tells k_apply how many there are.
 int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, bool count_atomics,
                 cudaStream_t st, int* slots_used) {
     int used = 0;
     if (count_atomics) {
-        int rc = ensure_tags(h, 2);
+        int rc = ensure_tags(h, SMAP_FUSE_PERSISTENT ? kMaxBatch : (smap_handle::kAux > 0 ? smap_handle::kAux : 1));
         if (rc) return rc;
         if (h->frame_tag > 0xffffffffu - (uint32_t)n_frames - 1u) {   // tag space exhausted: start over
             CK(cudaDeviceSynchronize());
@@ -460,45 +509,85 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         }
     }
     if (!h->fuse_attr_set) {   // the per-warp TMA stages + stacks need more than the default 48 KB
-        CK(cudaFuncSetAttribute(k_fuse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFBlockSmem));
-        CK(cudaFuncSetAttribute(k_fuse<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFBlockSmem));
+        CK(cudaFuncSetAttribute(k_fuse<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
+        CK(cudaFuncSetAttribute(k_fuse<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
+        CK(cudaFuncSetAttribute(k_fuse<0, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
+        CK(cudaFuncSetAttribute(k_fuse<1, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
         h->fuse_attr_set = true;
     }
     const size_t plane_words = (size_t)h->cells * (size_t)(h->cfg.num_classes + 1);
-    FuseBatch* fb = &h->fuse_batch;
-    int64_t n_max = 0;
+#if SMAP_FUSE_PERSISTENT
+    const int per_launch = count_atomics ? h->n_tag_planes : kMaxBatch;
+    FuseBatchT<kMaxBatch>* fb = &h->fuse_batch;
+    int i = 0;
+    while (i < n_frames) {
+        int in_launch = 0;
+        const int first_slot = used;
+        for (; i < n_frames && in_launch < per_launch; ++i) {
+            if (frames[i].n_points == 0) continue;
+            int rc = fill_fuse_frame(h, frames + i, fps[i], count_atomics, used, fb->f[in_launch]);
+            if (rc) return rc;
+            ++in_launch;
+            ++used;
+        }
+        if (in_launch == 0) break;
+        int64_t gx = 0;
+        int rc = fuse_grid(h, fb->f, in_launch, &gx);
+        if (rc) return rc;
+        fb->tags = count_atomics ? h->tags : nullptr;
+        fb->n_frames = in_launch;
+        fb->tag_planes = h->n_tag_planes > 0 ? h->n_tag_planes : 1;
+        FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + first_slot;
+        if (count_atomics) k_fuse<1, kMaxBatch><<<(unsigned)gx, kThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
+        else k_fuse<0, kMaxBatch><<<(unsigned)gx, kThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
+        CK(cudaGetLastError());
+        h->stats.kernel_launches += 1;
+    }
+#else
+    // one launch per frame, alternating over the internal streams (fork / join with events around the batch)
+    int n_nonempty = 0;
+    for (int i = 0; i < n_frames; ++i) n_nonempty += frames[i].n_points > 0;
+    const bool fork = smap_handle::kAux > 0 && n_nonempty > 1 && !h->profiling;
+    if (fork) {
+        if (!h->ev_fork) {
+            CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            for (int a = 0; a < smap_handle::kAux; ++a) {
+                CK(cudaStreamCreateWithFlags(&h->aux[a], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming));
+            }
+        }
+        CK(cudaEventRecord(h->ev_fork, st));
+        for (int a = 0; a < smap_handle::kAux; ++a) CK(cudaStreamWaitEvent(h->aux[a], h->ev_fork, 0));
+    }
+    FuseBatchT<1>* fb = &h->fuse_one;
     for (int i = 0; i < n_frames; ++i) {
         if (frames[i].n_points == 0) continue;
-        if (frames[i].layout != SMAP_PTS_F32X4) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
-        FuseFrame& f = fb->f[used];
-        f.fp = fps[i];
-        fill_fast32(h, frames + i, fps[i], f.fk);
-        f.pts = static_cast<const float4*>(frames[i].points_dev);
-        f.image = frames[i].image_dev;
-        f.fk.tag = ++h->frame_tag;
-        f.mask = count_atomics ? nullptr : h->mask + (size_t)used * h->slot_words;
-        // consecutive frames alternate between the two tag planes; k_fuse makes frame f + 2 wait for frame f
-        f.tags = count_atomics ? h->tags + plane_words * (f.fk.tag & 1u) : nullptr;
-        f.n = frames[i].n_points;
-        if (f.n > n_max) n_max = f.n;
+        const int lane_stream = fork ? used % smap_handle::kAux : 0;
+        cudaStream_t ls = fork ? h->aux[lane_stream] : st;
+        int rc = fill_fuse_frame(h, frames + i, fps[i], count_atomics, used, fb->f[0]);
+        if (rc) return rc;
+        int64_t gx = 0;
+        rc = fuse_grid(h, fb->f, 1, &gx);
+        if (rc) return rc;
+        // one tag plane per launching stream; a frame's tag is larger than every tag written to its plane before
+        fb->tags = count_atomics ? h->tags + plane_words * (size_t)(lane_stream % h->n_tag_planes) : nullptr;
+        fb->n_frames = 1;
+        fb->tag_planes = 1;
+        FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + used;
+        if (count_atomics) k_fuse<1, 1><<<(unsigned)gx, kThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+        else k_fuse<0, 1><<<(unsigned)gx, kThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+        CK(cudaGetLastError());
+        h->stats.kernel_launches += 1;
         ++used;
     }
-    *slots_used = used;
-    if (used == 0) return SMAP_OK;
-    // one full wave of resident blocks per frame (fewer for a small cloud): at most two frames are then in flight
-    int64_t gx = (int64_t)h->sm_count * SMAP_FUSE_MINB;
-    const int64_t rounds = ceil_div(n_max, kFBlockRoundPts);
-    if (gx > rounds) gx = rounds;
-    const dim3 grid((unsigned)gx, (unsigned)used);
-    FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch;
-    if (count_atomics) {
-        CK(cudaMemsetAsync(h->frames_done, 0, sizeof(unsigned int) * kMaxBatch, st));
-        k_fuse<1><<<grid, kThreads, kFBlockSmem, st>>>(*fb, h->gp, boxes, h->map, h->frames_done);
-    } else {
-        k_fuse<0><<<grid, kThreads, kFBlockSmem, st>>>(*fb, h->gp, boxes, h->map, h->frames_done);
+    if (fork) {
+        for (int a = 0; a < smap_handle::kAux; ++a) {
+            CK(cudaEventRecord(h->ev_join[a], h->aux[a]));
+            CK(cudaStreamWaitEvent(st, h->ev_join[a], 0));
+        }
     }
-    CK(cudaGetLastError());
-    h->stats.kernel_launches += 1;
+#endif
+    *slots_used = used;
     return SMAP_OK;
 }
 
@@ -629,7 +718,6 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     if (e == cudaSuccess) e = cudaMalloc(&h->cm_dev, sizeof(double) * SMAP_MAX_CLASSES * SMAP_MAX_CLASSES);
     if (e == cudaSuccess) e = cudaMalloc(&h->total_dev, sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&h->frames_done, sizeof(unsigned int) * kMaxBatch);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         fail(e == cudaErrorMemoryAllocation ? SMAP_ERR_NOMEM : SMAP_ERR_CUDA, "smap_create: %s", cudaGetErrorString(e));
@@ -649,7 +737,13 @@ int smap_destroy(smap_handle* h) {
     if (h->own_map) cudaFree(h->map);
     cudaFree(h->mask); cudaFree(h->tags); cudaFree(h->boxes); cudaFree(h->touched); cudaFree(h->cm_dev); cudaFree(h->total_dev);
     cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
-    cudaFree(h->frames_done);
+    if (h->ev_fork) {
+        cudaEventDestroy(h->ev_fork);
+        for (int a = 0; a < smap_handle::kAux; ++a) {
+            cudaEventDestroy(h->ev_join[a]);
+            cudaStreamDestroy(h->aux[a]);
+        }
+    }
     for (int i = 0; i < smap_handle::kStages; ++i) {
         cudaFree(h->stage_pts[i]);
         cudaFree(h->stage_img[i]);

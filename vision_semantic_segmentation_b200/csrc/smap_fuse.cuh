@@ -62,24 +62,37 @@ struct Fast32 {
 
 constexpr float kMagic32 = 12582912.0f;   // 1.5 * 2^23: adding it rounds |t| < 2^22 to the nearest integer
 
-// One frame of a batched launch.
+// One frame of a batch.
 struct FuseFrame {
     FrameParams fp;        // float64 constants (deferred points only)
     Fast32 fk;
     const float4* pts;
     const uint8_t* image;
     uint32_t* mask;        // MODE 0: this frame's mask slot
-    uint32_t* tags;        // MODE 1: (cells, C + 1) uint32 tag plane of this frame (two planes alternate)
     int64_t n;
+    int32_t per_warp;      // points per warp: ceil(n / (gridDim.x * kWarps)), computed by the host
+    int32_t img64;         // label image readable with aligned 8-byte loads (base aligned, size a multiple of 8)
 };
 
-// Kernel parameter of k_fuse: up to kMaxBatch frames, frame = blockIdx.y.  One launch per batch: the blocks of
-// frame f + 1 start as the blocks of frame f retire, so the ramp-up and tail of consecutive frames overlap and
-// there is no launch gap between frames (a launch per frame on alternating streams left 4 us of each 20 us idle).
-// The per-frame constants are read from the constant bank with the (block-uniform) frame index.
-struct FuseBatch {
-    FuseFrame f[kMaxBatch];
+// Kernel parameter of k_fuse<MODE, NF>: the NF frames a launch walks.
+//   NF == 1          one launch per frame (on alternating internal streams, so that the ramp-up and tail of one
+//                    launch overlap the next one's body); every per-frame constant then sits at a fixed offset of the
+//                    constant bank.  This is what the library uses: 17.2 us / frame on the benchmark workload.
+//   NF == kMaxBatch  ONE persistent launch walks all the frames of a batch: frame f + 1's cloud is already in flight
+//                    while frame f's last survivors are decided, records and deferred points carry their frame
+//                    index, nothing is flushed between frames.  Kept as a measured alternative (SMAP_FUSE_PERSISTENT):
+//                    19.0 us / frame -- the run-time frame index turns every constant operand into an indexed LDC,
+//                    which costs more than the per-launch ramp it saves.  (A third variant, one launch per batch with
+//                    frame = blockIdx.y, measured 21.4 us / frame.)
+template <int NF>
+struct FuseBatchT {
+    FuseFrame f[NF];
+    uint32_t* tags;        // MODE 1: (cells * (C + 1), tag_planes) uint32; frame f of the launch uses plane f
+    int32_t n_frames;
+    int32_t tag_planes;    // plane stride (>= n_frames)
 };
+
+constexpr int kFidShift = 28;   // a record's pixel index carries the frame index above bit 28
 
 #ifndef SMAP_FUSE_ROUND
 #define SMAP_FUSE_ROUND 2
@@ -158,69 +171,85 @@ constexpr int kFStages = SMAP_FUSE_STAGES;
 constexpr int kFGather = SMAP_FUSE_GATHER;         // records per lane in one label-lookup + update pass
 constexpr int kFRecCap = 32 * kFGather + 64;       // record stack: < 32 * kFGather left over + 32 (float32) + 32 (float64)
 // dynamic shared memory of k_fuse, per warp: kFStages cloud stages, the survivor stack, the deferred stack, the
-// record stack, the stages' mbarriers; then the two colour tables of the block
-constexpr int kFWarpSmem = (kFStages * kFRoundPts + kFQueueCap + kFDeferCap) * 16 + kFRecCap * 8 + (kFStages * 8 + 15) / 16 * 16;
-constexpr int kFBlockSmem = kWarps * kFWarpSmem + 2 * 256 * 4;
+// record stack, the deferred points' frame indices, the stages' mbarriers; then the two colour tables of the block
+// (the deferred points' frame indices are only needed when a launch walks several frames.)  Keeping this small
+// matters beyond occupancy: the unified L1 / shared memory is carved in steps, and a block size that pushes the SM
+// from the 196 KB to the 228 KB carve-out (28 KB of L1 left) costs 20 % on the label gather.
+__host__ __device__ constexpr int fuse_warp_smem(int nf) {
+    return (kFStages * kFRoundPts + kFQueueCap + kFDeferCap) * 16 + kFRecCap * 8 + (nf > 1 ? kFDeferCap : 0) +
+           (kFStages * 8 + 15) / 16 * 16;
+}
+__host__ __device__ constexpr int fuse_block_smem(int nf) { return kWarps * fuse_warp_smem(nf) + 2 * 256 * 4; }
 
 // ------------------------------------------------------------------------------------------------
 // MODE 0: masks only (RED.OR into the frame's slot, bounding box) -- k_apply replays the frames in order.
-// MODE 1: count update (matrix == np.eye(C), grid of integer-valued counts): one uint32 tag per (cell, class)
-//         and one per (cell, boost); ATOM.MAX with the frame's tag returns an older tag exactly once per frame,
-//         and that lane adds 1.0 (boost: 2.0 on the lane class; src/mapping_replay.py:281,294) with a float64 RED.
-//         Sums of small integers are exact in any order.  Nothing to clear, no second kernel.
+// MODE 1: count update (matrix == np.eye(C), grid of integer-valued counts): one uint32 tag per (cell, class, frame
+//         of the batch) and one per (cell, boost, frame); ATOM.MAX with the frame's tag returns an older tag exactly
+//         once per frame, and that lane adds 1.0 (boost: 2.0 on the lane class; src/mapping_replay.py:281,294) with a
+//         float64 RED.  Sums of small integers are exact in any order.  Nothing to clear, no second kernel.  The
+//         frames of a batch use different tag planes (interleaved: the planes of one element share a sector), so
+//         warps may be at different frames without any synchronisation.
 //
-// Every warp is autonomous (no block barrier after the prologue) and owns a contiguous, equally sized slice of the
-// cloud, which it walks in rounds of kFRoundPts points:
+// Persistent grid, every warp autonomous (no block barrier after the prologue).  Per frame a warp owns a contiguous,
+// equally sized slice of the cloud, which it walks in rounds of kFRoundPts points:
 //   cloud     a private ring of kFStages shared-memory stages filled by TMA bulk copies (cp.async.bulk +
-//             mbarrier complete_tx): kFStages - 1 rounds are always in flight per warp, no registers and no
-//             scoreboards are tied up by the stream (the register-prefetched version stalled on exactly those);
+//             mbarrier complete_tx) that runs ahead across frame boundaries: no registers and no scoreboards are
+//             tied up by the stream (a register-prefetched version stalled on exactly those);
 //   cull      one LDS.128 per point, conservative float32 test (cull32), survivors (~36 %) pushed on the warp's
 //             stack (ballot + popc);
-//   drain     whenever >= 32 survivors are stacked, pop 32 -- one per lane, all lanes busy -- through a software
-//             pipeline of three batches, so that no lane waits for its own loads or atomics:
-//               stage A (batch k)    float32 decisions (deferred points: float64), label bytes requested
-//               stage B (batch k-1)  label bytes -> class bits (shared colour tables) -> ATOM.MAX / RED.OR issued
-//               stage C (batch k-2)  returned tags -> RED.ADD
+//   decide    whenever >= 32 survivors are stacked, pop 32 -- one per lane, all lanes busy: float32 decisions; the
+//             undecided points go to the deferred stack (decided in float64, 32 at a time), the accepted ones to
+//             the record stack as {pixel | frame, cell | intensity flag};
+//   gather    whenever >= 32 * kFGather records are stacked: label lookup + update in straight-line code, all the
+//             label bytes requested before the first is used, all the tag atomics issued before the first result
+//             is used -- the two memory round trips are paid once per 32 * kFGather records.  (A software pipeline
+//             that carried loads and atomics across loop iterations was tried first: ptxas puts every carried
+//             operation on one scoreboard and waits for it at the loop head, which serialised everything.)
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, int NF>
 __global__ void __launch_bounds__(kThreads, SMAP_FUSE_MINB)
-k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams gp, FrameBox* __restrict__ boxes,
-       double* __restrict__ map, unsigned int* __restrict__ frames_done) {
+k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridParams gp, FrameBox* __restrict__ boxes,
+       double* __restrict__ map) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    __shared__ int s_box[4];
+    __shared__ int s_box[NF][4];
 
-    const FuseFrame& F = B.f[blockIdx.y];
-    const Fast32& fk = F.fk;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    constexpr int kFWarpSmem = fuse_warp_smem(NF);
     unsigned char* const wbase = s_dyn + (size_t)warp * kFWarpSmem;
     float4* const stages = reinterpret_cast<float4*>(wbase);
     float4* const queue = stages + kFStages * kFRoundPts;
     float4* const defer = queue + kFQueueCap;
     uint2* const recs = reinterpret_cast<uint2*>(defer + kFDeferCap);
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(recs + kFRecCap);
+    uint8_t* const defer_f = reinterpret_cast<uint8_t*>(recs + kFRecCap);   // NF > 1 only
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(defer_f + (NF > 1 ? kFDeferCap : 0));
     uint32_t* const s_tab_r = reinterpret_cast<uint32_t*>(s_dyn + (size_t)kWarps * kFWarpSmem);
     uint32_t* const s_tab_g = s_tab_r + 256;
 
-    // this warp's slice of the cloud: [w_begin, w_end), the same size (+-1 round-up) for every warp of the frame
-    const int64_t f_n = F.n;
-    const int64_t n_warps = (int64_t)gridDim.x * kWarps;
-    const int64_t per = (f_n + n_warps - 1) / n_warps;
-    const int64_t w_begin = ((int64_t)blockIdx.x * kWarps + warp) * per;
-    const int64_t w_end = (w_begin + per < f_n) ? w_begin + per : f_n;
-    const int w_pts = (w_end > w_begin) ? (int)(w_end - w_begin) : 0;      // < 2^31: a frame has < 2^31 * n_warps points
-    const int n_rounds = (w_pts + kFRoundPts - 1) / kFRoundPts;
+    const int nf = (NF == 1) ? 1 : B.n_frames;   // NF == 1: every B.f[f] below is B.f[0], a fixed constant-bank offset
+    const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;   // this warp's index in the grid
+    // this warp's slice of frame f: [gw * per_warp, ...) clipped to the cloud
+    auto slice_pts = [&](int f) -> int {
+        const int64_t left = B.f[f].n - gw * B.f[f].per_warp;
+        return left <= 0 ? 0 : (left < B.f[f].per_warp ? (int)left : B.f[f].per_warp);
+    };
 
-    // TMA producer state (meaningful in lane 0): next round to issue, its source, the points left to issue
+    // ---- TMA producer state (meaningful in lane 0): frame, source and points left of the next round to issue
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     const uint32_t stg0 = smem_u32(stages), bar0 = smem_u32(bars);
-    const float4* i_src = F.pts + w_begin;
-    int i_left = w_pts;
+    int i_f = -1, i_left = 0;
+    const float4* i_src = nullptr;
     uint32_t i_st = 0;
-    auto issue_round = [&]() {   // one elected lane; no-op when the slice is exhausted
-        if (lane == 0 && i_left > 0) {
+    auto issue_round = [&]() {   // no-op once the batch is exhausted; issues exactly the rounds the consumer walks
+        while (i_left <= 0 && i_f + 1 < nf) {
+            ++i_f;
+            i_left = slice_pts(i_f);
+            i_src = B.f[i_f].pts + gw * B.f[i_f].per_warp;
+        }
+        if (i_left <= 0) return;
+        if (lane == 0) {
             const uint32_t bytes = (uint32_t)(i_left < kFRoundPts ? i_left : kFRoundPts) * 16u;
             const uint32_t bar = bar0 + i_st * 8u;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -239,43 +268,32 @@ k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams g
     }
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < kFStages - 1; ++r) issue_round();   // round kFStages - 1 is issued in the first loop turn
+    for (int r = 0; r < kFStages - 1; ++r) issue_round();   // one more is issued at the top of every round
     // the first rounds are on their way while the block builds its colour tables
     build_color_tables(gp, s_tab_r, s_tab_g);
-    if (threadIdx.x == 0) {
-        box_reset(s_box);
-        if (MODE == 1 && blockIdx.y >= 2) {
-            // the tag plane of this frame was last used by frame blockIdx.y - 2: all its blocks must have retired
-            // (they were dispatched before this one, so the wait cannot deadlock; normally it is already true)
-            const volatile unsigned int* d = frames_done + (blockIdx.y - 2);
-            while (*d < gridDim.x) {}
-            __threadfence();
-        }
-    }
+    if (threadIdx.x < NF) box_reset(s_box[threadIdx.x]);
     __syncthreads();
 
-    const uint8_t* const f_image = F.image;
     const uint32_t c1 = (uint32_t)gp.c + 1u;
     const uint32_t lane_bit = (gp.use_intensity && gp.lane >= 0) ? (1u << gp.lane) : 0u;
 
     uint32_t qn = 0, dn = 0, rn = 0;   // entries on the survivor / deferred / record stacks (warp-uniform)
-    // MODE 0 bounding box: magic-shifted floats on the float32 path (monotone in the cell coordinates), ints for
-    // the deferred points
+    // MODE 0 bounding box of the current frame: magic-shifted floats (monotone in the cell coordinates)
     float fbx0 = 3.0e38f, fbx1 = -3.0e38f, fby0 = 3.0e38f, fby1 = -3.0e38f;
-    int ibx0 = 0x7fffffff, ibx1 = -1, iby0 = 0x7fffffff, iby1 = -1;
 
-    // a decided point -> record stack: {pixel index, cell index | intensity flag << 31}
-    auto push_record = [&](bool have, uint32_t pix, uint32_t cell, float it) {
+    // a decided point -> record stack: {pixel index | frame << 28, cell index | intensity flag << 31}
+    auto push_record = [&](bool have, uint32_t pix_f, uint32_t cell, float it) {
         const unsigned ballot = __ballot_sync(0xffffffffu, have);
         if (have) {
             const uint32_t extreme = (it < 2.0f || it > 14.0f) ? 0x80000000u : 0u;   // src/mapping_replay.py:290
-            recs[rn + __popc(ballot & lt_mask)] = make_uint2(pix, cell | extreme);
+            recs[rn + __popc(ballot & lt_mask)] = make_uint2(pix_f, cell | extreme);
         }
         rn += __popc(ballot);
     };
 
-    // float32 decisions for up to 32 stacked survivors, one per lane
-    auto decide32 = [&](uint32_t count) {
+    // float32 decisions for up to 32 stacked survivors of frame f, one per lane
+    auto decide32 = [&](int f, uint32_t count) {
+        const Fast32& fk = B.f[f].fk;
         const uint32_t first = qn - count;
         qn = first;
         bool defer_me = false, have = false;
@@ -284,7 +302,7 @@ k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams g
 #ifdef SMAP_ABL_NO_DRAIN   // ablation builds (profiles/): streaming + cull + stack traffic alone
         if ((uint32_t)lane < count) {
             w = queue[first + lane];
-            if (w.x == 1234.5f) atomicOr(F.mask, (uint32_t)w.z);
+            if (w.x == 1234.5f) atomicOr(B.f[f].mask, (uint32_t)w.z);
         }
         count = 0;
 #endif
@@ -326,14 +344,14 @@ k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams g
             have = cert & inside;
             tp.x = fmaxf(tp.x, kMagic32); tp.y = fmaxf(tp.y, kMagic32);              // floor -1 -> pixel 0
             tc.x = fmaxf(tc.x, fk.clamp_c.x); tc.y = fmaxf(tc.y, fk.clamp_c.y);      // floor -1 -> cell 0
-            pix = __float_as_uint(tp.y) * (uint32_t)F.fp.img_w + __float_as_uint(tp.x) + fk.pix_k;
+            pix = __float_as_uint(tp.y) * (uint32_t)B.f[f].fp.img_w + __float_as_uint(tp.x) + fk.pix_k;
             cell = __float_as_uint(tc.x) * (uint32_t)gp.mw + __float_as_uint(tc.y) + fk.cell_k;
             if (MODE == 0 && have) {
                 fbx0 = fminf(fbx0, tc.x); fbx1 = fmaxf(fbx1, tc.x);
                 fby0 = fminf(fby0, tc.y); fby1 = fmaxf(fby1, tc.y);
             }
         }
-        push_record(have, pix, cell, w.w);
+        push_record(have, pix | ((uint32_t)f << kFidShift), cell, w.w);
         const unsigned dballot = __ballot_sync(0xffffffffu, defer_me);
 #ifdef SMAP_FUSE_STATS
         {
@@ -347,75 +365,99 @@ k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams g
 #endif
 #ifndef SMAP_ABL_NO_DEFER   // ablation builds: deferred points are dropped (wrong results, timing only)
         if (dballot) {
-            if (defer_me) defer[dn + __popc(dballot & lt_mask)] = w;
+            if (defer_me) {
+                const uint32_t slot = dn + __popc(dballot & lt_mask);
+                defer[slot] = w;
+                if (NF > 1) defer_f[slot] = (uint8_t)f;
+            }
             dn += __popc(dballot);
         }
 #endif
     };
 
-    // float64 decisions for up to 32 deferred points
+    // float64 decisions for up to 32 deferred points (possibly of different frames)
     auto decide64 = [&](uint32_t count) {
         const uint32_t first = dn - count;
         dn = first;
         bool have = false;
         uint2 pc = make_uint2(0u, kNone);
         float it = 0.f;
+        uint32_t fid = 0;
         if ((uint32_t)lane < count) {
             const float4 w = defer[first + lane];
+            fid = (NF == 1) ? 0u : defer_f[first + lane];
             it = w.w;
-            pc = fuse_decide64(&F.fp, &gp, w);
+            pc = fuse_decide64(&B.f[fid].fp, &gp, w);
             have = pc.y != kNone;
-            if (MODE == 0 && have) {
+            if (MODE == 0 && have) {   // rare: straight into the block's box of that frame
                 const int cx = (int)(pc.y / (uint32_t)gp.mw), cy = (int)(pc.y - (uint32_t)cx * (uint32_t)gp.mw);
-                ibx0 = min(ibx0, cx); ibx1 = max(ibx1, cx); iby0 = min(iby0, cy); iby1 = max(iby1, cy);
+                atomicMin(&s_box[fid][0], cx); atomicMax(&s_box[fid][1], cx);
+                atomicMin(&s_box[fid][2], cy); atomicMax(&s_box[fid][3], cy);
             }
         }
-        push_record(have, pc.x, pc.y, it);
+        push_record(have, pc.x | (fid << kFidShift), pc.y, it);
     };
 
-    // label lookup + update for up to 32 * kFGather records, kFGather per lane, in straight-line code: all the label
-    // bytes are requested before the first one is used, then all the tag atomics are issued before the first
-    // result is used -- the two memory round trips are paid once per 32 * kFGather records.  (A software pipeline that
-    // carried loads and atomics across loop iterations was tried first: ptxas puts every carried operation on one
-    // scoreboard and waits for it at the loop head, which serialised everything.)
+    // label lookup + update for up to 32 * kFGather records, kFGather per lane
     auto gather = [&](uint32_t count) {
         const uint32_t first = rn - count;
         rn = first;
-        uint32_t cellf[kFGather], lr[kFGather], lg[kFGather];
+        uint32_t cellf[kFGather], lr[kFGather], lg[kFGather], fid[kFGather];
 #pragma unroll
         for (int k = 0; k < kFGather; ++k) {
             const uint32_t i = (uint32_t)(k * 32 + lane);
             cellf[k] = kNone;
-            lr[k] = 0; lg[k] = 0;
+            lr[k] = 0; lg[k] = 0; fid[k] = 0;
             if (i < count) {
                 const uint2 rec = recs[first + i];
                 cellf[k] = rec.y;
+                fid[k] = (NF == 1) ? 0u : (rec.x >> kFidShift);
+                const uint32_t pix = rec.x & ((1u << kFidShift) - 1u);
 #ifdef SMAP_ABL_NO_GATHER
-                lr[k] = (rec.x & 1u) ? 128u : 255u; lg[k] = (rec.x & 1u) ? 64u : 255u;
+                lr[k] = (pix & 1u) ? 128u : 255u; lg[k] = (pix & 1u) ? 64u : 255u;
 #else
-                const uint8_t* px = f_image + (size_t)rec.x * 3u;
-                lr[k] = __ldg(px);
-                lg[k] = __ldg(px + 1);
+                const uint8_t* img = B.f[fid[k]].image;
+                const size_t a = (size_t)pix * 3u;
+#ifdef SMAP_FUSE_LABEL8
+                lr[k] = __ldg(img + a);
+                lg[k] = __ldg(img + a + 1);
+#else
+                if (B.f[fid[k]].img64) {
+                    // R and G from ONE aligned 8-byte load (a second one only when R is the last byte of its 8: one
+                    // pixel in eight): the L1 sees one sector request per point instead of two
+                    const uint2 wv = __ldg(reinterpret_cast<const uint2*>(img + (a & ~(size_t)7)));
+                    const uint32_t sh = ((uint32_t)a & 7u) * 8u;
+                    const uint64_t v = (((uint64_t)wv.y << 32) | wv.x) >> sh;
+                    lr[k] = (uint32_t)v & 0xffu;
+                    lg[k] = (sh == 56u) ? __ldg(img + a + 1) : (((uint32_t)v >> 8) & 0xffu);
+                } else {
+                    lr[k] = __ldg(img + a);
+                    lg[k] = __ldg(img + a + 1);
+                }
+#endif
 #endif
             }
         }
-        uint32_t bits[kFGather], old0[kFGather], old1[kFGather];
+        uint32_t bits[kFGather], old0[kFGather], old1[kFGather], tag[kFGather];
 #pragma unroll
         for (int k = 0; k < kFGather; ++k) {
             bits[k] = (cellf[k] != kNone) ? (s_tab_r[lr[k]] & s_tab_g[lg[k]]) : 0u;
-            old0[k] = fk.tag; old1[k] = fk.tag;
+            tag[k] = 0u; old0[k] = 0u; old1[k] = 0u;
 #ifdef SMAP_ABL_NO_SCATTER
-            if (bits[k] && cellf[k] == 0x7ffffff0u) atomicOr(F.mask, bits[k]);
+            if (bits[k] && cellf[k] == 0x7ffffff0u) atomicOr(B.f[0].mask, bits[k]);
             bits[k] = 0;
 #endif
             if (!bits[k]) continue;
             const uint32_t cell = cellf[k] & 0x7fffffffu;
             const bool boost = (bits[k] & lane_bit) && (cellf[k] >> 31);
             if (MODE == 0) {
-                atomicOr(F.mask + cell, boost ? (bits[k] | (1u << gp.c)) : bits[k]);   // result unused: RED.OR
+                atomicOr(B.f[fid[k]].mask + cell, boost ? (bits[k] | (1u << gp.c)) : bits[k]);   // result unused: RED.OR
                 bits[k] = 0;
             } else {
-                uint32_t* trow = F.tags + cell * c1;   // element indices fit 32 bits (checked by the host)
+                const uint32_t t = B.f[fid[k]].fk.tag;
+                // element indices fit 32 bits (checked by the host); the planes of one element are adjacent
+                uint32_t* trow = B.tags + ((size_t)(cell * c1) * (uint32_t)B.tag_planes + fid[k]);
+                const size_t tstride = (size_t)(uint32_t)B.tag_planes;
                 if (bits[k] & (bits[k] - 1u)) {
                     // several classes share this pixel's (R, G): rare, done in place
                     double* row = map + cell * (uint32_t)gp.c;
@@ -423,14 +465,15 @@ k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams g
                     while (b) {
                         const int i = __ffs(b) - 1;
                         b &= b - 1u;
-                        if (atomicMax(trow + i, fk.tag) != fk.tag) atomicAdd(row + i, 1.0);
+                        if (atomicMax(trow + i * tstride, t) != t) atomicAdd(row + i, 1.0);
                     }
-                    if (boost && atomicMax(trow + gp.c, fk.tag) != fk.tag) atomicAdd(row + gp.lane, 2.0);
+                    if (boost && atomicMax(trow + gp.c * tstride, t) != t) atomicAdd(row + gp.lane, 2.0);
                     bits[k] = 0;
                 } else {
                     const uint32_t cls = (uint32_t)__ffs(bits[k]) - 1u;
-                    old0[k] = atomicMax(trow + cls, fk.tag);
-                    if (boost) old1[k] = atomicMax(trow + gp.c, fk.tag);
+                    tag[k] = t; old0[k] = t; old1[k] = t;
+                    old0[k] = atomicMax(trow + cls * tstride, t);
+                    if (boost) old1[k] = atomicMax(trow + gp.c * tstride, t);
                     bits[k] = cell * (uint32_t)gp.c + cls;   // from here on: the grid element
                 }
             }
@@ -438,14 +481,14 @@ k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams g
         if (MODE == 1) {
 #pragma unroll
             for (int k = 0; k < kFGather; ++k) {
-                if (old0[k] != fk.tag) atomicAdd(map + bits[k], 1.0);
-                if (old1[k] != fk.tag) atomicAdd(map + bits[k], 2.0);
+                if (old0[k] != tag[k]) atomicAdd(map + bits[k], 1.0);
+                if (old1[k] != tag[k]) atomicAdd(map + bits[k], 2.0);
             }
         }
     };
 
-    auto drain = [&](uint32_t count) {
-        decide32(count);
+    auto drain = [&](int f, uint32_t count) {
+        decide32(f, count);
         __syncwarp();
         if (dn >= 32u) {
             decide64(32u);
@@ -457,29 +500,54 @@ k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams g
         }
     };
 
-    for (int r = 0; r < n_rounds; ++r) {
-        // keep kFStages - 1 rounds in flight: the next one goes into the stage that round r - 1 used (every lane
-        // has consumed its reads of that stage, and the warp has re-converged since)
-        issue_round();
-        const int st = r % kFStages;
-        const uint32_t parity = (uint32_t)(r / kFStages) & 1u;
-        while (!mbar_try_wait(bars + st, parity)) {}
-        const int left = w_pts - r * kFRoundPts;
-        const int pts = left < kFRoundPts ? left : kFRoundPts;
-        const float4* sp = stages + st * kFRoundPts + lane;
+    uint32_t rr = 0;   // rounds consumed so far (all frames): stage = rr % kFStages, parity from rr / kFStages
+    for (int f = 0; f < nf; ++f) {
+        const Fast32& fk = B.f[f].fk;
+        const int w_pts = slice_pts(f);
+        const int n_rounds = (w_pts + kFRoundPts - 1) / kFRoundPts;
+        for (int r = 0; r < n_rounds; ++r, ++rr) {
+            // keep kFStages - 1 rounds in flight: the next one goes into the stage that the previous round used
+            // (every lane has consumed its reads of that stage, and the warp has re-converged since)
+            issue_round();
+            const uint32_t st = rr % (uint32_t)kFStages;
+            const uint32_t parity = (rr / (uint32_t)kFStages) & 1u;
+            while (!mbar_try_wait(bars + st, parity)) {}
+            const int left = w_pts - r * kFRoundPts;
+            const int pts = left < kFRoundPts ? left : kFRoundPts;
+            const float4* sp = stages + st * kFRoundPts + lane;
 #pragma unroll
-        for (int j = 0; j < kFRound; ++j) {
-            const float4 w = sp[j * 32];
-            const bool pass = cull32(fk, w.x, w.y, w.z) & (j * 32 + lane < pts);
-            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-            if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
-            qn += __popc(ballot);
+            for (int j = 0; j < kFRound; ++j) {
+                const float4 w = sp[j * 32];
+                const bool pass = cull32(fk, w.x, w.y, w.z) & (j * 32 + lane < pts);
+                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
+                qn += __popc(ballot);
+            }
+            __syncwarp();
+            while (qn >= 32u) drain(f, 32u);
         }
-        __syncwarp();
-        while (qn >= 32u) drain(32u);
+        // end of the frame for this warp: the survivors left over are decided with this frame's constants (records
+        // and deferred points carry their frame and stay stacked)
+        if (qn) drain(f, qn);
+        if (MODE == 0) {
+            // fold this frame's bounding box: lane -> warp -> block (shared atomics); flushed to the frame's box at the end
+            if (__any_sync(0xffffffffu, fbx1 >= fbx0)) {
+                // magic-shifted float -> cell coordinate: bits - (bits(magic) - I0); clamp_c = magic - I0
+                const int ox = (int)__float_as_uint(fk.clamp_c.x), oy = (int)__float_as_uint(fk.clamp_c.y);
+                const bool any = fbx1 >= fbx0;
+                const int a = __reduce_min_sync(0xffffffffu, any ? (int)__float_as_uint(fbx0) - ox : 0x7fffffff);
+                const int b = __reduce_max_sync(0xffffffffu, any ? (int)__float_as_uint(fbx1) - ox : -1);
+                const int c = __reduce_min_sync(0xffffffffu, any ? (int)__float_as_uint(fby0) - oy : 0x7fffffff);
+                const int d = __reduce_max_sync(0xffffffffu, any ? (int)__float_as_uint(fby1) - oy : -1);
+                if (lane == 0) {
+                    atomicMin(&s_box[f][0], a); atomicMax(&s_box[f][1], b);
+                    atomicMin(&s_box[f][2], c); atomicMax(&s_box[f][3], d);
+                }
+                fbx0 = 3.0e38f; fbx1 = -3.0e38f; fby0 = 3.0e38f; fby1 = -3.0e38f;
+            }
+        }
     }
-    // flush: the partial batch of survivors, the deferred points, the records
-    if (qn) drain(qn);
+    // flush: the deferred points, then the records
     if (dn) {
         decide64(dn);
         __syncwarp();
@@ -489,34 +557,12 @@ k_fuse(const __grid_constant__ FuseBatch B, const __grid_constant__ GridParams g
         __syncwarp();
     }
 
-    if (MODE == 1) {
-        // frame blockIdx.y + 2 reuses this frame's tag plane: publish "this block's atomics are performed"
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) atomicAdd(frames_done + blockIdx.y, 1u);
-    }
     if (MODE == 0) {
-        FrameBox* box = boxes + blockIdx.y;
-        // fold the bounding boxes: lane -> warp -> block (shared atomics) -> frame (4 global atomics per block)
-        int bx0 = ibx0, bx1 = ibx1, by0 = iby0, by1 = iby1;
-        if (fbx1 >= fbx0) {
-            // magic-shifted float -> cell coordinate: bits - (bits(magic) - I0); clamp_c = magic - I0
-            const int ox = (int)__float_as_uint(fk.clamp_c.x), oy = (int)__float_as_uint(fk.clamp_c.y);
-            bx0 = min(bx0, (int)__float_as_uint(fbx0) - ox); bx1 = max(bx1, (int)__float_as_uint(fbx1) - ox);
-            by0 = min(by0, (int)__float_as_uint(fby0) - oy); by1 = max(by1, (int)__float_as_uint(fby1) - oy);
-        }
-        if (__any_sync(0xffffffffu, bx1 >= bx0)) {
-            const int a = __reduce_min_sync(0xffffffffu, bx0), b = __reduce_max_sync(0xffffffffu, bx1);
-            const int c = __reduce_min_sync(0xffffffffu, by0), d = __reduce_max_sync(0xffffffffu, by1);
-            if (lane == 0) {
-                atomicMin(&s_box[0], a); atomicMax(&s_box[1], b);
-                atomicMin(&s_box[2], c); atomicMax(&s_box[3], d);
-            }
-        }
         __syncthreads();
-        if (threadIdx.x == 0 && s_box[1] >= s_box[0]) {
-            atomicMin(&box->x0, s_box[0]); atomicMax(&box->x1, s_box[1]);
-            atomicMin(&box->y0, s_box[2]); atomicMax(&box->y1, s_box[3]);
+        if ((int)threadIdx.x < nf && s_box[threadIdx.x][1] >= s_box[threadIdx.x][0]) {
+            FrameBox* box = boxes + threadIdx.x;
+            atomicMin(&box->x0, s_box[threadIdx.x][0]); atomicMax(&box->x1, s_box[threadIdx.x][1]);
+            atomicMin(&box->y0, s_box[threadIdx.x][2]); atomicMax(&box->y1, s_box[threadIdx.x][3]);
         }
     }
 }
