@@ -8,8 +8,8 @@ fraction of the HBM roofline, next to the CPU path timed on the same box).
 A "step" is one frame of BASELINE.json configs[1]: a 2M-point local cloud + one 1920x1440
 19-class label image, count-based update into the default 2000x2000 BEV grid.  Inputs are a ring of
 distinct frames resident in HBM (ring >> L2), so every step streams its cloud and image from DRAM.
-Frames are handed to the C ABI 16 at a time (smap_integrate_batch: one streaming kernel per frame, one
-apply/clear kernel per batch).
+Frames are handed to the C ABI 16 at a time (smap_integrate_batch: one fused kernel per frame, launched on two
+alternating internal streams; the count update needs no second kernel).
 N > 1: one process per GPU (torchrun), frames sharded by rank (weak scaling: every rank integrates K
 frames), one NCCL all-reduce of the grids at the end of the timed region.
 """
@@ -279,7 +279,7 @@ def run_b200(args):
     ms = float(t.item())
     value = world * args.steps * n_pts / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_stream: project + cull + lookup + update of one frame).
+    # ---- roofline of the dominant kernel (k_fuse: project + cull + lookup + update of one frame).
     # Its launch duration is measured live with CUDA events recorded by the library on the launching stream
     # (smap_set_profiling: the per-frame launches are then serialised on that stream); the algorithmic bytes are
     # SURVEY.md 8d's  16 N + 3 M + 2*8 U  per frame with N, M, U measured above on the device path.
@@ -298,7 +298,7 @@ def run_b200(args):
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")   # from the committed ncu --set full capture
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("k_stream_c%d" % args.classes)
+            traffic = json.load(f).get("k_fuse_c%d" % args.classes)
 
     # ---- end to end through the host-buffer entry point: H2D of cloud + image and a D2H read every step
     e2e = None
@@ -353,7 +353,7 @@ def run_b200(args):
             "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_stream<float4, count> (project+cull+lookup+update, one frame per launch)",
+                         "kernel": "k_fuse<count> (TMA-staged cloud, float32 certified project+cull+lookup+update, one frame per launch)",
                          "kernel_ms": kernel_ms, "apply_kernel_ms_per_frame": apply_ms,
                          "step_frac": bytes_per_frame / (ms / args.steps * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_frame": bytes_per_frame,

@@ -515,7 +515,6 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         CK(cudaFuncSetAttribute(k_fuse<1, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
         h->fuse_attr_set = true;
     }
-    const size_t plane_words = (size_t)h->cells * (size_t)(h->cfg.num_classes + 1);
 #if SMAP_FUSE_PERSISTENT
     const int per_launch = count_atomics ? h->n_tag_planes : kMaxBatch;
     FuseBatchT<kMaxBatch>* fb = &h->fuse_batch;
@@ -559,6 +558,7 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         CK(cudaEventRecord(h->ev_fork, st));
         for (int a = 0; a < smap_handle::kAux; ++a) CK(cudaStreamWaitEvent(h->aux[a], h->ev_fork, 0));
     }
+    const size_t plane_words = (size_t)h->cells * (size_t)(h->cfg.num_classes + 1);
     FuseBatchT<1>* fb = &h->fuse_one;
     for (int i = 0; i < n_frames; ++i) {
         if (frames[i].n_points == 0) continue;
