@@ -14,6 +14,9 @@
 #ifndef SMAP_AUX_STREAMS
 #define SMAP_AUX_STREAMS 2      // internal streams the per-frame k_fuse launches of a batch alternate over
 #endif
+#ifndef SMAP_TAG_MAX_PLANES
+#define SMAP_TAG_MAX_PLANES 8   // count update: per-(cell, class) tags up to this many tags per cell (C + 1), masks beyond
+#endif
 #ifndef SMAP_FUSE_GRID_DIV
 #define SMAP_FUSE_GRID_DIV 1    // > 1: a frame's launch fills only 1/DIV of the resident block slots, so that the
 #endif                          // launches of DIV frames (on different internal streams) run side by side
@@ -416,6 +419,22 @@ int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st)
     return SMAP_OK;
 }
 
+// After a count update through the masks (k_fuse MODE 2): zero the slots inside the frames' boxes; flips parity.
+int launch_clear(smap_handle* h, int n_slots_used, cudaStream_t st) {
+    ApplyParams ap;
+    memset(&ap, 0, sizeof ap);
+    ap.n_frames = n_slots_used;
+    for (int i = 0; i < n_slots_used; ++i) ap.mask[i] = h->mask + (size_t)i * h->slot_words;
+    const dim3 grid((unsigned)h->sm_count, kMaxBatch);
+    k_clear_masks<<<grid, kThreads, 0, st>>>(ap, h->boxes + (size_t)h->parity * kMaxBatch,
+                                             h->boxes + (size_t)(h->parity ^ 1) * kMaxBatch, h->touched + (h->parity ^ 1),
+                                             h->cfg.map_width);
+    CK(cudaGetLastError());
+    h->parity ^= 1;
+    h->stats.kernel_launches += 1;
+    return SMAP_OK;
+}
+
 // Queue one k_stream_soa launch per non-empty (4, N) float64 frame; frame i of the non-empty ones scatters into
 // mask slot i.  Returns the number of slots used in *slots_used.
 int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, cudaStream_t st,
@@ -462,7 +481,7 @@ int ensure_tags(smap_handle* h, int want) {
     return SMAP_OK;
 }
 
-int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp, bool count_atomics, int slot, FuseFrame& f) {
+int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp, int mode, int slot, FuseFrame& f) {
     if (fr->layout != SMAP_PTS_F32X4) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
     if ((int64_t)fr->image_width * fr->image_height >= ((int64_t)1 << kFidShift))
         return fail(SMAP_ERR_INVALID, "label image has 2^28 pixels or more");
@@ -470,7 +489,7 @@ int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp,
     fill_fast32(h, fr, fp, f.fk);
     f.pts = static_cast<const float4*>(fr->points_dev);
     f.image = fr->image_dev;
-    f.mask = count_atomics ? nullptr : h->mask + (size_t)slot * h->slot_words;
+    f.mask = mode == 1 ? nullptr : h->mask + (size_t)slot * h->slot_words;
     f.fk.tag = ++h->frame_tag;   // larger than every tag written to this frame's plane before
     f.n = fr->n_points;
     f.img64 = ((reinterpret_cast<uintptr_t>(fr->image_dev) & 7u) == 0u &&
@@ -496,9 +515,12 @@ int fuse_grid(const smap_handle* h, FuseFrame* f, int n, int64_t* gx_out) {
 
 // Queue the float4 frames of a batch.  Count update: nothing else to do afterwards; otherwise frame i of the
 // non-empty ones scatters into mask slot i and *slots_used tells k_apply how many there are.
-int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, bool count_atomics,
+// mode: 0 ordered update (masks, k_apply afterwards), 1 count update with tags, 2 count update through the masks
+// (k_clear_masks afterwards)
+int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, int mode,
                 cudaStream_t st, int* slots_used) {
     int used = 0;
+    const bool count_atomics = mode == 1;
     if (count_atomics) {
         int rc = ensure_tags(h, SMAP_FUSE_PERSISTENT ? kMaxBatch : (smap_handle::kAux > 0 ? smap_handle::kAux : 1));
         if (rc) return rc;
@@ -511,12 +533,14 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
     if (!h->fuse_attr_set) {   // the per-warp TMA stages + stacks need more than the default 48 KB
         CK(cudaFuncSetAttribute(k_fuse<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
         CK(cudaFuncSetAttribute(k_fuse<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
+        CK(cudaFuncSetAttribute(k_fuse<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
+        CK(cudaFuncSetAttribute(k_fuse<2, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
         CK(cudaFuncSetAttribute(k_fuse<0, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
         CK(cudaFuncSetAttribute(k_fuse<1, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
         h->fuse_attr_set = true;
     }
 #if SMAP_FUSE_PERSISTENT
-    const int per_launch = count_atomics ? h->n_tag_planes : kMaxBatch;
+    const int per_launch = mode == 1 ? h->n_tag_planes : kMaxBatch;
     FuseBatchT<kMaxBatch>* fb = &h->fuse_batch;
     int i = 0;
     while (i < n_frames) {
@@ -524,7 +548,7 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         const int first_slot = used;
         for (; i < n_frames && in_launch < per_launch; ++i) {
             if (frames[i].n_points == 0) continue;
-            int rc = fill_fuse_frame(h, frames + i, fps[i], count_atomics, used, fb->f[in_launch]);
+            int rc = fill_fuse_frame(h, frames + i, fps[i], mode, used, fb->f[in_launch]);
             if (rc) return rc;
             ++in_launch;
             ++used;
@@ -537,7 +561,8 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         fb->n_frames = in_launch;
         fb->tag_planes = h->n_tag_planes > 0 ? h->n_tag_planes : 1;
         FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + first_slot;
-        if (count_atomics) k_fuse<1, kMaxBatch><<<(unsigned)gx, kThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
+        if (mode == 1) k_fuse<1, kMaxBatch><<<(unsigned)gx, kThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
+        else if (mode == 2) k_fuse<2, kMaxBatch><<<(unsigned)gx, kThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
         else k_fuse<0, kMaxBatch><<<(unsigned)gx, kThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
         CK(cudaGetLastError());
         h->stats.kernel_launches += 1;
@@ -564,7 +589,7 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         if (frames[i].n_points == 0) continue;
         const int lane_stream = fork ? used % smap_handle::kAux : 0;
         cudaStream_t ls = fork ? h->aux[lane_stream] : st;
-        int rc = fill_fuse_frame(h, frames + i, fps[i], count_atomics, used, fb->f[0]);
+        int rc = fill_fuse_frame(h, frames + i, fps[i], mode, used, fb->f[0]);
         if (rc) return rc;
         int64_t gx = 0;
         rc = fuse_grid(h, fb->f, 1, &gx);
@@ -574,7 +599,8 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         fb->n_frames = 1;
         fb->tag_planes = 1;
         FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + used;
-        if (count_atomics) k_fuse<1, 1><<<(unsigned)gx, kThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+        if (mode == 1) k_fuse<1, 1><<<(unsigned)gx, kThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+        else if (mode == 2) k_fuse<2, 1><<<(unsigned)gx, kThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
         else k_fuse<0, 1><<<(unsigned)gx, kThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
         CK(cudaGetLastError());
         h->stats.kernel_launches += 1;
@@ -854,14 +880,15 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
             h->stats.frames += 1;
             h->stats.points += frames[begin + i].n_points;
         }
-        // the count update on a grid of integer-valued counts may add its increments with float64 atomics (exact
-        // in any order); everything else goes through the ordered apply
         const bool f4 = frames[begin].layout == SMAP_PTS_F32X4;
-        // (the tag planes index (cell, class) elements with 32 bits)
+        // the count update on a grid of integer-valued counts may add its increments with float64 atomics (exact
+        // in any order): de-duplicated with per-(cell, class) frame tags when there are few classes, through the
+        // per-frame cell masks otherwise; everything else goes through the ordered apply
         const bool count_atomics = f4 && h->identity_cm && h->integer_grid &&
                                    h->cells * (int64_t)(h->cfg.num_classes + 1) < ((int64_t)1 << 32);
+        const int mode = !count_atomics ? 0 : (h->cfg.num_classes + 1 <= SMAP_TAG_MAX_PLANES ? 1 : 2);
         if (!h->identity_cm) h->integer_grid = false;
-        int rc = count_atomics ? SMAP_OK : ensure_slots(h, chunk);
+        int rc = mode == 1 ? SMAP_OK : ensure_slots(h, chunk);
         int used = 0;
         smap_handle::ProfRec* pr = nullptr;
         if (!rc && h->profiling) {
@@ -873,11 +900,12 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
                 CK(cudaEventRecord(pr->e[0], st));
             }
         }
-        if (!rc) rc = f4 ? launch_fuse(h, frames + begin, fps, chunk, count_atomics, st, &used)
+        if (!rc) rc = f4 ? launch_fuse(h, frames + begin, fps, chunk, mode, st, &used)
                          : launch_stream(h, frames + begin, fps, chunk, st, &used);
         if (pr) { pr->frames = used; CK(cudaEventRecord(pr->e[1], st)); }
-        if (!rc && used > 0 && !count_atomics) rc = launch_apply(h, h->map, used, st);
-        h->last_update_counted = !count_atomics;
+        if (!rc && used > 0 && mode == 0) rc = launch_apply(h, h->map, used, st);
+        if (!rc && used > 0 && mode == 2) rc = launch_clear(h, used, st);
+        h->last_update_counted = mode == 0;
         if (pr) CK(cudaEventRecord(pr->e[2], st));
         if (rc) return rc;
         begin += chunk;

@@ -183,6 +183,11 @@ __host__ __device__ constexpr int fuse_block_smem(int nf) { return kWarps * fuse
 
 // ------------------------------------------------------------------------------------------------
 // MODE 0: masks only (RED.OR into the frame's slot, bounding box) -- k_apply replays the frames in order.
+// MODE 2: count update through the masks (matrix == np.eye(C), grid of integer-valued counts): ATOM.OR returns what the
+//         frame had already put in the cell, every NEWLY set class bit adds 1.0 to map[cell, class] (a newly set boost
+//         bit 2.0 to map[cell, lane]) with a float64 RED; k_clear_masks zeroes the touched windows afterwards.  One
+//         word per cell whatever the number of classes: used when C + 1 > 8, where MODE 1's per-class tags would
+//         double the scattered traffic (C = 19: 45 us -> see DESIGN.md).
 // MODE 1: count update (matrix == np.eye(C), grid of integer-valued counts): one uint32 tag per (cell, class, frame
 //         of the batch) and one per (cell, boost, frame); ATOM.MAX with the frame's tag returns an older tag exactly
 //         once per frame, and that lane adds 1.0 (boost: 2.0 on the lane class; src/mapping_replay.py:281,294) with a
@@ -278,7 +283,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
     const uint32_t lane_bit = (gp.use_intensity && gp.lane >= 0) ? (1u << gp.lane) : 0u;
 
     uint32_t qn = 0, dn = 0, rn = 0;   // entries on the survivor / deferred / record stacks (warp-uniform)
-    // MODE 0 bounding box of the current frame: magic-shifted floats (monotone in the cell coordinates)
+    // MODE 0 / 2 bounding box of the current frame: magic-shifted floats (monotone in the cell coordinates)
     float fbx0 = 3.0e38f, fbx1 = -3.0e38f, fby0 = 3.0e38f, fby1 = -3.0e38f;
 
     // a decided point -> record stack: {pixel index | frame << 28, cell index | intensity flag << 31}
@@ -346,7 +351,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             tc.x = fmaxf(tc.x, fk.clamp_c.x); tc.y = fmaxf(tc.y, fk.clamp_c.y);      // floor -1 -> cell 0
             pix = __float_as_uint(tp.y) * (uint32_t)B.f[f].fp.img_w + __float_as_uint(tp.x) + fk.pix_k;
             cell = __float_as_uint(tc.x) * (uint32_t)gp.mw + __float_as_uint(tc.y) + fk.cell_k;
-            if (MODE == 0 && have) {
+            if (MODE != 1 && have) {
                 fbx0 = fminf(fbx0, tc.x); fbx1 = fmaxf(fbx1, tc.x);
                 fby0 = fminf(fby0, tc.y); fby1 = fmaxf(fby1, tc.y);
             }
@@ -389,7 +394,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             it = w.w;
             pc = fuse_decide64(&B.f[fid].fp, &gp, w);
             have = pc.y != kNone;
-            if (MODE == 0 && have) {   // rare: straight into the block's box of that frame
+            if (MODE != 1 && have) {   // rare: straight into the block's box of that frame
                 const int cx = (int)(pc.y / (uint32_t)gp.mw), cy = (int)(pc.y - (uint32_t)cx * (uint32_t)gp.mw);
                 atomicMin(&s_box[fid][0], cx); atomicMax(&s_box[fid][1], cx);
                 atomicMin(&s_box[fid][2], cy); atomicMax(&s_box[fid][3], cy);
@@ -453,6 +458,10 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             if (MODE == 0) {
                 atomicOr(B.f[fid[k]].mask + cell, boost ? (bits[k] | (1u << gp.c)) : bits[k]);   // result unused: RED.OR
                 bits[k] = 0;
+            } else if (MODE == 2) {
+                tag[k] = boost ? (bits[k] | (1u << gp.c)) : bits[k];          // the bits this point wants set
+                old0[k] = atomicOr(B.f[fid[k]].mask + cell, tag[k]);          // what the frame had set before
+                bits[k] = cell;                                               // from here on: the cell
             } else {
                 const uint32_t t = B.f[fid[k]].fk.tag;
                 // element indices fit 32 bits (checked by the host); the planes of one element are adjacent
@@ -483,6 +492,23 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             for (int k = 0; k < kFGather; ++k) {
                 if (old0[k] != tag[k]) atomicAdd(map + bits[k], 1.0);
                 if (old1[k] != tag[k]) atomicAdd(map + bits[k], 2.0);
+            }
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int k = 0; k < kFGather; ++k) {
+                uint32_t fresh = tag[k] & ~old0[k];   // inactive slots: tag == 0
+                if (!fresh) continue;
+                double* row = map + bits[k] * (uint32_t)gp.c;   // element indices fit 32 bits (checked by the host)
+                if (fresh >> gp.c) {   // boost bit newly set: +2 on the lane class (src/mapping_replay.py:294)
+                    atomicAdd(row + gp.lane, 2.0);
+                    fresh &= (1u << gp.c) - 1u;
+                }
+                while (fresh) {
+                    const int i = __ffs(fresh) - 1;
+                    fresh &= fresh - 1u;
+                    atomicAdd(row + i, 1.0);
+                }
             }
         }
     };
@@ -529,7 +555,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
         // end of the frame for this warp: the survivors left over are decided with this frame's constants (records
         // and deferred points carry their frame and stay stacked)
         if (qn) drain(f, qn);
-        if (MODE == 0) {
+        if (MODE != 1) {
             // fold this frame's bounding box: lane -> warp -> block (shared atomics); flushed to the frame's box at the end
             if (__any_sync(0xffffffffu, fbx1 >= fbx0)) {
                 // magic-shifted float -> cell coordinate: bits - (bits(magic) - I0); clamp_c = magic - I0
@@ -557,13 +583,33 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
         __syncwarp();
     }
 
-    if (MODE == 0) {
+    if (MODE != 1) {
         __syncthreads();
         if ((int)threadIdx.x < nf && s_box[threadIdx.x][1] >= s_box[threadIdx.x][0]) {
             FrameBox* box = boxes + threadIdx.x;
             atomicMin(&box->x0, s_box[threadIdx.x][0]); atomicMax(&box->x1, s_box[threadIdx.x][1]);
             atomicMin(&box->y0, s_box[threadIdx.x][2]); atomicMax(&box->y1, s_box[threadIdx.x][3]);
         }
+    }
+}
+
+// After a MODE 2 batch: zero every frame slot inside its frame's bounding box, reset the boxes of the next batch.
+// blockIdx.y = slot; the blocks of a slot stride over the rows of its box.
+__global__ void __launch_bounds__(kThreads)
+k_clear_masks(const __grid_constant__ ApplyParams ap, const FrameBox* __restrict__ boxes, FrameBox* __restrict__ next_boxes,
+              unsigned long long* __restrict__ next_touched_total, int mw) {
+    const int f = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        box_reset(&next_boxes[f].x0);
+        if (f == 0) *next_touched_total = 0ull;
+    }
+    if (f >= ap.n_frames) return;
+    const FrameBox b = boxes[f];
+    if (b.x1 < b.x0) return;
+    uint32_t* const m = ap.mask[f];
+    for (int x = b.x0 + (int)blockIdx.x; x <= b.x1; x += (int)gridDim.x) {
+        uint32_t* row = m + (size_t)x * mw;
+        for (int y = b.y0 + (int)threadIdx.x; y <= b.y1; y += kThreads) row[y] = 0u;
     }
 }
 
