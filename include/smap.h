@@ -139,19 +139,24 @@ SMAP_API int smap_update(smap_handle *h, double *map_dev, const double *pcd_dev,
 
 /* ---- fused path: project_pcd + update_map of ONE frame, nothing materialised -------------------
  * (src/mapping_replay.py:184-192 loop body).  Bit-exact with the reference for any update matrix (count or
- * log-likelihood): a streaming kernel ORs the frame's class bits into a per-frame cell mask (the per-frame
+ * log-likelihood): a fused kernel ORs the frame's class bits into a per-frame cell mask (the per-frame
  * (cell, class) de-duplication), a second kernel adds the matrix columns to the touched cells in ascending
  * class order and clears the mask.
  * Count update shortcut: when the matrix is exactly np.eye(C) AND the grid is known to hold integer-valued
  * counts (zero-initialised -- by the handle, by smap_clear, or declared with cfg.map_is_zero -- and since then
- * only updated by count updates of this handle), the streaming kernel adds 1.0 per newly observed (cell, class)
- * and 2.0 per lane boost with float64 atomics: sums of small integers, exact in any order, so the result is
- * the same bits.  smap_upload / smap_notify_map_modified switch back to the ordered update. */
+ * only updated by count updates of this handle), the fused kernel itself adds 1.0 per newly observed
+ * (cell, class) and 2.0 per lane boost with float64 atomics: sums of small integers, exact in any order, so the
+ * result is the same bits.  "Newly observed" is decided with per-(cell, class) frame tags (up to 7 classes; the
+ * handle then allocates 2 x cells x (C + 1) uint32 on first use) or with the per-frame cell masks (more classes).
+ * smap_upload / smap_notify_map_modified switch back to the ordered update.
+ * float4 clouds take the fast kernel (float32 decisions with rigorous error bounds, float64 only for the few
+ * points they cannot decide); label images of 2^28 pixels or more are rejected there. */
 SMAP_API int smap_integrate(smap_handle *h, const smap_frame *frame, void *stream);
 
-/* Same rule for n_frames frames IN ORDER.  Up to 16 frames share one pair of launches: each frame scatters
- * into its own mask slot and the apply kernel replays the slots in frame order per cell, so the result is
- * bit-identical to n_frames calls of smap_integrate.  Frames of one call must share a point layout. */
+/* Same rule for n_frames frames IN ORDER.  Up to 16 frames are queued together (one fused launch per frame on
+ * alternating internal streams, joined back into `stream`): each frame scatters into its own mask slot and the
+ * apply kernel replays the slots in frame order per cell, so the result is bit-identical to n_frames calls of
+ * smap_integrate.  Frames of one call must share a point layout. */
 SMAP_API int smap_integrate_batch(smap_handle *h, const smap_frame *frames_host, int n_frames, void *stream);
 
 /* Same as smap_integrate with HOST buffers: points (layout as in frame) and image are copied to the

@@ -287,3 +287,75 @@ def test_precull_is_conservative_near_the_frustum_and_range_borders():
         dm.integrate(dm.make_frame(cloud, dev(image), T, 0))
         assert np.array_equal(dm.map.cpu().numpy(), ref)
     dm.close()
+
+
+@pytest.mark.parametrize("offset,hw", [(1, (1440, 1920)), (4, (1440, 1920)), (0, (1439, 1917)), (3, (1439, 1917))])
+def test_label_image_alignment_and_odd_sizes(offset, hw):
+    """The fused kernel reads R and G with one aligned 8-byte load when the image allows it and with byte loads
+    otherwise (base not 8-byte aligned, size not a multiple of 8); both must give the reference's labels, for the
+    tagged (5 classes) and the masked (19 classes) count update."""
+    from vision_semantic_segmentation_b200.camera import camera_setup_1
+    cam = camera_setup_1()
+    boundary, res, mh, mw = [[100, 300], [800, 1000]], 0.1, 2000, 2000
+    for full19 in (False, True):
+        labels, names, colors = syn.class_setup(full19)
+        c = len(labels)
+        lane = names.index("lane")
+        dm = DeviceMapper(mh, mw, colors, np.eye(c), boundary, res, 100.0, True, lane, cameras=[cam], device=0)
+        ref = np.zeros((mh, mw, c))
+        for f in range(2):
+            fr = syn.synthetic_frame(55, f, 150000, height=hw[0], width=hw[1], blocky=(f == 1))
+            T = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
+            image = fr["semantic_image"]
+            buf = torch.zeros(image.size + 16, dtype=torch.uint8, device="cuda")
+            view = buf[offset:offset + image.size].view(hw[0], hw[1], 3)
+            view.copy_(torch.from_numpy(image))
+            assert view.data_ptr() % 8 == offset % 8
+            dm.integrate(dm.make_frame(dev(fr["points"]), view, T, 0))
+            mp, lab, _, _ = c_oracle.project_pcd(fr["pcd"], T, cam.P, image, 100.0)
+            c_oracle.update_map(ref, mp, lab, colors, np.eye(c), boundary, res, True, lane)
+            assert np.array_equal(dm.map.cpu().numpy(), ref), "frame %d" % f
+        dm.close()
+
+
+def test_points_on_cell_boundaries():
+    """Kept points snapped to within float32 noise of BEV cell edges -- including the grid's own edges and the
+    (-1, 0) strip that truncates to cell 0 -- must land in the reference's cells: the float32 cell decision has to
+    hand exactly these to the float64 / exact path."""
+    case = Case("cfg1_c19_count")
+    dm = make_mapper(case)
+    pcd, points, image, T = case.frame(0)
+    _, _, _, keep = c_oracle.project_pcd(pcd, T, case.cam.P, image, case.range_max)
+    rng = np.random.default_rng(5)
+    base = pcd[:, keep][:, :30000].copy()
+    off = np.array([1369.0496826171875, 562.84814453125])
+    b0 = np.array([case.boundary[0][0], case.boundary[1][0]], dtype=np.float64)
+    clouds = []
+    for axis in (0, 1):
+        v = base.copy()
+        g = ((v[axis] + off[axis]) - b0[axis]) / case.resolution
+        k = np.rint(g)
+        # a third of the points go to the grid's edges: -1, 0 and the last cell's upper edge
+        edge = rng.choice([-1.0, 0.0, float(case.mh if axis == 0 else case.mw)], size=k.shape)
+        k = np.where(rng.random(k.shape) < 0.33, edge, k)
+        x = k * case.resolution + b0[axis] - off[axis]
+        x32 = x.astype(np.float32)
+        # the float32 value next to the edge, one ulp below, one ulp above
+        step = rng.integers(-1, 2, size=x32.shape)
+        x32 = np.where(step < 0, np.nextafter(x32, np.float32(-np.inf)), np.where(step > 0, np.nextafter(x32, np.float32(np.inf)), x32))
+        v[axis] = x32.astype(np.float64)
+        clouds.append(v)
+    pcd2 = np.ascontiguousarray(np.hstack(clouds))
+    pts = np.ascontiguousarray(pcd2.T.astype(np.float32))
+    assert np.array_equal(pts.T.astype(np.float64), pcd2)
+    mp, lab, _, keep2 = c_oracle.project_pcd(pcd2, T, case.cam.P, image, case.range_max)
+    assert keep2.mean() > 0.2
+    ref = np.zeros((case.mh, case.mw, case.c))
+    c_oracle.update_map(ref, mp, lab, case.colors, case.cm, case.boundary, case.resolution, True, case.lane)
+    for ordered in (False, True):
+        dm.clear()
+        if ordered:
+            dm.notify_map_modified()
+        dm.integrate(dm.make_frame(dev(pts), dev(image), T, 0))
+        assert np.array_equal(dm.map.cpu().numpy(), ref), "ordered=%s" % ordered
+    dm.close()
