@@ -128,23 +128,31 @@ __device__ __forceinline__ bool cull32(const Fast32& k, float x, float y, float 
 
 // A deferred point: the float64 certified path (fast_project / fast_cell, exact chain behind them).  Returns
 // {pixel index, cell index}; cell == kNone: dropped.  About 3 % of the cull's survivors come here.
-__device__ __noinline__ uint2 fuse_decide64(const FrameParams* fp, const GridParams* gp, float4 w) {
+// Inlined on purpose: with one frame per launch `fp` and `gp` are kernel parameters at fixed offsets, so the float64
+// instructions take their constants straight from the constant bank; behind a call they were ~40 dependent generic
+// loads per point.  Only the exact chains (a few points per 10 000) stay out of line.
+#ifdef SMAP_FUSE_DECIDE64_CALL
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+uint2 fuse_decide64(const FrameParams& fp, const GridParams& gp, float4 w) {
     const double x = (double)w.x, y = (double)w.y, z = (double)w.z;
     const bool coords_ok = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fabsf(w.z)) < (float)kCoordBound;
-    int pix = fast_project(*fp, x, y, z, coords_ok);
-    if (pix == kAsk) pix = exact_project_slow(fp, x, y, z);
+    int pix = fast_project(fp, x, y, z, coords_ok);
+    if (pix == kAsk) pix = exact_project_slow(&fp, x, y, z);
     if (pix < 0) return make_uint2(0u, kNone);
     int cx = 0, cy = 0;
-    const int on = fast_cell(*gp, x, y, cx, cy);
+    const int on = fast_cell(gp, x, y, cx, cy);
     if (on == kAsk) {
-        const long long c2 = exact_cell_slow(gp, x, y);
+        const long long c2 = exact_cell_slow(&gp, x, y);
         if (c2 < 0) return make_uint2(0u, kNone);
         cx = (int)(c2 >> 32); cy = (int)(c2 & 0xffffffffll);
     } else if (on == kDrop) {
         return make_uint2(0u, kNone);
     }
-    return make_uint2((uint32_t)(pix >> 16) * (uint32_t)fp->img_w + (uint32_t)(pix & 0xffff),
-                      (uint32_t)cx * (uint32_t)gp->mw + (uint32_t)cy);
+    return make_uint2((uint32_t)(pix >> 16) * (uint32_t)fp.img_w + (uint32_t)(pix & 0xffff),
+                      (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy);
 }
 
 // ---- TMA (bulk async copy) + mbarrier plumbing of the per-warp cloud pipeline
@@ -392,7 +400,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             const float4 w = defer[first + lane];
             fid = (NF == 1) ? 0u : defer_f[first + lane];
             it = w.w;
-            pc = fuse_decide64(&B.f[fid].fp, &gp, w);
+            pc = fuse_decide64(B.f[fid].fp, gp, w);
             have = pc.y != kNone;
             if (MODE != 1 && have) {   // rare: straight into the block's box of that frame
                 const int cx = (int)(pc.y / (uint32_t)gp.mw), cy = (int)(pc.y - (uint32_t)cx * (uint32_t)gp.mw);
