@@ -103,7 +103,12 @@ constexpr int kFidShift = 28;   // a record's pixel index carries the frame inde
 constexpr int kFRound = SMAP_FUSE_ROUND;
 constexpr int kFRoundPts = 32 * kFRound;
 constexpr int kFBlockRoundPts = kWarps * kFRoundPts;
-constexpr int kFQueueCap = kFRoundPts + 32;
+#ifndef SMAP_FUSE_GROUP
+#define SMAP_FUSE_GROUP SMAP_FUSE_ROUND   // chunks culled back to back (unrolled) before the survivor stack is looked at
+#endif
+constexpr int kFGroup = SMAP_FUSE_GROUP;
+static_assert(kFRound % kFGroup == 0, "a round is a whole number of groups");
+constexpr int kFQueueCap = 32 * kFGroup + 32;      // survivor stack: < 32 left over + one group
 constexpr int kFDeferCap = 64;
 constexpr uint32_t kNone = 0xffffffffu;
 
@@ -549,16 +554,19 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             const int left = w_pts - r * kFRoundPts;
             const int pts = left < kFRoundPts ? left : kFRoundPts;
             const float4* sp = stages + st * kFRoundPts + lane;
+#pragma unroll 1
+            for (int g = 0; g < kFRound; g += kFGroup) {
 #pragma unroll
-            for (int j = 0; j < kFRound; ++j) {
-                const float4 w = sp[j * 32];
-                const bool pass = cull32(fk, w.x, w.y, w.z) & (j * 32 + lane < pts);
-                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
-                qn += __popc(ballot);
+                for (int j = 0; j < kFGroup; ++j) {
+                    const float4 w = sp[(g + j) * 32];
+                    const bool pass = cull32(fk, w.x, w.y, w.z) & ((g + j) * 32 + lane < pts);
+                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                    if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
+                    qn += __popc(ballot);
+                }
+                __syncwarp();
+                while (qn >= 32u) drain(f, 32u);
             }
-            __syncwarp();
-            while (qn >= 32u) drain(f, 32u);
         }
         // end of the frame for this warp: the survivors left over are decided with this frame's constants (records
         // and deferred points carry their frame and stay stacked)
