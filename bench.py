@@ -25,6 +25,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 from vision_semantic_segmentation_b200 import synthetic as syn  # noqa: E402
 from vision_semantic_segmentation_b200.utils import transforms as tr  # noqa: E402
