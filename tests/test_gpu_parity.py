@@ -359,3 +359,68 @@ def test_points_on_cell_boundaries():
         dm.integrate(dm.make_frame(dev(pts), dev(image), T, 0))
         assert np.array_equal(dm.map.cpu().numpy(), ref), "ordered=%s" % ordered
     dm.close()
+
+
+def test_cfg3_shape_log_likelihood_on_a_2km_grid():
+    """BASELINE.json configs[2] shape: confusion-matrix log-likelihood update into a 0.2 m, 2 km x 2 km grid
+    (10^4 x 10^4 x 5 float64 = 4 GB), then the count update on the same grid size (tag planes of 2.4 GB each);
+    whole grids compared with the oracle."""
+    from oracle import numpy_port
+    from vision_semantic_segmentation_b200.camera import camera_setup_1
+    labels, names, colors = syn.class_setup(False)
+    c = len(labels)
+    cam = camera_setup_1()
+    boundary, res, mh, mw = [[0, 2000], [0, 2000]], 0.2, 10000, 10000
+    lane = names.index("lane")
+    log_cm = numpy_port.confusion_submatrix_log(syn.synthetic_confusion_matrix(11), labels)
+    frames = []
+    for f in range(3):
+        fr = syn.synthetic_frame(2000, 7 * f, 400000, blocky=(f == 1))   # poses 21 m apart
+        T = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
+        frames.append((fr, T))
+    for cm in (log_cm, np.eye(c)):
+        dm = DeviceMapper(mh, mw, colors, cm, boundary, res, 100.0, True, lane, cameras=[cam], device=0)
+        ref = np.zeros((mh, mw, c))
+        keep = [(dev(fr["points"]), dev(fr["semantic_image"])) for fr, _ in frames]   # frames only hold raw pointers
+        dm.integrate_batch([dm.make_frame(dp, di, T, 0) for (dp, di), (_, T) in zip(keep, frames)])
+        for fr, T in frames:
+            mp, lab, _, _ = c_oracle.project_pcd(fr["pcd"], T, cam.P, fr["semantic_image"], 100.0)
+            c_oracle.update_map(ref, mp, lab, colors, cm, boundary, res, True, lane)
+        got = dm.map.cpu().numpy()
+        assert np.count_nonzero(ref) > 50000
+        assert np.array_equal(got, ref)
+        del got
+        dm.close()
+        del dm
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("log_cm", [False, True])
+def test_cfg5_shape_two_cameras_in_one_batch(log_cm):
+    """BASELINE.json configs[4] shape: frames of cam1 and cam6 (each with its own projection matrix) fused into one
+    grid, alternating inside a batch."""
+    from oracle import numpy_port
+    from vision_semantic_segmentation_b200.camera import camera_setup_1, camera_setup_6
+    labels, names, colors = syn.class_setup(True)
+    c = len(labels)
+    cams = [camera_setup_1(), camera_setup_6()]
+    boundary, res, mh, mw = [[0, 600], [0, 1400]], 0.2, 3000, 7000
+    lane = names.index("lane")
+    cm = numpy_port.confusion_submatrix_log(syn.synthetic_confusion_matrix(5), labels) if log_cm else np.eye(c)
+    dm = DeviceMapper(mh, mw, colors, cm, boundary, res, 100.0, True, lane, cameras=cams, device=0)
+    ref = np.zeros((mh, mw, c))
+    batch, keep = [], []
+    for f in range(6):
+        cam = cams[f % 2]
+        fr = syn.synthetic_frame(4000, f, 120000, blocky=(f % 3 == 0))
+        T = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
+        dp, di = dev(fr["points"]), dev(fr["semantic_image"])
+        keep.append((dp, di))
+        batch.append(dm.make_frame(dp, di, T, cam))
+        mp, lab, _, _ = c_oracle.project_pcd(fr["pcd"], T, cam.P, fr["semantic_image"], 100.0)
+        c_oracle.update_map(ref, mp, lab, colors, cm, boundary, res, True, lane)
+    dm.integrate_batch(batch)
+    assert np.array_equal(dm.map.cpu().numpy(), ref)
+    rgb = renderer.filter_and_render(dm.map, colors)
+    assert np.array_equal(rgb.cpu().numpy(), c_oracle.render_bev_map(c_oracle.apply_filter(ref), colors))
+    dm.close()
