@@ -39,8 +39,8 @@ MAP_H = MAP_W = 2000
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1024)
+    ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=2000000)
     ap.add_argument("--classes", type=int, default=5, choices=[5, 19],
@@ -64,17 +64,61 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every millisecond
+    (the timed region is only a few milliseconds long; nvidia-smi -lms cannot sample that fast), nvidia-smi as a
+    fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self._stop, self._thread, self._nvml = threading.Event(), None, None
+
+    def _poll(self):
+        nv, h = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def sample_now(self):
+        """One sample from the calling thread (called right after the timed loop has been queued, while the GPU is
+        still executing it): guarantees a sample under load even for a very short timed region."""
+        if self._nvml is not None:
+            nv, h = self._nvml
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: go through the PCI bus id of the torch device
+            try:
+                import torch
+                pr = torch.cuda.get_device_properties(self.index)
+                h = nv.nvmlDeviceGetHandleByPciBusId("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip().isdigit()]
+                h = nv.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._nvml = (nv, h)
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -85,6 +129,17 @@ class ClockSampler(object):
             self.lines.append(line.strip())
 
     def stop(self):
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            nv = self._nvml[0]
+            names = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                     ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                     ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                     ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+            reasons = sorted(n for n, bit in names if self.reason_bits & bit)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(self.samples), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -103,7 +158,7 @@ class ClockSampler(object):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def make_ring(args, rank):
@@ -271,6 +326,8 @@ def run_b200(args):
     e0.record()
     device_loop(args.steps, True)
     e1.record()
+    if rank == 0:
+        sampler.sample_now()
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None

@@ -12,14 +12,14 @@
 #include "smap_fuse.cuh"
 
 #ifndef SMAP_AUX_STREAMS
-#define SMAP_AUX_STREAMS 2      // internal streams the per-frame k_fuse launches of a batch alternate over
+#define SMAP_AUX_STREAMS 4      // internal streams the per-frame k_fuse launches of a batch alternate over
 #endif
 #ifndef SMAP_TAG_MAX_PLANES
 #define SMAP_TAG_MAX_PLANES 8   // count update: per-(cell, class) tags up to this many tags per cell (C + 1), masks beyond
 #endif
 #ifndef SMAP_FUSE_GRID_DIV
-#define SMAP_FUSE_GRID_DIV 1    // > 1: a frame's launch fills only 1/DIV of the resident block slots, so that the
-#endif                          // launches of DIV frames (on different internal streams) run side by side
+#define SMAP_FUSE_GRID_DIV 2    // > 1: inside a batch a frame's launch fills only 1/DIV of the resident block slots, so
+#endif                          // that the launches of DIV frames (on different internal streams) run side by side
 #ifndef SMAP_FUSE_PERSISTENT
 #define SMAP_FUSE_PERSISTENT 0  // 1: one persistent k_fuse launch per batch (measured alternative, see smap_fuse.cuh)
 #endif
@@ -498,10 +498,10 @@ int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp,
 }
 
 // persistent grid: as many blocks as stay resident, never more than the largest cloud has block-rounds
-int fuse_grid(const smap_handle* h, FuseFrame* f, int n, int64_t* gx_out) {
+int fuse_grid(const smap_handle* h, FuseFrame* f, int n, int div, int64_t* gx_out) {
     int64_t n_max = 0;
     for (int k = 0; k < n; ++k) n_max = f[k].n > n_max ? f[k].n : n_max;
-    int64_t gx = (int64_t)h->sm_count * SMAP_FUSE_MINB / SMAP_FUSE_GRID_DIV;
+    int64_t gx = (int64_t)h->sm_count * SMAP_FUSE_MINB / div;
     const int64_t rounds = ceil_div(n_max, kFBlockRoundPts);
     if (gx > rounds) gx = rounds;
     for (int k = 0; k < n; ++k) {
@@ -555,7 +555,7 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         }
         if (in_launch == 0) break;
         int64_t gx = 0;
-        int rc = fuse_grid(h, fb->f, in_launch, &gx);
+        int rc = fuse_grid(h, fb->f, in_launch, 1, &gx);
         if (rc) return rc;
         fb->tags = count_atomics ? h->tags : nullptr;
         fb->n_frames = in_launch;
@@ -592,7 +592,7 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         int rc = fill_fuse_frame(h, frames + i, fps[i], mode, used, fb->f[0]);
         if (rc) return rc;
         int64_t gx = 0;
-        rc = fuse_grid(h, fb->f, 1, &gx);
+        rc = fuse_grid(h, fb->f, 1, fork ? SMAP_FUSE_GRID_DIV : 1, &gx);
         if (rc) return rc;
         // one tag plane per launching stream; a frame's tag is larger than every tag written to its plane before
         fb->tags = count_atomics ? h->tags + plane_words * (size_t)(lane_stream % h->n_tag_planes) : nullptr;

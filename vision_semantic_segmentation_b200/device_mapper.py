@@ -119,6 +119,7 @@ class DeviceMapper(object):
                 raise ValueError("world_to_velodyne must be 4x4")
             f.has_transform = 1
             ctypes.memmove(f.world_to_velodyne, T.ctypes.data, 128)
+        f._tensors = (points, image)   # the struct holds raw pointers: keep the tensors alive as long as it lives
         return f
 
     # ------------------------------------------------------------------ the path
