@@ -147,7 +147,7 @@ SMAP_API int smap_update(smap_handle *h, double *map_dev, const double *pcd_dev,
  * only updated by count updates of this handle), the fused kernel itself adds 1.0 per newly observed
  * (cell, class) and 2.0 per lane boost with float64 atomics: sums of small integers, exact in any order, so the
  * result is the same bits.  "Newly observed" is decided with per-(cell, class) frame tags (up to 7 classes; the
- * handle then allocates 2 x cells x (C + 1) uint32 on first use) or with the per-frame cell masks (more classes).
+ * handle then allocates 4 x cells x (C + 1) uint32 on first use) or with the per-frame cell masks (more classes).
  * smap_upload / smap_notify_map_modified switch back to the ordered update.
  * float4 clouds take the fast kernel (float32 decisions with rigorous error bounds, float64 only for the few
  * points they cannot decide); label images of 2^28 pixels or more are rejected there. */
