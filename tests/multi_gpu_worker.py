@@ -25,7 +25,15 @@ frames = [syn.synthetic_frame(case.spec["seed"], f, case.spec["n_points"], block
           for f in range(case.spec["frames"])]
 color_map = sm.mapping_replay(frames, "sharded", write_image=(rank == 0))
 assert np.array_equal(color_map, case.arrays["rgb"]), "rank %d: rendered map differs" % rank
-assert sha(sm.map) == case.spec["filtered_sha"], "rank %d: filtered grid differs" % rank
+filtered_full = sm.map
+assert sha(filtered_full) == case.spec["filtered_sha"], "rank %d: filtered grid differs" % rank
+# large-map variant: reduce-scatter by rows + halo exchange, every rank renders its own tile, image all-gathered
+color_map = sm.mapping_replay(frames, "sharded_tiles", write_image=False, row_tiles=True)
+assert np.array_equal(color_map, case.arrays["rgb"]), "rank %d: row-tiled rendered map differs" % rank
+r0, r1 = frame_sharding.row_tile(case.mh, rank, world)
+want = np.zeros_like(filtered_full)
+want[r0:r1] = filtered_full[r0:r1]
+assert np.array_equal(sm.map, want), "rank %d: filtered tile differs" % rank
 dist.barrier()
 print("rank %d/%d ok" % (rank, world))
 dist.destroy_process_group()

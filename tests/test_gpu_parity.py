@@ -424,3 +424,27 @@ def test_cfg5_shape_two_cameras_in_one_batch(log_cm):
     rgb = renderer.filter_and_render(dm.map, colors)
     assert np.array_equal(rgb.cpu().numpy(), c_oracle.render_bev_map(c_oracle.apply_filter(ref), colors))
     dm.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 7])
+def test_row_tiled_render_equals_whole_map_render(world):
+    """frame_sharding.render_row_tile on row tiles with one-row halos (what sum_grid_row_tile hands every rank)
+    reproduces the whole-map filter + render, seams and true borders included."""
+    from vision_semantic_segmentation_b200 import frame_sharding
+    rng = np.random.default_rng(world)
+    mh, mw, c = 61, 45, 5
+    grid = rng.integers(0, 4, (mh, mw, c)).astype(np.float64) * (rng.random((mh, mw, 1)) < 0.4)
+    colors = rng.integers(0, 256, (c, 3))
+    whole_rgb, whole_f = renderer.filter_and_render(dev(grid), colors, return_filtered=True)
+    rows_rgb, rows_f = [], []
+    for rank in range(world):
+        r0, r1 = frame_sharding.row_tile(mh, rank, world)
+        top = 1 if r0 > 0 and r1 > r0 else 0
+        bottom = 1 if r1 < mh and r1 > r0 else 0
+        tile = dev(grid[r0 - top:r1 + bottom])
+        rgb, filt = frame_sharding.render_row_tile(tile, top, bottom, colors, return_filtered=True)
+        assert rgb.shape[0] == r1 - r0
+        rows_rgb.append(rgb)
+        rows_f.append(filt)
+    assert torch.equal(torch.cat(rows_rgb), whole_rgb)
+    assert torch.equal(torch.cat(rows_f), whole_f)

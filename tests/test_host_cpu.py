@@ -172,12 +172,21 @@ n_frames = 5
 mine = np.zeros((400, 400, 5))
 for f in frame_sharding.shard_range(n_frames, rank, world):
     add(mine, f)
+partial = mine.copy()
 t = torch.from_numpy(mine)
 frame_sharding.sum_grids(t)
 full = np.zeros((400, 400, 5))
 for f in range(n_frames):
     add(full, f)
 assert np.array_equal(t.numpy(), full), "sharded sum differs from the sequential grid"
+# row tiles: reduce-scatter by rows + one-row halos, filter + render per tile, image all-gathered
+tile, r0, r1, top, bottom = frame_sharding.sum_grid_row_tile(torch.from_numpy(partial))
+assert (r0, r1) == frame_sharding.row_tile(400, rank, world)
+assert np.array_equal(tile.numpy(), full[r0 - top:r1 + bottom]), "row tile / halo differs"
+f_tile = c_oracle.apply_filter(tile.numpy())   # the oracle stands in for the CUDA renderer on CPU
+rgb_tile = c_oracle.render_bev_map(f_tile, colors)[top:tile.shape[0] - bottom]
+rgb = frame_sharding.gather_rgb_rows(torch.from_numpy(np.ascontiguousarray(rgb_tile)), 400)
+assert np.array_equal(rgb.numpy(), c_oracle.render_bev_map(c_oracle.apply_filter(full), colors)), "tiled render differs"
 dist.barrier()
 dist.destroy_process_group()
 sys.stdout.write("rank %%d ok\n" %% rank)   # one write per rank: the two ranks share a pipe

@@ -245,9 +245,14 @@ class SemanticMapping(object):
                                       frame_input_dict["pose"], cam)
         self.device_mapper.integrate(frame)
 
-    def mapping_replay(self, input_list, file_name, write_image=True):
+    def mapping_replay(self, input_list, file_name, write_image=True, row_tiles=False):
         """Map all frames of ``input_list`` into a fresh grid, smooth, render, save
-        ``global_map_<file_name>.png`` (``src/mapping_replay.py:175-211``).  Returns the colour map."""
+        ``global_map_<file_name>.png`` (``src/mapping_replay.py:175-211``).  Returns the colour map.
+        Under torch.distributed the frames are sharded over the ranks.  ``row_tiles=False``: the grids are all-reduced
+        and every rank filters and renders the whole map (``self.map`` = the filtered map, as in the reference).
+        ``row_tiles=True`` (large maps): the grids are reduce-scattered by rows, every rank filters and renders its own
+        tile (one-row halos from the neighbours), the image is all-gathered; ``self.map`` then holds the filtered rows
+        of this rank's tile only, zeros elsewhere."""
         from . import frame_sharding
         dm = self.device_mapper
         dm.clear()
@@ -255,11 +260,17 @@ class SemanticMapping(object):
         rank, world = frame_sharding.rank_and_world()
         for idx in frame_sharding.shard_range(len(input_list), rank, world):
             self.integrate_frame(input_list[idx])
-        if world > 1:
-            frame_sharding.sum_grids(dm.map)
-
-        color_map, filtered = filter_and_render(dm.map, self.label_colors, return_filtered=True)
-        dm.map.copy_(filtered)  # self.map = apply_filter(self.map)
+        if world > 1 and row_tiles:
+            tile, r0, r1, top, bottom = frame_sharding.sum_grid_row_tile(dm.map)
+            rgb_tile, filtered = frame_sharding.render_row_tile(tile, top, bottom, self.label_colors, return_filtered=True)
+            color_map = frame_sharding.gather_rgb_rows(rgb_tile, dm.map.shape[0])
+            dm.map.zero_()
+            dm.map[r0:r1].copy_(filtered)
+        else:
+            if world > 1:
+                frame_sharding.sum_grids(dm.map)
+            color_map, filtered = filter_and_render(dm.map, self.label_colors, return_filtered=True)
+            dm.map.copy_(filtered)  # self.map = apply_filter(self.map)
         dm.notify_map_modified()
         color_map = color_map.cpu().numpy()
 
