@@ -108,6 +108,9 @@ constexpr int kFBlockRoundPts = kWarps * kFRoundPts;
 #endif
 constexpr int kFGroup = SMAP_FUSE_GROUP;
 static_assert(kFRound % kFGroup == 0, "a round is a whole number of groups");
+#if !defined(SMAP_FUSE_TMA) || !SMAP_FUSE_TMA
+static_assert(kFGroup == kFRound, "the register-prefetch path culls a whole round before it looks at the stack");
+#endif
 constexpr int kFQueueCap = 32 * kFGroup + 32;      // survivor stack: < 32 left over + one group
 constexpr int kFDeferCap = 64;
 constexpr uint32_t kNone = 0xffffffffu;
@@ -174,10 +177,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // (the bulk copies themselves -- cp.async.bulk global -> shared, 16-byte granular, completion counted in bytes on
 // the stage's mbarrier, evict-first in L2 because the cloud is read once -- are issued inline in k_fuse)
 
+// How the cloud reaches the cull.  Default: the next round is prefetched into registers with plain LDG.128 while the
+// current one is processed.  -DSMAP_FUSE_TMA=1: a private ring of SMAP_FUSE_STAGES shared-memory stages per warp filled
+// by TMA bulk copies (cp.async.bulk + mbarrier complete_tx, L2 evict-first), one LDS.128 per point.  Both keep one
+// round per warp in flight; the TMA ring costs 52 instructions of round set-up per 64 points (elect, expect_tx,
+// descriptor operands through uniform registers, try_wait) against 25 for the register prefetch, and its stages push
+// the block over a shared-memory carve-out step: 15.3 vs 14.5 us / frame (profiles/r1_sweep27.log).
+#ifndef SMAP_FUSE_TMA
+#define SMAP_FUSE_TMA 0
+#endif
 #ifndef SMAP_FUSE_STAGES
 #define SMAP_FUSE_STAGES 2
 #endif
-constexpr int kFStages = SMAP_FUSE_STAGES;
+constexpr int kFStages = SMAP_FUSE_TMA ? SMAP_FUSE_STAGES : 0;
 #ifndef SMAP_FUSE_GATHER
 #define SMAP_FUSE_GATHER 2
 #endif
@@ -208,13 +220,12 @@ __host__ __device__ constexpr int fuse_block_smem(int nf) { return kWarps * fuse
 //         frames of a batch use different tag planes (interleaved: the planes of one element share a sector), so
 //         warps may be at different frames without any synchronisation.
 //
-// Persistent grid, every warp autonomous (no block barrier after the prologue).  Per frame a warp owns a contiguous,
-// equally sized slice of the cloud, which it walks in rounds of kFRoundPts points:
-//   cloud     a private ring of kFStages shared-memory stages filled by TMA bulk copies (cp.async.bulk +
-//             mbarrier complete_tx) that runs ahead across frame boundaries: no registers and no scoreboards are
-//             tied up by the stream (a register-prefetched version stalled on exactly those);
-//   cull      one LDS.128 per point, conservative float32 test (cull32), survivors (~36 %) pushed on the warp's
-//             stack (ballot + popc);
+// Every warp is autonomous (no block barrier after the prologue).  Per frame a warp owns a contiguous, equally sized
+// slice of the cloud, which it walks in rounds of kFRoundPts points:
+//   cloud     the next round is prefetched into registers (LDG.128, streaming) while the current one is processed;
+//             -DSMAP_FUSE_TMA=1 selects a per-warp ring of shared-memory stages filled by TMA bulk copies instead
+//             (measured: more round set-up instructions than it saves, see above);
+//   cull      conservative float32 test (cull32), survivors (~36 %) pushed on the warp's stack (ballot + popc);
 //   decide    whenever >= 32 survivors are stacked, pop 32 -- one per lane, all lanes busy: float32 decisions; the
 //             undecided points go to the deferred stack (decided in float64, 32 at a time), the accepted ones to
 //             the record stack as {pixel | frame, cell | intensity flag};
@@ -242,6 +253,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
     uint2* const recs = reinterpret_cast<uint2*>(defer + kFDeferCap);
     uint8_t* const defer_f = reinterpret_cast<uint8_t*>(recs + kFRecCap);   // NF > 1 only
     uint64_t* const bars = reinterpret_cast<uint64_t*>(defer_f + (NF > 1 ? kFDeferCap : 0));
+    (void)bars;
     uint32_t* const s_tab_r = reinterpret_cast<uint32_t*>(s_dyn + (size_t)kWarps * kFWarpSmem);
     uint32_t* const s_tab_g = s_tab_r + 256;
 
@@ -253,6 +265,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
         return left <= 0 ? 0 : (left < B.f[f].per_warp ? (int)left : B.f[f].per_warp);
     };
 
+#if SMAP_FUSE_TMA
     // ---- TMA producer state (meaningful in lane 0): frame, source and points left of the next round to issue
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
@@ -288,6 +301,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
 #pragma unroll
     for (int r = 0; r < kFStages - 1; ++r) issue_round();   // one more is issued at the top of every round
     // the first rounds are on their way while the block builds its colour tables
+#endif
     build_color_tables(gp, s_tab_r, s_tab_g);
     if (threadIdx.x < NF) box_reset(s_box[threadIdx.x]);
     __syncthreads();
@@ -539,11 +553,44 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
         }
     };
 
+#if SMAP_FUSE_TMA
     uint32_t rr = 0;   // rounds consumed so far (all frames): stage = rr % kFStages, parity from rr / kFStages
+#endif
     for (int f = 0; f < nf; ++f) {
         const Fast32& fk = B.f[f].fk;
         const int w_pts = slice_pts(f);
         const int n_rounds = (w_pts + kFRoundPts - 1) / kFRoundPts;
+#if !SMAP_FUSE_TMA
+        // the next round is prefetched into registers (LDG.128, streaming) while the current one is processed
+        {
+            const float4* gp_pts = B.f[f].pts + gw * B.f[f].per_warp + lane;
+            float4 buf[kFRound];
+#pragma unroll
+            for (int j = 0; j < kFRound; ++j)
+                buf[j] = (j * 32 + lane < w_pts) ? __ldcs(gp_pts + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < n_rounds; ++r) {
+                const int left = w_pts - r * kFRoundPts;
+                const int pts = left < kFRoundPts ? left : kFRoundPts;
+                float4 nxt[kFRound];
+#pragma unroll
+                for (int j = 0; j < kFRound; ++j)
+                    nxt[j] = (kFRoundPts + j * 32 + lane < left) ? __ldcs(gp_pts + (r + 1) * kFRoundPts + j * 32)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < kFRound; ++j) {
+                    const float4 w = buf[j];
+                    const bool pass = cull32(fk, w.x, w.y, w.z) & (j * 32 + lane < pts);
+                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                    if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
+                    qn += __popc(ballot);
+                }
+                __syncwarp();
+                while (qn >= 32u) drain(f, 32u);
+#pragma unroll
+                for (int j = 0; j < kFRound; ++j) buf[j] = nxt[j];
+            }
+        }
+#else
         for (int r = 0; r < n_rounds; ++r, ++rr) {
             // keep kFStages - 1 rounds in flight: the next one goes into the stage that the previous round used
             // (every lane has consumed its reads of that stage, and the warp has re-converged since)
@@ -568,6 +615,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
                 while (qn >= 32u) drain(f, 32u);
             }
         }
+#endif
         // end of the frame for this warp: the survivors left over are decided with this frame's constants (records
         // and deferred points carry their frame and stay stacked)
         if (qn) drain(f, qn);
