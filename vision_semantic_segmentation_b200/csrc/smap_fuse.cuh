@@ -1,10 +1,10 @@
 // k_fuse: the fused project -> cull -> label lookup -> cell -> update kernel for float4 clouds (sm_100a).
 //
-// Same per-point rule as k_stream (SURVEY.md section 9 = src/mapping_replay.py:214-301), but every point is first
+// Same per-point rule as k_stream_soa (SURVEY.md section 9 = src/mapping_replay.py:214-301), but every point is first
 // decided in FLOAT32 with a rigorous error bound ("filtered predicate"), because the kernel is bound by
 // instruction issue, not by HBM: the integers the reference produces -- keep / drop, pixel (iu, iv), cell
 // (cx, cy) -- are floors of real quantities, and a float32 evaluation in coordinates re-centred on the vehicle
-// yields the same integers unless a quantity lies within its error bound of an integer.  Those points (~1 %)
+// yields the same integers unless a quantity lies within its error bound of an integer.  Those points (2.7 %)
 // are set aside on a second per-warp stack and decided by the float64 certified path of smap_device.cuh
 // (fast_project / fast_cell, themselves backed by the reference's own rounding chain), 32 at a time.
 // The results are therefore bit-identical to the reference by construction; the float32 arithmetic only
@@ -16,8 +16,8 @@
 //                 exact Q = sum A_j D_j + beta:  |q~ - Q| <= 5.1 u (sum |A_j| |D_j| + |beta|)
 //                 -> E_r(rho) = 6 u (amax_r rho + |beta_r|) + e_ref_r,   rho = |xl| + |yl| + |zl|
 //                 (e_ref_r: what the reference's own float64 chain and the host's composition may differ from Q)
-//   quotient      us = q0' r~ (kept unrounded inside two FMAs), r~ = MUFU.RCP(q2~) (<= 2 ulp), q0' = q0 - q2 / 2 so that us ~ u - 1/2 and
-//                 RN(us) = floor(u) away from the integers.  With |q2~| > 4 E_2:
+//   quotient      us = q0' r~ (kept unrounded inside two FMAs), r~ = MUFU.RCP(q2~) (<= 2 ulp), q0' = q0 - q2 / 2, so
+//                 that us ~ u - 1/2 and RN(us) = floor(u) away from the integers.  With |q2~| > 4 E_2:
 //                 |us - (u_ref - 1/2)| <= (4/3)(E_0' + Umax E_2) |r~| + Umax 2^-21  =: g
 //                 certified  <=>  |us - RN(us)| < 1/2 - g   (implies |q2~| > 4 E_2, see smap.cu)
 //   range         |d~ - vx_ref| <= E_d(rho);  certified inside  <=>  |d~ - R/2| < R/2 - E_d
@@ -77,11 +77,12 @@ struct FuseFrame {
 // Kernel parameter of k_fuse<MODE, NF>: the NF frames a launch walks.
 //   NF == 1          one launch per frame (on alternating internal streams, so that the ramp-up and tail of one
 //                    launch overlap the next one's body); every per-frame constant then sits at a fixed offset of the
-//                    constant bank.  This is what the library uses: 17.2 us / frame on the benchmark workload.
+//                    constant bank.  This is what the library uses (13.4 us / frame on the benchmark workload; 17.2
+//                    at the time of the comparison below).
 //   NF == kMaxBatch  ONE persistent launch walks all the frames of a batch: frame f + 1's cloud is already in flight
 //                    while frame f's last survivors are decided, records and deferred points carry their frame
 //                    index, nothing is flushed between frames.  Kept as a measured alternative (SMAP_FUSE_PERSISTENT):
-//                    19.0 us / frame -- the run-time frame index turns every constant operand into an indexed LDC,
+//                    18.4 - 19.0 us / frame -- the run-time frame index turns every constant operand into an indexed LDC,
 //                    which costs more than the per-launch ramp it saves.  (A third variant, one launch per batch with
 //                    frame = blockIdx.y, measured 21.4 us / frame.)
 template <int NF>
