@@ -8,8 +8,10 @@ fraction of the HBM roofline, next to the CPU path timed on the same box).
 A "step" is one frame of BASELINE.json configs[1]: a 2M-point local cloud + one 1920x1440
 19-class label image, count-based update into the default 2000x2000 BEV grid.  Inputs are a ring of
 distinct frames resident in HBM (ring >> L2), so every step streams its cloud and image from DRAM.
-Frames are handed to the C ABI 16 at a time (smap_integrate_batch: one fused kernel per frame, launched on two
-alternating internal streams; the count update needs no second kernel).
+Frames are handed to the C ABI 16 at a time (smap_integrate_batch: one fused kernel per frame; inside a batch a launch
+takes half of the resident block slots and the launches alternate over four internal streams, so two frames run side by
+side; the count update needs no second kernel).  `roofline.kernel_ms` is the same kernel launched alone with the full
+grid (the library's profiling mode serialises the launches on the caller's stream).
 N > 1: one process per GPU (torchrun), frames sharded by rank (weak scaling: every rank integrates K
 frames), one NCCL all-reduce of the grids at the end of the timed region.
 """

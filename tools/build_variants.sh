@@ -1,14 +1,15 @@
 #!/bin/bash
 # Builds kernel-tuning variants of the library (dev tool for the sweeps recorded in profiles/).
-# usage: [EXTRA="-D..."] tools/build_variants.sh "ROUND MINB" ...  -> csrc/variants/r<ROUND>_b<MINB>[_tag].so
+# usage: tools/build_variants.sh NAME "-DSMAP_FUSE_MINB=3 -DSMAP_FUSE_GATHER=4 ..." [NAME2 "..."]  -> csrc/variants/NAME.so
+# knobs: SMAP_FUSE_MINB / ROUND / GATHER, SMAP_FUSE_TMA (+ STAGES, GROUP), SMAP_FUSE_PERSISTENT, SMAP_FUSE_GRID_DIV,
+#        SMAP_AUX_STREAMS, SMAP_TAG_MAX_PLANES, SMAP_FUSE_STATS, SMAP_ABL_NO_{DRAIN,GATHER,SCATTER,DEFER}
 set -e
 cd "$(dirname "$0")/../vision_semantic_segmentation_b200/csrc"
 mkdir -p variants
-for v in "$@"; do
-  set -- $v
-  out=variants/r$1_b$2${TAG:+_$TAG}.so
+while [ $# -ge 2 ]; do
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC \
-       -Xcompiler -fvisibility=hidden -shared -DSMAP_STREAM_ROUND=$1 -DSMAP_STREAM_MINB=$2 $EXTRA \
-       -Xptxas -v -o $out smap.cu 2>&1 | grep -A2 "k_streamILi0" | grep -E "registers|spill" | sed 's/ptxas info    ://g' | tr '\n' ' '
-  echo " -> $out"
+       -Xcompiler -fvisibility=hidden -shared $2 -Xptxas -v -o variants/$1.so smap.cu 2>&1 \
+       | grep -A2 "k_fuseILi1ELi1E" | grep -E "registers|spill" | sed 's/ptxas info    ://g' | tr '\n' ' '
+  echo " -> variants/$1.so ($2)"
+  shift 2
 done
