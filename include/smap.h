@@ -191,6 +191,10 @@ SMAP_API int smap_get_stats(smap_handle *h, smap_stats *out);     /* synchronise
 /* on != 0: time the kernels of every smap_integrate* call with CUDA events (the per-frame launches are then
  * issued on the caller's stream only, not over the internal streams); read the totals with smap_get_stats. */
 SMAP_API int smap_set_profiling(smap_handle *h, int on);
+/* Test hook: sets the counter the count update draws its per-frame tags from (uint32, strictly increasing; the tag
+ * planes are re-zeroed and the counter restarts when it would overflow).  Lets a test reach that path without
+ * integrating 2^32 frames.  Only moves the counter forward. */
+SMAP_API int smap_debug_set_frame_tag(smap_handle *h, uint32_t value);
 
 #ifdef __cplusplus
 }

@@ -448,3 +448,25 @@ def test_row_tiled_render_equals_whole_map_render(world):
         rows_f.append(filt)
     assert torch.equal(torch.cat(rows_rgb), whole_rgb)
     assert torch.equal(torch.cat(rows_f), whole_f)
+
+
+def test_frame_tag_space_wraps_cleanly():
+    """The count update de-duplicates with uint32 frame tags that only grow; when the counter is about to overflow
+    the tag planes are re-zeroed and it restarts.  A test hook moves the counter next to 2^32 so that the wrap
+    happens in the middle of 40 frames (three batches); every count must still be right."""
+    from vision_semantic_segmentation_b200 import _native
+    case = Case("cfg1_c5_count")
+    dm = make_mapper(case)
+    lib = _native.load()
+    frames = [case.frame(f % 3) for f in range(3)]
+    keep = [(dev(points), dev(image)) for _, points, image, _ in frames]
+    batch = [dm.make_frame(keep[f % 3][0], keep[f % 3][1], frames[f % 3][3], 0) for f in range(40)]
+    dm.integrate_batch(batch[:5])                      # allocates the tag planes, tags 1..5
+    _native.check(lib.smap_debug_set_frame_tag(dm._h, 0xffffffff - 25))
+    dm.integrate_batch(batch[5:])                      # 16 + 16 + 3 frames: the second batch trips the wrap
+    # frames 0, 1, 2 were integrated 14, 13 and 13 times; counts are additive
+    per = [_oracle_grid(case, [frames[k]]) for k in range(3)]
+    ref = 14.0 * per[0] + 13.0 * per[1] + 13.0 * per[2]
+    assert np.array_equal(dm.map.cpu().numpy(), ref)
+    assert lib.smap_debug_set_frame_tag(dm._h, 1) != 0   # only forward
+    dm.close()

@@ -1034,6 +1034,13 @@ int smap_set_profiling(smap_handle* h, int on) {
     return SMAP_OK;
 }
 
+int smap_debug_set_frame_tag(smap_handle* h, uint32_t value) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    if (value < h->frame_tag) return fail(SMAP_ERR_INVALID, "the frame tag only moves forward");
+    h->frame_tag = value;
+    return SMAP_OK;
+}
+
 int smap_notify_map_modified(smap_handle* h) {
     if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
     h->integer_grid = false;
