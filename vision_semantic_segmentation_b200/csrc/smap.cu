@@ -587,7 +587,9 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
     FuseBatchT<1>* fb = &h->fuse_one;
     for (int i = 0; i < n_frames; ++i) {
         if (frames[i].n_points == 0) continue;
-        const int lane_stream = fork ? used % smap_handle::kAux : 0;
+        // tagged count update: never more streams than tag planes (two frames on one plane must not overlap)
+        const int n_streams = (mode == 1 && h->n_tag_planes < smap_handle::kAux) ? h->n_tag_planes : smap_handle::kAux;
+        const int lane_stream = fork ? used % n_streams : 0;
         cudaStream_t ls = fork ? h->aux[lane_stream] : st;
         int rc = fill_fuse_frame(h, frames + i, fps[i], mode, used, fb->f[0]);
         if (rc) return rc;
@@ -595,7 +597,7 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         rc = fuse_grid(h, fb->f, 1, fork ? SMAP_FUSE_GRID_DIV : 1, &gx);
         if (rc) return rc;
         // one tag plane per launching stream; a frame's tag is larger than every tag written to its plane before
-        fb->tags = count_atomics ? h->tags + plane_words * (size_t)(lane_stream % h->n_tag_planes) : nullptr;
+        fb->tags = count_atomics ? h->tags + plane_words * (size_t)lane_stream : nullptr;
         fb->n_frames = 1;
         fb->tag_planes = 1;
         FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + used;
