@@ -195,6 +195,11 @@ SMAP_API int smap_set_profiling(smap_handle *h, int on);
  * planes are re-zeroed and the counter restarts when it would overflow).  Lets a test reach that path without
  * integrating 2^32 frames.  Only moves the counter forward. */
 SMAP_API int smap_debug_set_frame_tag(smap_handle *h, uint32_t value);
+/* Test hook, host only (no device needed): the per-frame constants of the float32 decision path of the fused kernel
+ * (csrc/smap_fuse.cuh, struct Fast32, in declaration order, uint32 fields as exact doubles; 69 values) for a
+ * configuration, a frame description (pointers ignored) and a camera matrix.  tests/test_fast32_bounds.py emulates
+ * the kernel's float32 arithmetic with them on the CPU and checks every certified decision against the oracle. */
+SMAP_API int smap_debug_fast32(const smap_config *cfg, const smap_frame *frame, const double P_host[12], double *out69);
 
 #ifdef __cplusplus
 }

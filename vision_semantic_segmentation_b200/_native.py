@@ -19,7 +19,7 @@ EXPORTS = [
     "smap_abi_version", "smap_last_error", "smap_device_count", "smap_device_info", "smap_create",
     "smap_destroy", "smap_set_camera", "smap_set_classes", "smap_project", "smap_update", "smap_integrate",
     "smap_integrate_batch", "smap_integrate_host", "smap_apply_filter", "smap_render", "smap_filter_render",
-    "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_notify_map_modified", "smap_download", "smap_upload", "smap_get_stats", "smap_set_profiling", "smap_debug_set_frame_tag",
+    "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_notify_map_modified", "smap_download", "smap_upload", "smap_get_stats", "smap_set_profiling", "smap_debug_set_frame_tag", "smap_debug_fast32",
 ]
 
 
@@ -112,6 +112,9 @@ def load():
     L.smap_notify_map_modified.argtypes = [vp]
     L.smap_debug_set_frame_tag.restype = i32
     L.smap_debug_set_frame_tag.argtypes = [vp, ctypes.c_uint32]
+    L.smap_debug_fast32.restype = i32
+    L.smap_debug_fast32.argtypes = [ctypes.POINTER(SmapConfig), ctypes.POINTER(SmapFrame), ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_double)]
     L.smap_download.restype = i32
     L.smap_download.argtypes = [vp, vp]
     L.smap_upload.restype = i32

@@ -290,6 +290,9 @@ void fill_fast32(const smap_handle* h, const smap_frame* f, const FrameParams& f
     k.n_ctr_xy = make_float2(-cf[0], -cf[1]);
     k.n_ctr_z = -cf[2];
     bool ok = r_ok;
+    for (int r = 0; r < 4; ++r)
+        for (int j = 0; j < 4; ++j)
+            if (!(fabs(row[r][j]) < 1e30)) ok = false;   // NaN / inf in the matrices: fmax() below would skip them
     {
         const double bloc = cmax + L;
         // local rows: 0 = q0 - q2/2, 1 = q1 - q2/2, 2 = q2, 3 = velodyne x;  beta = row . (c, 1)
@@ -1041,6 +1044,46 @@ int smap_debug_set_frame_tag(smap_handle* h, uint32_t value) {
     if (value < h->frame_tag) return fail(SMAP_ERR_INVALID, "the frame tag only moves forward");
     h->frame_tag = value;
     return SMAP_OK;
+}
+
+int smap_debug_fast32(const smap_config* cfg, const smap_frame* frame, const double P_host[12], double* out) {
+    if (!cfg || !frame || !P_host || !out) return fail(SMAP_ERR_INVALID, "NULL argument");
+    smap_handle* h = new (std::nothrow) smap_handle();
+    if (!h) return fail(SMAP_ERR_NOMEM, "out of host memory");
+    h->cfg = *cfg;
+    memcpy(h->P[0], P_host, sizeof(double) * 12);
+    h->cam_set[0] = true;
+    smap_frame f = *frame;
+    f.camera = 0;
+    f.points_dev = nullptr;
+    f.image_dev = nullptr;
+    f.n_points = 0;
+    f.layout = SMAP_PTS_F32X4;
+    FrameParams fp;
+    int rc = fill_frame_params(h, &f, fp);
+    if (!rc) {
+        Fast32 k;
+        fill_fast32(h, &f, fp, k);
+        int n = 0;
+        auto put2 = [&](float2 v) { out[n++] = v.x; out[n++] = v.y; };
+        for (int j = 0; j < 4; ++j) put2(k.c_dc[j]);
+        for (int j = 0; j < 4; ++j) put2(k.c_ab[j]);
+        put2(k.c_wh);
+        out[n++] = k.c_bw; out[n++] = k.c_rh; out[n++] = k.c_rthr; out[n++] = k.c_depth;
+        out[n++] = k.c_lo_u; out[n++] = k.c_hi_u; out[n++] = k.c_lo_v; out[n++] = k.c_hi_v;
+        put2(k.n_ctr_xy);
+        out[n++] = k.n_ctr_z; out[n++] = k.coord_l;
+        for (int j = 0; j < 4; ++j) put2(k.d_uv[j]);
+        for (int j = 0; j < 4; ++j) put2(k.d_cd[j]);
+        out[n++] = k.g_k1; out[n++] = k.g_k0; out[n++] = k.g_hc;
+        out[n++] = k.r_h; out[n++] = k.r_kd; out[n++] = k.r_thr0;
+        put2(k.mid_uv); put2(k.half_uv); put2(k.cell_f0);
+        out[n++] = k.cell_rf; out[n++] = k.cell_kc; out[n++] = k.cell_hg0;
+        put2(k.mid_c); put2(k.half_c); put2(k.clamp_c);
+        out[n++] = (double)k.pix_k; out[n++] = (double)k.cell_k;
+    }
+    delete h;
+    return rc;
 }
 
 int smap_notify_map_modified(smap_handle* h) {
