@@ -222,3 +222,33 @@ def test_certification_holds_on_points_snapped_to_cell_and_range_borders():
     assert np.array_equal(pix[have].astype(np.int64), ref_pix[passed][have])
     assert np.array_equal(cell[have].astype(np.int64), ref_cell[passed][have])
     assert 0.05 < (~cert).mean() < 0.9   # the borders really are exercised: many points are NOT certified
+
+
+def test_velodyne_frame_cloud_without_transform():
+    """pcd_frame_id == "velodyne": no world -> velodyne transform, re-centring point at the origin."""
+    cam = camera_setup_1()
+    boundary, res, mh, mw, hw = [[1360, 1500], [500, 630]], 0.5, 280, 260, (1440, 1920)
+    fr = syn.synthetic_frame(77, 1, 200000)
+    T = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
+    pcd = fr["pcd"].copy()
+    pcd[0:3] = (T @ np.vstack((pcd[0:3], np.ones((1, pcd.shape[1])))))[0:3].astype(F)
+    pts = np.ascontiguousarray(pcd.T.astype(F))
+    k = fast32(dict(map_height=mh, map_width=mw, num_classes=5, use_intensity=1, lane_index=2, device=0,
+                    boundary_x_min=float(boundary[0][0]), boundary_y_min=float(boundary[1][0]), resolution=res,
+                    origin_offset_x=OFF[0], origin_offset_y=OFF[1], range_max=100.0), None, cam.P, hw)
+    assert k["coord_l"] > 0 and np.all(k["n_ctr"] == 0)
+    _, _, uv, keep = c_oracle.project_pcd(pcd, None, cam.P, fr["semantic_image"], 100.0)
+    gx = ((pcd[0] + OFF[0]) - boundary[0][0]) / res
+    gy = ((pcd[1] + OFF[1]) - boundary[1][0]) / res
+    on_grid = (gx > -1) & (gx < mh) & (gy > -1) & (gy < mw)
+    ref_cell = np.trunc(gx).astype(np.int64) * mw + np.trunc(gy).astype(np.int64)
+    ref_pix = np.zeros(pcd.shape[1], np.int64)
+    ref_pix[keep] = uv[1].astype(np.int64) * hw[1] + uv[0].astype(np.int64)
+    passed = cull32(k, pts)
+    assert not np.any(keep & ~passed)
+    cert, inside, pix, cell = decide32(k, pts[passed], hw[1], mw)
+    have = cert & inside
+    assert np.array_equal(have[cert], (keep & on_grid)[passed][cert])
+    assert np.array_equal(pix[have].astype(np.int64), ref_pix[passed][have])
+    assert np.array_equal(cell[have].astype(np.int64), ref_cell[passed][have])
+    assert cert.mean() > 0.9
