@@ -508,7 +508,7 @@ int fuse_grid(const smap_handle* h, FuseFrame* f, int n, int div, int64_t* gx_ou
     const int64_t rounds = ceil_div(n_max, kFBlockRoundPts);
     if (gx > rounds) gx = rounds;
     for (int k = 0; k < n; ++k) {
-        const int64_t per = ceil_div(f[k].n, gx * kWarps);
+        const int64_t per = ceil_div(f[k].n, gx * kFWarps);
         if (per >= ((int64_t)1 << 31)) return fail(SMAP_ERR_INVALID, "cloud too large for one launch");
         f[k].per_warp = (int32_t)per;
     }
@@ -564,9 +564,9 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         fb->n_frames = in_launch;
         fb->tag_planes = h->n_tag_planes > 0 ? h->n_tag_planes : 1;
         FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + first_slot;
-        if (mode == 1) k_fuse<1, kMaxBatch><<<(unsigned)gx, kThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
-        else if (mode == 2) k_fuse<2, kMaxBatch><<<(unsigned)gx, kThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
-        else k_fuse<0, kMaxBatch><<<(unsigned)gx, kThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
+        if (mode == 1) k_fuse<1, kMaxBatch><<<(unsigned)gx, kFThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
+        else if (mode == 2) k_fuse<2, kMaxBatch><<<(unsigned)gx, kFThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
+        else k_fuse<0, kMaxBatch><<<(unsigned)gx, kFThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
         CK(cudaGetLastError());
         h->stats.kernel_launches += 1;
     }
@@ -604,9 +604,9 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         fb->n_frames = 1;
         fb->tag_planes = 1;
         FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + used;
-        if (mode == 1) k_fuse<1, 1><<<(unsigned)gx, kThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
-        else if (mode == 2) k_fuse<2, 1><<<(unsigned)gx, kThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
-        else k_fuse<0, 1><<<(unsigned)gx, kThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+        if (mode == 1) k_fuse<1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+        else if (mode == 2) k_fuse<2, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+        else k_fuse<0, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
         CK(cudaGetLastError());
         h->stats.kernel_launches += 1;
         ++used;

@@ -70,7 +70,7 @@ struct FuseFrame {
     const uint8_t* image;
     uint32_t* mask;        // MODE 0: this frame's mask slot
     int64_t n;
-    int32_t per_warp;      // points per warp: ceil(n / (gridDim.x * kWarps)), computed by the host
+    int32_t per_warp;      // points per warp: ceil(n / (gridDim.x * kFWarps)), computed by the host
     int32_t img64;         // label image readable with aligned 8-byte loads (base aligned, size a multiple of 8)
 };
 
@@ -98,12 +98,17 @@ constexpr int kFidShift = 28;   // a record's pixel index carries the frame inde
 #ifndef SMAP_FUSE_ROUND
 #define SMAP_FUSE_ROUND 2
 #endif
-#ifndef SMAP_FUSE_MINB
-#define SMAP_FUSE_MINB 4
+#ifndef SMAP_FUSE_THREADS
+#define SMAP_FUSE_THREADS 256   // threads per k_fuse block
 #endif
+#ifndef SMAP_FUSE_MINB
+#define SMAP_FUSE_MINB (1024 / SMAP_FUSE_THREADS)   // resident blocks per SM: 32 warps, 64 registers per thread
+#endif
+constexpr int kFThreads = SMAP_FUSE_THREADS;
+constexpr int kFWarps = kFThreads / 32;
 constexpr int kFRound = SMAP_FUSE_ROUND;
 constexpr int kFRoundPts = 32 * kFRound;
-constexpr int kFBlockRoundPts = kWarps * kFRoundPts;
+constexpr int kFBlockRoundPts = kFWarps * kFRoundPts;
 #ifndef SMAP_FUSE_GROUP
 #define SMAP_FUSE_GROUP SMAP_FUSE_ROUND   // chunks culled back to back (unrolled) before the survivor stack is looked at
 #endif
@@ -205,7 +210,7 @@ __host__ __device__ constexpr int fuse_warp_smem(int nf) {
     return (kFStages * kFRoundPts + kFQueueCap + kFDeferCap) * 16 + kFRecCap * 8 + (nf > 1 ? kFDeferCap : 0) +
            (kFStages * 8 + 15) / 16 * 16;
 }
-__host__ __device__ constexpr int fuse_block_smem(int nf) { return kWarps * fuse_warp_smem(nf) + 2 * 256 * 4; }
+__host__ __device__ constexpr int fuse_block_smem(int nf) { return kFWarps * fuse_warp_smem(nf) + 2 * 256 * 4; }
 
 // ------------------------------------------------------------------------------------------------
 // MODE 0: masks only (RED.OR into the frame's slot, bounding box) -- k_apply replays the frames in order.
@@ -237,7 +242,7 @@ __host__ __device__ constexpr int fuse_block_smem(int nf) { return kWarps * fuse
 //             operation on one scoreboard and waits for it at the loop head, which serialised everything.)
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int NF>
-__global__ void __launch_bounds__(kThreads, SMAP_FUSE_MINB)
+__global__ void __launch_bounds__(kFThreads, SMAP_FUSE_MINB)
 k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridParams gp, FrameBox* __restrict__ boxes,
        double* __restrict__ map) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -255,11 +260,11 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
     uint8_t* const defer_f = reinterpret_cast<uint8_t*>(recs + kFRecCap);   // NF > 1 only
     uint64_t* const bars = reinterpret_cast<uint64_t*>(defer_f + (NF > 1 ? kFDeferCap : 0));
     (void)bars;
-    uint32_t* const s_tab_r = reinterpret_cast<uint32_t*>(s_dyn + (size_t)kWarps * kFWarpSmem);
+    uint32_t* const s_tab_r = reinterpret_cast<uint32_t*>(s_dyn + (size_t)kFWarps * kFWarpSmem);
     uint32_t* const s_tab_g = s_tab_r + 256;
 
     const int nf = (NF == 1) ? 1 : B.n_frames;   // NF == 1: every B.f[f] below is B.f[0], a fixed constant-bank offset
-    const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;   // this warp's index in the grid
+    const int64_t gw = (int64_t)blockIdx.x * kFWarps + warp;   // this warp's index in the grid
     // this warp's slice of frame f: [gw * per_warp, ...) clipped to the cloud
     auto slice_pts = [&](int f) -> int {
         const int64_t left = B.f[f].n - gw * B.f[f].per_warp;
