@@ -252,3 +252,49 @@ def test_velodyne_frame_cloud_without_transform():
     assert np.array_equal(pix[have].astype(np.int64), ref_pix[passed][have])
     assert np.array_equal(cell[have].astype(np.int64), ref_cell[passed][have])
     assert cert.mean() > 0.9
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_certification_holds_for_random_poses_grids_and_cameras(seed):
+    """Random vehicle positions (up to tens of kilometres from the origin, where float32 world coordinates are
+    centimetre-coarse), headings, small roll / pitch, grid resolutions and origins, both cameras: the cull stays
+    conservative and every certified float32 decision equals the reference's."""
+    from vision_semantic_segmentation_b200.synthetic import Pose
+    import math
+    rng = np.random.default_rng(1000 + seed)
+    cam = (camera_setup_1, camera_setup_6)[seed % 2]()
+    scale = (50.0, 2000.0, 60000.0)[seed % 3]
+    px, py = rng.uniform(-scale, scale, 2)
+    yaw, pitch, roll = rng.uniform(-math.pi, math.pi), rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05)
+    cy, sy, cp, sp, cr, sr = math.cos(yaw / 2), math.sin(yaw / 2), math.cos(pitch / 2), math.sin(pitch / 2), math.cos(roll / 2), math.sin(roll / 2)
+    quat = (sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy)
+    pose = Pose((px, py, rng.uniform(-2, 2)), quat)
+    res = float(rng.choice([0.05, 0.1, 0.2, 0.5, 1.0]))
+    mh, mw = int(rng.integers(200, 3000)), int(rng.integers(200, 3000))
+    # grid placed so that the vehicle is somewhere inside it (map coordinate = world + offset - boundary_min)
+    bx = px + OFF[0] - rng.uniform(0.1, 0.9) * mh * res
+    by = py + OFF[1] - rng.uniform(0.1, 0.9) * mw * res
+    hw = (1440, 1920)
+    fr = syn.synthetic_frame(500 + seed, 0, 120000, pose=pose)
+    T = np.linalg.inv(tr.get_transform_from_pose(pose) @ syn.velodyne_to_baselink())
+    k = fast32(dict(map_height=mh, map_width=mw, num_classes=5, use_intensity=1, lane_index=2, device=0,
+                    boundary_x_min=float(bx), boundary_y_min=float(by), resolution=res, origin_offset_x=OFF[0],
+                    origin_offset_y=OFF[1], range_max=100.0), T, cam.P, hw)
+    assert k["coord_l"] > 0
+    pts, pcd = fr["points"], fr["pcd"]
+    _, _, uv, keep = c_oracle.project_pcd(pcd, T, cam.P, fr["semantic_image"], 100.0)
+    gx = ((pcd[0] + OFF[0]) - bx) / res
+    gy = ((pcd[1] + OFF[1]) - by) / res
+    on_grid = (gx > -1) & (gx < mh) & (gy > -1) & (gy < mw)
+    ref_cell = np.trunc(gx).astype(np.int64) * mw + np.trunc(gy).astype(np.int64)
+    ref_pix = np.zeros(pcd.shape[1], np.int64)
+    ref_pix[keep] = uv[1].astype(np.int64) * hw[1] + uv[0].astype(np.int64)
+    passed = cull32(k, pts)
+    assert not np.any(keep & ~passed), "the cull dropped a point the reference keeps"
+    cert, inside, pix, cell = decide32(k, pts[passed], hw[1], mw)
+    have = cert & inside
+    assert np.array_equal(have[cert], (keep & on_grid)[passed][cert]), "a certified decision differs from the reference"
+    assert np.array_equal(pix[have].astype(np.int64), ref_pix[passed][have])
+    assert np.array_equal(cell[have].astype(np.int64), ref_cell[passed][have])
+    if keep.sum() > 1000:
+        assert cert[keep[passed]].mean() > 0.5, "the float32 path certifies too little to be useful (%.3f)" % cert[keep[passed]].mean()
