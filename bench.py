@@ -168,9 +168,9 @@ def make_ring(args, rank):
     frames = []
     for i in range(args.ring):
         f = rank * 100000 + i
-        fr = syn.synthetic_frame(SEED, f, args.points, blocky=(i % 2 == 1), as_float64=False)
+        fr = syn.synthetic_frame(SEED, f, args.points, blocky=(i % 2 == 1), as_float64=False, with_ids=True)
         T = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
-        frames.append((fr["points"], fr["semantic_image"], T))
+        frames.append((fr["points"], fr["semantic_image"], T, fr["semantic_ids"]))
     return frames
 
 
@@ -184,7 +184,7 @@ def cpu_frame_fn(args):
     cam, cm = camera_setup_1(), np.eye(len(labels))
     grid = np.zeros((MAP_H, MAP_W, len(labels)))
 
-    def run(points, image, T):
+    def run(points, image, T, ids=None):
         pcd = np.ascontiguousarray(points.T.astype(np.float64))
         masked, label, _, _ = numpy_port.project_pcd(pcd, T, cam.P, image, RANGE_MAX)
         numpy_port.update_map(grid, masked, label, colors, cm, BOUNDARY, RESOLUTION, True, names)
@@ -214,7 +214,7 @@ def run_reference(args):
     budget = 150.0
     frac = min(1.0, budget / max(t_frame * (args.steps + args.warmup), 1e-9))
     n_sub = max(1000, int(args.points * frac))
-    sample = [(p[:n_sub], im, T) for p, im, T in ring]
+    sample = [(p[:n_sub], im, T) for p, im, T, _ in ring]
     for i in range(args.warmup):
         run(*sample[i % len(sample)])
     t0 = time.perf_counter()
@@ -278,7 +278,7 @@ def run_b200(args):
 
     ring_host = make_ring(args, rank)
     ring_dev, ring_pinned = [], []
-    for pts, img, T in ring_host:
+    for pts, img, T, _ in ring_host:
         dp, di = torch.from_numpy(pts).to(dev), torch.from_numpy(img).to(dev)
         ring_dev.append((dm.make_frame(dp, di, T, 0), dp, di))
     torch.cuda.synchronize()
@@ -365,17 +365,21 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         dm.clear()
-        for pts, img, T in ring_host[: min(4, len(ring_host))]:
+        dm.set_label_palette(syn.COLORS_19)
+        ring_pinned_ids = []
+        for pts, img, T, ids in ring_host[: min(4, len(ring_host))]:
             hp, hi = torch.from_numpy(pts).pin_memory(), torch.from_numpy(img).pin_memory()
             ring_pinned.append((dm.make_frame(hp, hi, T, 0, host=True), hp, hi))
+            hd = torch.from_numpy(ids).pin_memory()
+            ring_pinned_ids.append((dm.make_frame(hp, hd, T, 0, host=True), hp, hd))
         h2d = ring_pinned[0][1].numel() * 4 + ring_pinned[0][2].numel()
         e2e_steps = min(args.steps, 50)
         result = torch.zeros(1, dtype=torch.float64, device=dev)
         host_result = torch.zeros(1, dtype=torch.float64).pin_memory()
 
-        def e2e_loop(steps):
+        def e2e_loop(steps, ring=ring_pinned):
             for i in range(steps):
-                dm.integrate_host(ring_pinned[i % len(ring_pinned)][0])
+                dm.integrate_host(ring[i % len(ring)][0])
                 # the step's "metric": evidence mass in the grid cell under the vehicle's first hit (8 bytes)
                 host_result.copy_(dm.map.view(-1)[:1], non_blocking=False)
         e2e_loop(2)
@@ -390,6 +394,26 @@ def run_b200(args):
         e2e = {"value": world * e2e_steps * n_pts / float(tt.item()), "unit": "points/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8, "steps": e2e_steps,
                "note": "smap_integrate_host: pinned host cloud (float32 x,y,z,i) + RGB label image copied per step"}
+        # the same loop fed with the network's class-id plane instead of the painted RGB image (SMAP_IMG_CLASS_IDS:
+        # 1 byte per pixel over PCIe, same grid bit for bit -- tests/test_gpu_label_ids.py)
+        grid_rgb = dm.map.clone()
+        dm.clear()
+        e2e_loop(2, ring_pinned_ids)
+        barrier()
+        dm.clear()
+        e2e_loop(2, ring_pinned)   # same 2 warm-up frames as the RGB loop above saw before its timed region
+        t0 = time.perf_counter()
+        e2e_loop(e2e_steps, ring_pinned_ids)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e["class_ids"] = {"value": world * e2e_steps * n_pts / float(tt.item()), "unit": "points/s",
+                            "h2d_bytes_per_step": int(ring_pinned_ids[0][1].numel() * 4 + ring_pinned_ids[0][2].numel()),
+                            "d2h_bytes_per_step": 8, "steps": e2e_steps,
+                            "same_grid_as_rgb": bool(torch.equal(grid_rgb, dm.map)),
+                            "note": "label image handed over as the network's (1440, 1920) uint8 class-id plane"}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -414,7 +438,7 @@ def run_b200(args):
             "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_fuse<count> (TMA-staged cloud, float32 certified project+cull+lookup+update, one frame per launch)",
+                         "kernel": "k_fuse<count> (register-prefetched cloud, float32 certified project+cull+lookup+update, one frame per launch)",
                          "kernel_ms": kernel_ms, "apply_kernel_ms_per_frame": apply_ms,
                          "step_frac": bytes_per_frame / (ms / args.steps * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_frame": bytes_per_frame,

@@ -32,7 +32,7 @@ extern "C" {
 #define SMAP_API
 #endif
 
-#define SMAP_ABI_VERSION 1
+#define SMAP_ABI_VERSION 2
 #define SMAP_MAX_CLASSES 31 /* C class bits + 1 intensity-boost bit in a 32-bit cell mask */
 #define SMAP_MAX_CAMERAS 8
 
@@ -49,6 +49,19 @@ enum {
 enum {
     SMAP_PTS_F32X4 = 0,  /* N x {x, y, z, intensity} float32, 16-byte aligned (PointCloud2 / float4) */
     SMAP_PTS_F64_SOA = 1 /* (4, N) float64 rows x, y, z, intensity with row stride `ld` (the reference's pcd) */
+};
+
+/* what smap_frame.image_dev holds */
+enum {
+    SMAP_IMG_RGB = 0,      /* (H, W, 3) uint8 colour-coded label image: what the segmentation node publishes
+                            * (src/vision_semantic_segmentation_node.py:113-121) and project_pcd indexes */
+    SMAP_IMG_CLASS_IDS = 1 /* (h, w) uint8 class-id plane: the network's own output BEFORE the node's
+                            * cv2.resize(..., INTER_NEAREST) and apply_color_map
+                            * (src/vision_semantic_segmentation_node.py:109-113,
+                            * src/network/deeplab_v3_plus/data/utils/mapillary_visualization.py:70-89).
+                            * The fused kernel applies the same nearest-neighbour index map and the palette
+                            * (smap_set_label_palette) on the fly: same grid, bit for bit, as painting and
+                            * upscaling first; 1 byte per network pixel instead of 3 per camera pixel. */
 };
 
 typedef struct smap_handle smap_handle;
@@ -79,12 +92,15 @@ typedef struct smap_frame {
     int64_t ld;               /* row stride for SMAP_PTS_F64_SOA, ignored for F32X4 */
     int32_t layout;           /* SMAP_PTS_* */
     int32_t camera;           /* slot set with smap_set_camera */
-    const uint8_t *image_dev; /* (H, W, 3) uint8 RGB colour-coded label image */
-    int32_t image_width;
-    int32_t image_height;
+    const uint8_t *image_dev; /* label image, see image_format */
+    int32_t image_width;      /* W, H of the camera image the cloud is projected into (the frustum cull uses them); */
+    int32_t image_height;     /* for SMAP_IMG_RGB also the shape of image_dev */
     int32_t has_transform;    /* 0: cloud already in the velodyne frame (pcd_frame_id == "velodyne") */
-    int32_t reserved;
+    int32_t image_format;     /* SMAP_IMG_* (0 = RGB, the reference's format) */
     double world_to_velodyne[16]; /* row-major 4x4 = inv(T_base_to_origin(pose) @ T_velodyne_to_baselink) */
+    int32_t ids_width;        /* SMAP_IMG_CLASS_IDS: shape (ids_height, ids_width) of the class-id plane; 0 = W, H. */
+    int32_t ids_height;       /* Pixel (u, v) reads ids[min(floor(v * fy), h - 1), min(floor(u * fx), w - 1)] with
+                               * fx = 1.0 / ((double)W / w): cv2.resize's INTER_NEAREST index map, in double as OpenCV */
 } smap_frame;
 
 /* counters of the most recent frame(s); see smap_get_stats */
@@ -119,6 +135,14 @@ SMAP_API int smap_set_camera(smap_handle *h, int camera, const double P_host[12]
  * Column i is added to a cell when class i is observed there (src/mapping_replay.py:281). */
 SMAP_API int smap_set_classes(smap_handle *h, const uint8_t *colors_host, const double *cm_host);
 
+/* Palette of the segmentation network: colour of class id i = rgb[3 i .. 3 i + 2], n_ids <= 256 (the "labels" of the
+ * dataset config, src/network/deeplab_v3_plus/data/utils/mapillary_visualization.py:70-89).  Needed before a frame
+ * with image_format == SMAP_IMG_CLASS_IDS is integrated.  Ids >= n_ids are painted black, as apply_color_map leaves
+ * them (its canvas is np.zeros), so they match the classes whose colour has R == G == 0.  The handle folds palette and
+ * cfg.LABEL_COLORS into a 256-entry id -> class-bit table that reproduces the reference's R,G-only colour compare
+ * (src/mapping_replay.py:276), collisions included.  Synchronises (small upload). */
+SMAP_API int smap_set_label_palette(smap_handle *h, const uint8_t *rgb_host, int n_ids);
+
 /* ---- parity API: SemanticMapping.project_pcd (src/mapping_replay.py:214-246) -------------------
  * Transform, project, cull (range + frustum), stable compaction, label gather.
  * Outputs have room for n points with row stride out_ld (>= n):
@@ -150,7 +174,9 @@ SMAP_API int smap_update(smap_handle *h, double *map_dev, const double *pcd_dev,
  * handle then allocates 4 x cells x (C + 1) uint32 on first use) or with the per-frame cell masks (more classes).
  * smap_upload / smap_notify_map_modified switch back to the ordered update.
  * float4 clouds take the fast kernel (float32 decisions with rigorous error bounds, float64 only for the few
- * points they cannot decide); label images of 2^28 pixels or more are rejected there. */
+ * points they cannot decide); label images of 2^28 pixels or more are rejected there.
+ * Class-id planes (SMAP_IMG_CLASS_IDS) are accepted by the smap_integrate* calls for float4 clouds; smap_project
+ * returns RGB labels and therefore takes RGB images only. */
 SMAP_API int smap_integrate(smap_handle *h, const smap_frame *frame, void *stream);
 
 /* Same rule for n_frames frames IN ORDER.  Up to 16 frames are queued together (one fused launch per frame on
@@ -200,6 +226,11 @@ SMAP_API int smap_debug_set_frame_tag(smap_handle *h, uint32_t value);
  * configuration, a frame description (pointers ignored) and a camera matrix.  tests/test_fast32_bounds.py emulates
  * the kernel's float32 arithmetic with them on the CPU and checks every certified decision against the oracle. */
 SMAP_API int smap_debug_fast32(const smap_config *cfg, const smap_frame *frame, const double P_host[12], double *out69);
+
+/* Test hook, host only (no device needed): the nearest-neighbour index map of one image axis (dst entries into
+ * tab_out) as the library tabulates it for SMAP_IMG_CLASS_IDS frames, and the multiply-shift it hands to the kernel
+ * when one reproduces the whole table, (x * *mul) >> *shift; *shift == 0: none, the kernel reads the table. */
+SMAP_API int smap_debug_nearest_map(int dst, int src, uint16_t *tab_out, uint32_t *mul, uint32_t *shift);
 
 #ifdef __cplusplus
 }

@@ -274,3 +274,36 @@ def load_reference():
     )
     _loaded = ns
     return ns
+
+
+def load_reference_color_map():
+    """The reference's label-image producer functions, unmodified:
+    ``apply_color_map`` and ``get_labels`` of
+    ``src/network/deeplab_v3_plus/data/utils/mapillary_visualization.py`` (the dataset class and matplotlib that the
+    module imports at the top are inert placeholders: neither function touches them)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REF)
+    import importlib.util
+    stubs = {
+        'deeplab_v3_plus': _inert_module('deeplab_v3_plus'),
+        'deeplab_v3_plus.data': _inert_module('deeplab_v3_plus.data'),
+        'deeplab_v3_plus.data.dataset': _inert_module('deeplab_v3_plus.data.dataset'),
+        'deeplab_v3_plus.data.dataset.mapillary': _inert_module('deeplab_v3_plus.data.dataset.mapillary',
+                                                               MapillaryVistas=_Anything),
+        'matplotlib': _inert_module('matplotlib'),
+        'matplotlib.pyplot': _inert_module('matplotlib.pyplot'),
+    }
+    added = [name for name in stubs if name not in sys.modules]
+    for name in added:
+        sys.modules[name] = stubs[name]
+    try:
+        path = os.path.join(REF, 'src', 'network', 'deeplab_v3_plus', 'data', 'utils', 'mapillary_visualization.py')
+        spec = importlib.util.spec_from_file_location('_ref_mapillary_visualization', path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for name in added:
+            if name.startswith('deeplab_v3_plus'):
+                sys.modules.pop(name, None)
+    return types.SimpleNamespace(apply_color_map=mod.apply_color_map, get_labels=mod.get_labels,
+                                 config_19=os.path.join(REF, 'config', 'config_19.json'))

@@ -10,16 +10,20 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMAP_LIB_PATH") or os.path.join(_HERE, "csrc", "libsmap_b200.so")  # env: kernel-variant sweeps
 
+ABI_VERSION = 2   # SMAP_ABI_VERSION of include/smap.h this binding was written against
 SMAP_PTS_F32X4 = 0
 SMAP_PTS_F64_SOA = 1
+SMAP_IMG_RGB = 0
+SMAP_IMG_CLASS_IDS = 1
 SMAP_MAX_CLASSES = 31
 SMAP_MAX_CAMERAS = 8
 
 EXPORTS = [
     "smap_abi_version", "smap_last_error", "smap_device_count", "smap_device_info", "smap_create",
-    "smap_destroy", "smap_set_camera", "smap_set_classes", "smap_project", "smap_update", "smap_integrate",
+    "smap_destroy", "smap_set_camera", "smap_set_classes", "smap_set_label_palette", "smap_project", "smap_update", "smap_integrate",
     "smap_integrate_batch", "smap_integrate_host", "smap_apply_filter", "smap_render", "smap_filter_render",
     "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_notify_map_modified", "smap_download", "smap_upload", "smap_get_stats", "smap_set_profiling", "smap_debug_set_frame_tag", "smap_debug_fast32",
+    "smap_debug_nearest_map",
 ]
 
 
@@ -38,7 +42,8 @@ class SmapFrame(ctypes.Structure):
         ("points_dev", ctypes.c_void_p), ("n_points", ctypes.c_int64), ("ld", ctypes.c_int64),
         ("layout", ctypes.c_int32), ("camera", ctypes.c_int32), ("image_dev", ctypes.c_void_p),
         ("image_width", ctypes.c_int32), ("image_height", ctypes.c_int32), ("has_transform", ctypes.c_int32),
-        ("reserved", ctypes.c_int32), ("world_to_velodyne", ctypes.c_double * 16),
+        ("image_format", ctypes.c_int32), ("world_to_velodyne", ctypes.c_double * 16),
+        ("ids_width", ctypes.c_int32), ("ids_height", ctypes.c_int32),
     ]
 
 
@@ -67,6 +72,10 @@ def load():
             "CUDA extension %s not found; build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "or `make -C vision_semantic_segmentation_b200/csrc`. There is no CPU fallback." % LIB_PATH)
     L = ctypes.CDLL(LIB_PATH)
+    L.smap_abi_version.restype = ctypes.c_int
+    if L.smap_abi_version() != ABI_VERSION:
+        raise RuntimeError("%s has C-ABI version %d, this package binds version %d: rebuild it (no CPU fallback)"
+                           % (LIB_PATH, L.smap_abi_version(), ABI_VERSION))
     vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
     L.smap_abi_version.restype = i32
     L.smap_abi_version.argtypes = []
@@ -84,6 +93,8 @@ def load():
     L.smap_set_camera.argtypes = [vp, i32, ctypes.POINTER(dbl)]
     L.smap_set_classes.restype = i32
     L.smap_set_classes.argtypes = [vp, vp, vp]
+    L.smap_set_label_palette.restype = i32
+    L.smap_set_label_palette.argtypes = [vp, vp, i32]
     L.smap_project.restype = i32
     L.smap_project.argtypes = [vp, ctypes.POINTER(SmapFrame), vp, vp, vp, vp, i64, ctypes.POINTER(i64), vp]
     L.smap_update.restype = i32
@@ -115,6 +126,8 @@ def load():
     L.smap_debug_fast32.restype = i32
     L.smap_debug_fast32.argtypes = [ctypes.POINTER(SmapConfig), ctypes.POINTER(SmapFrame), ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double)]
+    L.smap_debug_nearest_map.restype = i32
+    L.smap_debug_nearest_map.argtypes = [i32, i32, vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
     L.smap_download.restype = i32
     L.smap_download.argtypes = [vp, vp]
     L.smap_upload.restype = i32

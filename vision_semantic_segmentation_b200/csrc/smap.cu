@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/smap.h"
 #include "smap_kernels.cuh"
@@ -98,6 +99,18 @@ struct smap_handle {
     bool classes_set = false;
     double P[SMAP_MAX_CAMERAS][12];
     bool cam_set[SMAP_MAX_CAMERAS] = {};
+    // class-id planes (SMAP_IMG_CLASS_IDS): the network's palette, the id -> class-bit table folded from it and
+    // cfg.LABEL_COLORS, and the most recent nearest-neighbour index map (see FuseFrame in smap_fuse.cuh)
+    uint8_t palette[256 * 3] = {};
+    bool palette_set = false;
+    uint32_t* id_lut_dev = nullptr;
+    struct NearestMap {
+        int W = 0, H = 0, w = 0, h = 0;   // key
+        uint32_t mx = 0, my = 0, sx = 0, sy = 0;
+        bool use_tab = false;
+        uint16_t* tab_dev = nullptr;      // W + H entries, only when no multiply-shift reproduces the map
+        size_t tab_cap = 0;
+    } nn;
     // project_pcd scratch
     uint8_t* keep = nullptr;
     int32_t* iu = nullptr;
@@ -134,6 +147,12 @@ int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp
     if (f->layout != SMAP_PTS_F32X4 && f->layout != SMAP_PTS_F64_SOA) return fail(SMAP_ERR_INVALID, "unknown point layout");
     if (f->layout == SMAP_PTS_F64_SOA && f->ld < f->n_points) return fail(SMAP_ERR_INVALID, "ld < n_points");
     if (f->image_width <= 0 || f->image_height <= 0) return fail(SMAP_ERR_INVALID, "empty label image");
+    if (f->image_format != SMAP_IMG_RGB && f->image_format != SMAP_IMG_CLASS_IDS) return fail(SMAP_ERR_INVALID, "unknown image format");
+    if (f->image_format == SMAP_IMG_CLASS_IDS) {
+        if (f->layout != SMAP_PTS_F32X4) return fail(SMAP_ERR_INVALID, "class-id planes need the float4 cloud layout");
+        if (f->ids_width < 0 || f->ids_height < 0 || f->ids_width > 65535 || f->ids_height > 65535)
+            return fail(SMAP_ERR_INVALID, "bad class-id plane shape");
+    }
     if (f->image_width > 65535 || f->image_height > 32767) return fail(SMAP_ERR_INVALID, "label image larger than 65535 x 32767");
     if (f->layout == SMAP_PTS_F64_SOA && f->n_points >= ((int64_t)1 << 32)) return fail(SMAP_ERR_INVALID, "more than 2^32 points in a float64 cloud");
     if (f->n_points > 0 && (!f->points_dev || !f->image_dev)) return fail(SMAP_ERR_INVALID, "NULL points / image");
@@ -484,10 +503,96 @@ int ensure_tags(smap_handle* h, int want) {
     return SMAP_OK;
 }
 
+// id -> class bits: bit i set when the palette colour of the id matches cfg.LABEL_COLORS[i] in R and G
+// (src/mapping_replay.py:276 compares only those two channels); ids beyond the palette are black, as
+// apply_color_map's np.zeros canvas leaves them (mapillary_visualization.py:80-87).
+int upload_id_lut(smap_handle* h) {
+    if (!h->palette_set || !h->classes_set) return SMAP_OK;
+    uint32_t lut[256];
+    for (int id = 0; id < 256; ++id) {
+        uint32_t bits = 0;
+        for (int i = 0; i < h->cfg.num_classes; ++i)
+            if (h->palette[3 * id] == h->colors[3 * i] && h->palette[3 * id + 1] == h->colors[3 * i + 1]) bits |= 1u << i;
+        lut[id] = bits;
+    }
+    if (!h->id_lut_dev) CK(cudaMalloc(&h->id_lut_dev, sizeof lut));
+    CK(cudaDeviceSynchronize());  // a previous frame may still be reading the table
+    CK(cudaMemcpy(h->id_lut_dev, lut, sizeof lut, cudaMemcpyHostToDevice));
+    return SMAP_OK;
+}
+
+// cv2.resize(..., INTER_NEAREST) index map of one axis, in double as OpenCV computes it:
+// x_ofs[x] = min(cvFloor(x * ifx), src - 1), ifx = 1. / ((double)dst / src).
+void nearest_table(int dst, int src, uint16_t* out) {
+    const double inv_scale = (double)dst / (double)src;
+    const double ifx = 1.0 / inv_scale;
+    for (int x = 0; x < dst; ++x) {
+        int sx = (int)floor((double)x * ifx);
+        out[x] = (uint16_t)(sx < src - 1 ? sx : src - 1);
+    }
+}
+
+// (m, s) with (x * m) >> s == tab[x] for every x < dst in 32-bit arithmetic, if there is one
+bool nearest_mulshift(int dst, int src, const uint16_t* tab, uint32_t* m_out, uint32_t* s_out) {
+    int bits = 1;
+    while (((int64_t)1 << bits) < dst) ++bits;          // x < 2^bits
+    for (int s = 31 - bits; s >= 1; --s) {               // m <= 2^s (src <= dst) keeps x * m below 2^32
+        const uint64_t base = ((uint64_t)src << s) / (uint64_t)dst;
+        for (uint64_t m = base; m <= base + 1; ++m) {
+            if (m == 0 || (uint64_t)(dst - 1) * m >= ((uint64_t)1 << 32)) continue;
+            bool ok = true;
+            for (int x = 0; x < dst && ok; ++x) ok = (uint32_t)(((uint64_t)x * m) >> s) == tab[x];
+            if (ok) { *m_out = (uint32_t)m; *s_out = (uint32_t)s; return true; }
+        }
+    }
+    return false;
+}
+
+int ensure_nearest_map(smap_handle* h, int W, int H, int w, int hh) {
+    smap_handle::NearestMap& nn = h->nn;
+    if (nn.W == W && nn.H == H && nn.w == w && nn.h == hh) return SMAP_OK;
+    std::vector<uint16_t> tab((size_t)W + (size_t)H);
+    nearest_table(W, w, tab.data());
+    nearest_table(H, hh, tab.data() + W);
+    const bool ms = w <= W && hh <= H && nearest_mulshift(W, w, tab.data(), &nn.mx, &nn.sx) &&
+                    nearest_mulshift(H, hh, tab.data() + W, &nn.my, &nn.sy);
+    if (!ms) {
+        // frames still in flight may be reading the previous table
+        CK(cudaDeviceSynchronize());
+        if (tab.size() > nn.tab_cap) {
+            cudaFree(nn.tab_dev);
+            nn.tab_dev = nullptr; nn.tab_cap = 0;
+            CK(cudaMalloc(&nn.tab_dev, tab.size() * sizeof(uint16_t)));
+            nn.tab_cap = tab.size();
+        }
+        CK(cudaMemcpy(nn.tab_dev, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    nn.use_tab = !ms;
+    nn.W = W; nn.H = H; nn.w = w; nn.h = hh;
+    return SMAP_OK;
+}
+
+inline int ids_w(const smap_frame* f) { return f->ids_width > 0 ? f->ids_width : f->image_width; }
+inline int ids_h(const smap_frame* f) { return f->ids_height > 0 ? f->ids_height : f->image_height; }
+
 int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp, int mode, int slot, FuseFrame& f) {
     if (fr->layout != SMAP_PTS_F32X4) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
     if ((int64_t)fr->image_width * fr->image_height >= ((int64_t)1 << kFidShift))
         return fail(SMAP_ERR_INVALID, "label image has 2^28 pixels or more");
+    f.nn_tab = nullptr;
+    f.nn_mx = f.nn_my = f.nn_sx = f.nn_sy = 0;
+    f.src_w = fr->image_width;
+    f.pad_f = 0;
+    if (fr->image_format == SMAP_IMG_CLASS_IDS) {
+        if (!h->palette_set) return fail(SMAP_ERR_STATE, "class-id plane without a palette (smap_set_label_palette)");
+        if ((int64_t)ids_w(fr) * ids_h(fr) >= ((int64_t)1 << kFidShift))
+            return fail(SMAP_ERR_INVALID, "class-id plane has 2^28 pixels or more");
+        int rc = ensure_nearest_map(h, fr->image_width, fr->image_height, ids_w(fr), ids_h(fr));
+        if (rc) return rc;
+        f.nn_tab = h->nn.use_tab ? h->nn.tab_dev : nullptr;
+        f.nn_mx = h->nn.mx; f.nn_my = h->nn.my; f.nn_sx = h->nn.sx; f.nn_sy = h->nn.sy;
+        f.src_w = ids_w(fr);
+    }
     f.fp = fp;
     fill_fast32(h, fr, fp, f.fk);
     f.pts = static_cast<const float4*>(fr->points_dev);
@@ -537,6 +642,9 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         CK(cudaFuncSetAttribute(k_fuse<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
         CK(cudaFuncSetAttribute(k_fuse<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
         CK(cudaFuncSetAttribute(k_fuse<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
+        CK(cudaFuncSetAttribute(k_fuse<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
+        CK(cudaFuncSetAttribute(k_fuse<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
+        CK(cudaFuncSetAttribute(k_fuse<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
         CK(cudaFuncSetAttribute(k_fuse<2, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
         CK(cudaFuncSetAttribute(k_fuse<0, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
         CK(cudaFuncSetAttribute(k_fuse<1, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
@@ -551,6 +659,7 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         const int first_slot = used;
         for (; i < n_frames && in_launch < per_launch; ++i) {
             if (frames[i].n_points == 0) continue;
+            if (frames[i].image_format != SMAP_IMG_RGB) return fail(SMAP_ERR_INVALID, "class-id planes: not in the persistent-launch build");
             int rc = fill_fuse_frame(h, frames + i, fps[i], mode, used, fb->f[in_launch]);
             if (rc) return rc;
             ++in_launch;
@@ -561,6 +670,7 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         int rc = fuse_grid(h, fb->f, in_launch, 1, &gx);
         if (rc) return rc;
         fb->tags = count_atomics ? h->tags : nullptr;
+        fb->id_lut = nullptr;
         fb->n_frames = in_launch;
         fb->tag_planes = h->n_tag_planes > 0 ? h->n_tag_planes : 1;
         FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + first_slot;
@@ -604,7 +714,13 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         fb->n_frames = 1;
         fb->tag_planes = 1;
         FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + used;
-        if (mode == 1) k_fuse<1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+        fb->id_lut = h->id_lut_dev;
+        if (frames[i].image_format == SMAP_IMG_CLASS_IDS) {
+            if (mode == 1) k_fuse<1, 1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+            else if (mode == 2) k_fuse<2, 1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+            else k_fuse<0, 1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
+        }
+        else if (mode == 1) k_fuse<1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
         else if (mode == 2) k_fuse<2, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
         else k_fuse<0, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
         CK(cudaGetLastError());
@@ -767,6 +883,7 @@ int smap_destroy(smap_handle* h) {
     harvest_profile(h);
     if (h->own_map) cudaFree(h->map);
     cudaFree(h->mask); cudaFree(h->tags); cudaFree(h->boxes); cudaFree(h->touched); cudaFree(h->cm_dev); cudaFree(h->total_dev);
+    cudaFree(h->id_lut_dev); cudaFree(h->nn.tab_dev);
     cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
     if (h->ev_fork) {
         cudaEventDestroy(h->ev_fork);
@@ -809,7 +926,17 @@ int smap_set_classes(smap_handle* h, const uint8_t* colors_host, const double* c
         for (int j = 0; j < c; ++j)
             if (cm_host[i * c + j] != (i == j ? 1.0 : 0.0)) h->identity_cm = false;
     h->classes_set = true;
-    return SMAP_OK;
+    return upload_id_lut(h);
+}
+
+int smap_set_label_palette(smap_handle* h, const uint8_t* rgb_host, int n_ids) {
+    if (!h || (n_ids > 0 && !rgb_host)) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (n_ids < 0 || n_ids > 256) return fail(SMAP_ERR_INVALID, "a palette has between 0 and 256 colours");
+    DeviceGuard guard(h->cfg.device);
+    memset(h->palette, 0, sizeof h->palette);
+    if (n_ids > 0) memcpy(h->palette, rgb_host, (size_t)n_ids * 3);
+    h->palette_set = true;
+    return upload_id_lut(h);
 }
 
 int smap_project(smap_handle* h, const smap_frame* frame, double* out_pcd, uint8_t* out_label, int32_t* out_uv,
@@ -819,6 +946,7 @@ int smap_project(smap_handle* h, const smap_frame* frame, double* out_pcd, uint8
     FrameParams fp;
     int rc = fill_frame_params(h, frame, fp);
     if (rc) return rc;
+    if (frame->image_format != SMAP_IMG_RGB) return fail(SMAP_ERR_INVALID, "smap_project returns RGB labels: it takes RGB label images only");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t n = frame->n_points;
     *m_host = 0;
@@ -929,7 +1057,8 @@ int smap_integrate_host(smap_handle* h, const smap_frame* f, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (f->n_points < 0 || f->image_width <= 0 || f->image_height <= 0) return fail(SMAP_ERR_INVALID, "bad frame sizes");
     const size_t pts_bytes = f->layout == SMAP_PTS_F32X4 ? (size_t)f->n_points * 16 : (size_t)f->ld * 4 * sizeof(double);
-    const size_t img_bytes = (size_t)f->image_width * f->image_height * 3;
+    const size_t img_bytes = f->image_format == SMAP_IMG_CLASS_IDS ? (size_t)ids_w(f) * (size_t)ids_h(f)
+                                                                   : (size_t)f->image_width * f->image_height * 3;
     const int s = h->stage_next;
     h->stage_next = (s + 1) % smap_handle::kStages;
     if (!h->stage_done[s]) CK(cudaEventCreateWithFlags(&h->stage_done[s], cudaEventDisableTiming));
@@ -1084,6 +1213,15 @@ int smap_debug_fast32(const smap_config* cfg, const smap_frame* frame, const dou
     }
     delete h;
     return rc;
+}
+
+int smap_debug_nearest_map(int dst, int src, uint16_t* tab_out, uint32_t* mul, uint32_t* shift) {
+    if (!tab_out || !mul || !shift) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (dst <= 0 || src <= 0 || dst > 65535 || src > 65535) return fail(SMAP_ERR_INVALID, "sizes must be in 1..65535");
+    nearest_table(dst, src, tab_out);
+    *mul = 0; *shift = 0;
+    if (src <= dst) nearest_mulshift(dst, src, tab_out, mul, shift);
+    return SMAP_OK;
 }
 
 int smap_notify_map_modified(smap_handle* h) {

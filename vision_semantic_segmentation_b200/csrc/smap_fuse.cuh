@@ -72,7 +72,33 @@ struct FuseFrame {
     int64_t n;
     int32_t per_warp;      // points per warp: ceil(n / (gridDim.x * kFWarps)), computed by the host
     int32_t img64;         // label image readable with aligned 8-byte loads (base aligned, size a multiple of 8)
+    // FMT 1 (class-id plane at the network's resolution, smap.h SMAP_IMG_CLASS_IDS): camera pixel (u, v) reads
+    // ids[nn(v) * src_w + nn(u)], nn = cv2.resize's INTER_NEAREST index map (min(floor(x * fl(1 / (W / w))), w - 1),
+    // src/vision_semantic_segmentation_node.py:109-110).  The host tabulates the map in double as OpenCV does and hands it
+    // over as a multiply-shift when one reproduces the whole table (checked exhaustively: at most 65535 entries), as
+    // the table itself (u entries, then v entries, W and H of them) otherwise.
+    const uint16_t* nn_tab;
+    uint32_t nn_mx, nn_my; // nn(u) = (u * nn_mx) >> nn_sx when nn_tab == nullptr
+    uint32_t nn_sx, nn_sy;
+    int32_t src_w;
+    int32_t pad_f;
 };
+
+// Index of the label byte(s) of camera pixel (iu, iv): the pixel itself for an RGB image, the nearest-neighbour source
+// pixel of the class-id plane otherwise.
+template <int FMT>
+__device__ __forceinline__ uint32_t label_index(const FuseFrame& F, uint32_t iu, uint32_t iv) {
+    if (FMT == 0) return iv * (uint32_t)F.fp.img_w + iu;
+    uint32_t sx, sy;
+    if (F.nn_tab) {
+        sx = __ldg(F.nn_tab + iu);
+        sy = __ldg(F.nn_tab + (uint32_t)F.fp.img_w + iv);
+    } else {
+        sx = (iu * F.nn_mx) >> F.nn_sx;
+        sy = (iv * F.nn_my) >> F.nn_sy;
+    }
+    return sy * (uint32_t)F.src_w + sx;
+}
 
 // Kernel parameter of k_fuse<MODE, NF>: the NF frames a launch walks.
 //   NF == 1          one launch per frame (on alternating internal streams, so that the ramp-up and tail of one
@@ -89,6 +115,7 @@ template <int NF>
 struct FuseBatchT {
     FuseFrame f[NF];
     uint32_t* tags;        // MODE 1: (cells * (C + 1), tag_planes) uint32; frame f of the launch uses plane f
+    const uint32_t* id_lut;   // FMT 1: class bits of the 256 class ids (palette x cfg.LABEL_COLORS, folded by the host)
     int32_t n_frames;
     int32_t tag_planes;    // plane stride (>= n_frames)
 };
@@ -145,12 +172,14 @@ __device__ __forceinline__ bool cull32(const Fast32& k, float x, float y, float 
 // Inlined on purpose: with one frame per launch `fp` and `gp` are kernel parameters at fixed offsets, so the float64
 // instructions take their constants straight from the constant bank; behind a call they were ~40 dependent generic
 // loads per point.  Only the exact chains (a few points per 10 000) stay out of line.
+template <int FMT>
 #ifdef SMAP_FUSE_DECIDE64_CALL
 __device__ __noinline__
 #else
 __device__ __forceinline__
 #endif
-uint2 fuse_decide64(const FrameParams& fp, const GridParams& gp, float4 w) {
+uint2 fuse_decide64(const FuseFrame& F, const GridParams& gp, float4 w) {
+    const FrameParams& fp = F.fp;
     const double x = (double)w.x, y = (double)w.y, z = (double)w.z;
     const bool coords_ok = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fabsf(w.z)) < (float)kCoordBound;
     int pix = fast_project(fp, x, y, z, coords_ok);
@@ -165,7 +194,7 @@ uint2 fuse_decide64(const FrameParams& fp, const GridParams& gp, float4 w) {
     } else if (on == kDrop) {
         return make_uint2(0u, kNone);
     }
-    return make_uint2((uint32_t)(pix >> 16) * (uint32_t)fp.img_w + (uint32_t)(pix & 0xffff),
+    return make_uint2(label_index<FMT>(F, (uint32_t)(pix & 0xffff), (uint32_t)(pix >> 16)),
                       (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy);
 }
 
@@ -241,7 +270,10 @@ __host__ __device__ constexpr int fuse_block_smem(int nf) { return kFWarps * fus
 //             that carried loads and atomics across loop iterations was tried first: ptxas puts every carried
 //             operation on one scoreboard and waits for it at the loop head, which serialised everything.)
 // ------------------------------------------------------------------------------------------------
-template <int MODE, int NF>
+//
+// FMT 0: RGB label image, class bits = tabR[R] & tabG[G].  FMT 1: class-id plane (1 byte per network pixel), class
+// bits = id_lut[id]; the only other difference is the label index (label_index<FMT>).
+template <int MODE, int NF, int FMT = 0>
 __global__ void __launch_bounds__(kFThreads, SMAP_FUSE_MINB)
 k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridParams gp, FrameBox* __restrict__ boxes,
        double* __restrict__ map) {
@@ -308,7 +340,11 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
     for (int r = 0; r < kFStages - 1; ++r) issue_round();   // one more is issued at the top of every round
     // the first rounds are on their way while the block builds its colour tables
 #endif
-    build_color_tables(gp, s_tab_r, s_tab_g);
+    if (FMT == 0) {
+        build_color_tables(gp, s_tab_r, s_tab_g);
+    } else {
+        for (int i = threadIdx.x; i < 256; i += kFThreads) s_tab_r[i] = __ldg(B.id_lut + i);
+    }
     if (threadIdx.x < NF) box_reset(s_box[threadIdx.x]);
     __syncthreads();
 
@@ -382,7 +418,12 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             have = cert & inside;
             tp.x = fmaxf(tp.x, kMagic32); tp.y = fmaxf(tp.y, kMagic32);              // floor -1 -> pixel 0
             tc.x = fmaxf(tc.x, fk.clamp_c.x); tc.y = fmaxf(tc.y, fk.clamp_c.y);      // floor -1 -> cell 0
-            pix = __float_as_uint(tp.y) * (uint32_t)B.f[f].fp.img_w + __float_as_uint(tp.x) + fk.pix_k;
+            if (FMT == 0) {
+                pix = __float_as_uint(tp.y) * (uint32_t)B.f[f].fp.img_w + __float_as_uint(tp.x) + fk.pix_k;
+            } else {
+                constexpr uint32_t kMagicBits = 0x4B400000u;   // bits of kMagic32: RN(u - 1/2) = bits(tp) - kMagicBits
+                pix = label_index<1>(B.f[f], __float_as_uint(tp.x) - kMagicBits, __float_as_uint(tp.y) - kMagicBits);
+            }
             cell = __float_as_uint(tc.x) * (uint32_t)gp.mw + __float_as_uint(tc.y) + fk.cell_k;
             if (MODE != 1 && have) {
                 fbx0 = fminf(fbx0, tc.x); fbx1 = fmaxf(fbx1, tc.x);
@@ -425,7 +466,7 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             const float4 w = defer[first + lane];
             fid = (NF == 1) ? 0u : defer_f[first + lane];
             it = w.w;
-            pc = fuse_decide64(B.f[fid].fp, gp, w);
+            pc = fuse_decide64<FMT>(B.f[fid], gp, w);
             have = pc.y != kNone;
             if (MODE != 1 && have) {   // rare: straight into the block's box of that frame
                 const int cx = (int)(pc.y / (uint32_t)gp.mw), cy = (int)(pc.y - (uint32_t)cx * (uint32_t)gp.mw);
@@ -456,9 +497,14 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
 #else
                 const uint8_t* img = B.f[fid[k]].image;
                 const size_t a = (size_t)pix * 3u;
+                if (FMT == 1) {
+                    lr[k] = __ldg(img + pix);   // the class id
+                } else
 #ifdef SMAP_FUSE_LABEL8
+                {
                 lr[k] = __ldg(img + a);
                 lg[k] = __ldg(img + a + 1);
+                }
 #else
                 if (B.f[fid[k]].img64) {
                     // R and G from ONE aligned 8-byte load (a second one only when R is the last byte of its 8: one
@@ -479,7 +525,8 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
         uint32_t bits[kFGather], old0[kFGather], old1[kFGather], tag[kFGather];
 #pragma unroll
         for (int k = 0; k < kFGather; ++k) {
-            bits[k] = (cellf[k] != kNone) ? (s_tab_r[lr[k]] & s_tab_g[lg[k]]) : 0u;
+            if (FMT == 0) bits[k] = (cellf[k] != kNone) ? (s_tab_r[lr[k]] & s_tab_g[lg[k]]) : 0u;
+            else bits[k] = (cellf[k] != kNone) ? s_tab_r[lr[k]] : 0u;
             tag[k] = 0u; old0[k] = 0u; old1[k] = 0u;
 #ifdef SMAP_ABL_NO_SCATTER
             if (bits[k] && cellf[k] == 0x7ffffff0u) atomicOr(B.f[0].mask, bits[k]);

@@ -83,9 +83,19 @@ class DeviceMapper(object):
         except KeyError:
             raise ValueError("unknown camera calibration object; pass it in `cameras` at construction")
 
-    def make_frame(self, points, image, world_to_velodyne, camera=0, host=False):
+    def set_label_palette(self, labels):
+        """Palette of the segmentation network (``labels`` of the dataset config, or an (n, 3) colour array): needed
+        before frames carry class-id planes instead of RGB label images (``label_image.py``, SMAP_IMG_CLASS_IDS)."""
+        from .label_image import palette_of
+        pal = palette_of(labels)
+        _native.check(self._lib.smap_set_label_palette(self._h, pal.ctypes.data_as(ctypes.c_void_p), pal.shape[0]))
+        self._palette = pal
+
+    def make_frame(self, points, image, world_to_velodyne, camera=0, host=False, image_size=None):
         """Describe one frame for the C ABI.  ``points``: torch tensor (N,4) float32 [float4 layout] or
-        (4,N) float64 [the reference's pcd layout]; ``image``: (H,W,3) uint8; ``world_to_velodyne``: 4x4
+        (4,N) float64 [the reference's pcd layout]; ``image``: (H,W,3) uint8 RGB label image, or an (h,w) uint8
+        class-id plane (the network's output; ``image_size=(H, W)`` is then the camera resolution it would be
+        upscaled to, default its own shape; float32 clouds only); ``world_to_velodyne``: 4x4
         float64 numpy or None for a cloud already in the velodyne frame.  host=True: tensors live in
         (pinned) host memory and are meant for ``integrate_host``."""
         torch = _native.require_cuda()
@@ -102,13 +112,24 @@ class DeviceMapper(object):
                 f.ld = 0
         else:
             raise TypeError("cloud must be float32 (N,4) or float64 (4,N)")
-        if image.dtype != torch.uint8 or image.dim() != 3 or image.shape[2] != 3 or not image.is_contiguous():
-            raise ValueError("label image must be contiguous (H, W, 3) uint8")
+        if image.dtype == torch.uint8 and image.dim() == 2 and image.is_contiguous():
+            if getattr(self, "_palette", None) is None:
+                raise ValueError("class-id planes need the network's palette: call set_label_palette first")
+            if f.layout != SMAP_PTS_F32X4:
+                raise ValueError("class-id planes go with float32 (N, 4) clouds")
+            f.image_format = _native.SMAP_IMG_CLASS_IDS
+            f.ids_height, f.ids_width = image.shape[0], image.shape[1]
+            f.image_height, f.image_width = (image.shape[0], image.shape[1]) if image_size is None else \
+                (int(image_size[0]), int(image_size[1]))
+        elif image.dtype != torch.uint8 or image.dim() != 3 or image.shape[2] != 3 or not image.is_contiguous():
+            raise ValueError("label image must be contiguous (H, W, 3) uint8, or an (h, w) uint8 class-id plane")
+        else:
+            f.image_format = _native.SMAP_IMG_RGB
+            f.image_height, f.image_width = image.shape[0], image.shape[1]
         if not host and (not points.is_cuda or not image.is_cuda):
             raise ValueError("device frames need CUDA tensors")
         f.points_dev = points.data_ptr()
         f.image_dev = image.data_ptr()
-        f.image_height, f.image_width = image.shape[0], image.shape[1]
         f.camera = self.camera_slot(camera)
         if world_to_velodyne is None:
             f.has_transform = 0

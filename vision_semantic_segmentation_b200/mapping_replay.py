@@ -100,6 +100,7 @@ class SemanticMapping(object):
             raise NotImplementedError("more than one class named 'lane' is not supported by the cell-mask layout")
         self._lane_index = lanes[0] if lanes else -1
         self._device_arg = device
+        self._label_palette = None   # the network's palette, for frames that carry class-id planes (set_label_palette)
         self._dev = None        # DeviceMapper, created on first device use
         self._host_map = None   # numpy grid assigned by the caller before the device exists
 
@@ -131,11 +132,24 @@ class SemanticMapping(object):
                 self.map_height, self.map_width, self.label_colors, self.confusion_matrix, self.map_boundary,
                 self.resolution, self.pcd_range_max, self.use_pcd_intensity, self._lane_index,
                 cameras=[self.cam1, self.cam6], device=self._device_arg)
+            if self._label_palette is not None:
+                self._dev.set_label_palette(self._label_palette)
             if self._host_map is not None:
                 self._dev.map.copy_(_native.require_cuda().from_numpy(self._host_map))
                 self._dev.notify_map_modified()
                 self._host_map = None
         return self._dev
+
+    def set_label_palette(self, labels):
+        """Palette of the segmentation network: the ``labels`` list of its dataset config
+        (``cfg.VISION_SEM_SEG.SEM_SEG_NETWORK.DATASET_CONFIG``, read with ``label_image.get_labels``) or an (n, 3)
+        colour array.  Frames may then carry ``"semantic_ids"`` -- the network's (h, w) uint8 class-id plane -- instead
+        of ``"semantic_image"``; the result is what the reference computes from the image its node would have painted
+        (``label_image.paint_class_ids``)."""
+        from .label_image import palette_of
+        self._label_palette = palette_of(labels)
+        if self._dev is not None:
+            self._dev.set_label_palette(self._label_palette)
 
     @property
     def map_device(self):
@@ -174,7 +188,7 @@ class SemanticMapping(object):
         """``inv(T_base_to_origin @ T_velodyne_to_baselink)`` (``src/mapping_replay.py:225-226``)."""
         return np.linalg.inv(np.matmul(get_transform_from_pose(pose), self.T_velodyne_to_basklink))
 
-    def _frame_for(self, pcd, pcd_frame_id, image, pose, camera_calibration):
+    def _frame_for(self, pcd, pcd_frame_id, image, pose, camera_calibration, image_size=None):
         """Move one frame's inputs to the device (if needed) and describe it for the C ABI."""
         torch = _native.require_cuda()
         dm = self.device_mapper
@@ -196,7 +210,14 @@ class SemanticMapping(object):
         else:
             img = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(dev)
         T = self.world_to_velodyne(pose) if pcd_frame_id != "velodyne" else None
-        return dm.make_frame(pts, img, T, camera_calibration), (pts, img)
+        if img.dim() == 2 and pts.dtype != torch.float32:
+            # class-id planes ride the float4 kernel; recorded clouds hold float32-representable values
+            # (PointCloud2 fields are FLOAT32, src/mapping.py:178-180), anything else would change results
+            p32 = pts[0:4].to(torch.float32)
+            if not torch.equal(p32.to(torch.float64), pts[0:4]):
+                raise ValueError("class-id planes need a cloud of float32-representable values")
+            pts = p32.t().contiguous()
+        return dm.make_frame(pts, img, T, camera_calibration, image_size=image_size), (pts, img)
 
     # ------------------------------------------------------------------ reference API
     def project_pcd(self, pcd, pcd_frame_id, image, pose, camera_calibration):
@@ -241,8 +262,17 @@ class SemanticMapping(object):
         cam = self.cam1
         if frame_input_dict.get("camera_id", 1) == 6:
             cam = self.cam6
-        frame, keep = self._frame_for(pcd, frame_input_dict["pcd_frame_id"], frame_input_dict["semantic_image"],
-                                      frame_input_dict["pose"], cam)
+        if frame_input_dict.get("semantic_ids") is not None:
+            # the network's class-id plane; camera resolution from "image_size" (H, W), default the 1920x1440 of
+            # the calibrations (src/camera.py:102-135)
+            image = frame_input_dict["semantic_ids"]
+            size = frame_input_dict.get("image_size")
+            if size is None:
+                size = (int(cam.imSize[1]), int(cam.imSize[0]))
+        else:
+            image, size = frame_input_dict["semantic_image"], None
+        frame, keep = self._frame_for(pcd, frame_input_dict["pcd_frame_id"], image, frame_input_dict["pose"], cam,
+                                      image_size=size)
         self.device_mapper.integrate(frame)
 
     def mapping_replay(self, input_list, file_name, write_image=True, row_tiles=False):

@@ -43,14 +43,19 @@ def synthetic_pose(frame_idx, origin=(-1200.0, 300.0), step=(3.0, 1.0), yaw0=0.3
                 (0.0, 0.0, math.sin(0.5 * yaw), math.cos(0.5 * yaw)))
 
 
-def synthetic_label_image(rng, height=IMAGE_H, width=IMAGE_W, blocky=False, block=64, colors=COLORS_19):
+def synthetic_label_ids(rng, height=IMAGE_H, width=IMAGE_W, blocky=False, block=64, num_ids=len(COLORS_19)):
+    """(H, W) class ids: what the segmentation network would output for the frame."""
     if blocky:
         gh, gw = -(-height // block), -(-width // block)
-        ids = rng.integers(0, len(colors), (gh, gw))
+        ids = rng.integers(0, num_ids, (gh, gw))
         ids = np.repeat(np.repeat(ids, block, axis=0), block, axis=1)[:height, :width]
     else:
-        ids = rng.integers(0, len(colors), (height, width))
-    return np.ascontiguousarray(colors[ids])
+        ids = rng.integers(0, num_ids, (height, width))
+    return ids
+
+
+def synthetic_label_image(rng, height=IMAGE_H, width=IMAGE_W, blocky=False, block=64, colors=COLORS_19):
+    return np.ascontiguousarray(colors[synthetic_label_ids(rng, height, width, blocky, block, len(colors))])
 
 
 def synthetic_points(rng, n_points, pose):
@@ -71,14 +76,18 @@ def synthetic_points(rng, n_points, pose):
 
 
 def synthetic_frame(seed, frame_idx, n_points, height=IMAGE_H, width=IMAGE_W, blocky=False,
-                    pose=None, as_float64=True):
+                    pose=None, as_float64=True, with_ids=False):
     """One frame dictionary.  ``points`` (N,4) float32 is the device-friendly record;
-    ``pcd`` (4,N) float64 is what the reference API takes (same values)."""
+    ``pcd`` (4,N) float64 is what the reference API takes (same values).  ``with_ids``: also ``semantic_ids``, the
+    (H, W) uint8 class-id plane the label image was painted from (palette ``COLORS_19``)."""
     rng = np.random.default_rng(seed + frame_idx)
     pose = synthetic_pose(frame_idx) if pose is None else pose
     pts = synthetic_points(rng, n_points, pose)
-    image = synthetic_label_image(rng, height, width, blocky)
+    ids = synthetic_label_ids(rng, height, width, blocky)
+    image = np.ascontiguousarray(COLORS_19[ids])
     frame = {"points": pts, "pcd_frame_id": "world", "semantic_image": image, "pose": pose}
+    if with_ids:
+        frame["semantic_ids"] = np.ascontiguousarray(ids.astype(np.uint8))
     if as_float64:
         frame["pcd"] = np.ascontiguousarray(pts.T.astype(np.float64))
     return frame
