@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--label-format", default="rgb", choices=["rgb", "ids"],
+                    help="rgb: the (1440, 1920, 3) colour-coded label image the reference consumes (default, the "
+                         "BASELINE.json workload); ids: the network's (1440, 1920) uint8 class-id plane "
+                         "(SMAP_IMG_CLASS_IDS) for the device-resident legs as well")
     ap.add_argument("--ordered", action="store_true",
                     help="dev switch: force the ordered update (cell masks + k_apply) although the matrix is np.eye(C)")
     return ap.parse_args()
@@ -241,13 +245,15 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": "mapping_replay cfg2: %d-point cloud + 1920x1440 19-class label image per frame, "
-                        "count update, %d mapped classes, grid %dx%d @ %.1f m" % (args.points, args.classes, MAP_H, MAP_W, RESOLUTION),
-            "points_per_frame": args.points, "image": [1440, 1920, 3], "mapped_classes": args.classes,
+    ids = getattr(args, "label_format", "rgb") == "ids"
+    return {"workload": "mapping_replay cfg2: %d-point cloud + 1920x1440 19-class label image per frame%s, "
+                        "count update, %d mapped classes, grid %dx%d @ %.1f m"
+                        % (args.points, " (as uint8 class-id plane)" if ids else "", args.classes, MAP_H, MAP_W, RESOLUTION),
+            "points_per_frame": args.points, "image": [1440, 1920] if ids else [1440, 1920, 3], "mapped_classes": args.classes,
             "grid": [MAP_H, MAP_W, args.classes], "update": "count", "frames_per_rank": args.steps,
             "parallelism": "frames sharded over %d rank(s), all-reduce(sum) of the grid at the end" % world,
             "l2_policy": "inputs larger than L2: ring of %d distinct frames (%.0f MB) resident in HBM"
-                         % (args.ring, args.ring * (args.points * 16 + 1440 * 1920 * 3) / 1e6)}
+                         % (args.ring, args.ring * (args.points * 16 + 1440 * 1920 * (1 if ids else 3)) / 1e6)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -278,8 +284,10 @@ def run_b200(args):
 
     ring_host = make_ring(args, rank)
     ring_dev, ring_pinned = [], []
-    for pts, img, T, _ in ring_host:
-        dp, di = torch.from_numpy(pts).to(dev), torch.from_numpy(img).to(dev)
+    if args.label_format == "ids":
+        dm.set_label_palette(syn.COLORS_19)
+    for pts, img, T, ids in ring_host:
+        dp, di = torch.from_numpy(pts).to(dev), torch.from_numpy(ids if args.label_format == "ids" else img).to(dev)
         ring_dev.append((dm.make_frame(dp, di, T, 0), dp, di))
     torch.cuda.synchronize()
 
@@ -287,14 +295,19 @@ def run_b200(args):
     n_pts = args.points
     m_list, u_list, k_list = [], [], []
     for frame, dp, di in ring_dev[: min(4, len(ring_dev))]:
-        masked, _ = dm.project(frame)
+        if args.label_format == "ids":   # the parity API takes RGB images: count the survivors with one
+            masked, _ = dm.project(dm.make_frame(dp, torch.from_numpy(ring_host[len(m_list)][1]).to(dev),
+                                                 ring_host[len(m_list)][2], 0))
+        else:
+            masked, _ = dm.project(frame)
         m_list.append(masked.shape[1])
         dm.clear()
         dm.integrate(frame)
         u_list.append(int(torch.count_nonzero(dm.map).item()))
         k_list.append(int(torch.count_nonzero(dm.map.sum(dim=2)).item()))
     M, U, Kc = float(np.mean(m_list)), float(np.mean(u_list)), float(np.mean(k_list))
-    bytes_per_frame = 16.0 * n_pts + 3.0 * M + 2.0 * 8.0 * U
+    label_bytes = 1.0 if args.label_format == "ids" else 3.0
+    bytes_per_frame = 16.0 * n_pts + label_bytes * M + 2.0 * 8.0 * U
     dm.clear()
     torch.cuda.synchronize()
 
@@ -357,7 +370,7 @@ def run_b200(args):
     achieved = bytes_per_frame / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")   # from the committed ncu --set full capture
-    if os.path.exists(tpath):
+    if args.label_format == "rgb" and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("k_fuse_c%d" % args.classes)
 

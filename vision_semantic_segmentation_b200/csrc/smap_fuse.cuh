@@ -91,6 +91,9 @@ __device__ __forceinline__ uint32_t label_index(const FuseFrame& F, uint32_t iu,
     if (FMT == 0) return iv * (uint32_t)F.fp.img_w + iu;
     uint32_t sx, sy;
     if (F.nn_tab) {
+        // decide32 also evaluates lanes whose point it then rejects or defers: their (iu, iv) may be anything
+        iu = min(iu, (uint32_t)F.fp.img_w - 1u);
+        iv = min(iv, (uint32_t)F.fp.img_h - 1u);
         sx = __ldg(F.nn_tab + iu);
         sy = __ldg(F.nn_tab + (uint32_t)F.fp.img_w + iv);
     } else {
