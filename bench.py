@@ -38,6 +38,23 @@ BOUNDARY, RESOLUTION, RANGE_MAX = [[100, 300], [800, 1000]], 0.1, 100.0
 MAP_H = MAP_W = 2000
 
 
+def select_workload(args):
+    """cfg2 (default, the configuration the metric is quoted on): count update, 2000 x 2000 grid at 0.1 m.
+    cfg3 (BASELINE.json configs[2]): confusion-matrix log-likelihood update -- the ordered two-kernel path -- into a
+    0.2 m, 2 km x 2 km grid (10^4 x 10^4 cells; 4 GB of float64 at 5 classes)."""
+    global BOUNDARY, RESOLUTION, MAP_H, MAP_W
+    if args.workload == "cfg3":
+        BOUNDARY, RESOLUTION, MAP_H, MAP_W = [[0, 2000], [0, 2000]], 0.2, 10000, 10000
+
+
+def update_matrix(args, labels):
+    if args.workload != "cfg3":
+        return np.eye(len(labels))
+    # src/mapping_replay.py:104-109 / src/data/confusion_matrix.py:43-48,59-63 on a synthetic strictly positive matrix
+    sub = syn.synthetic_confusion_matrix(11)[np.ix_(labels, labels)]
+    return np.log(sub / np.sum(sub, axis=1)[:, np.newaxis])
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -52,6 +69,9 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg2: BASELINE.json configs[1], the configuration the metric is quoted on (default); "
+                         "cfg3: configs[2], log-likelihood update into a 10^4 x 10^4 grid")
     ap.add_argument("--label-format", default="rgb", choices=["rgb", "ids"],
                     help="rgb: the (1440, 1920, 3) colour-coded label image the reference consumes (default, the "
                          "BASELINE.json workload); ids: the network's (1440, 1920) uint8 class-id plane "
@@ -185,7 +205,7 @@ def cpu_frame_fn(args):
     from oracle import numpy_port  # the ONLY place bench.py touches oracle/: the CPU baseline being timed
     from vision_semantic_segmentation_b200.camera import camera_setup_1
     labels, names, colors = syn.class_setup(args.classes == 19)
-    cam, cm = camera_setup_1(), np.eye(len(labels))
+    cam, cm = camera_setup_1(), update_matrix(args, labels)
     grid = np.zeros((MAP_H, MAP_W, len(labels)))
 
     def run(points, image, T, ids=None):
@@ -246,11 +266,13 @@ def run_reference(args):
 
 def workload_config(args, world):
     ids = getattr(args, "label_format", "rgb") == "ids"
-    return {"workload": "mapping_replay cfg2: %d-point cloud + 1920x1440 19-class label image per frame%s, "
-                        "count update, %d mapped classes, grid %dx%d @ %.1f m"
-                        % (args.points, " (as uint8 class-id plane)" if ids else "", args.classes, MAP_H, MAP_W, RESOLUTION),
+    cfg3 = getattr(args, "workload", "cfg2") == "cfg3"
+    return {"workload": "mapping_replay %s: %d-point cloud + 1920x1440 19-class label image per frame%s, "
+                        "%s update, %d mapped classes, grid %dx%d @ %.1f m"
+                        % ("cfg3" if cfg3 else "cfg2", args.points, " (as uint8 class-id plane)" if ids else "",
+                           "confusion-matrix log-likelihood" if cfg3 else "count", args.classes, MAP_H, MAP_W, RESOLUTION),
             "points_per_frame": args.points, "image": [1440, 1920] if ids else [1440, 1920, 3], "mapped_classes": args.classes,
-            "grid": [MAP_H, MAP_W, args.classes], "update": "count", "frames_per_rank": args.steps,
+            "grid": [MAP_H, MAP_W, args.classes], "update": "log-likelihood" if cfg3 else "count", "frames_per_rank": args.steps,
             "parallelism": "frames sharded over %d rank(s), all-reduce(sum) of the grid at the end" % world,
             "l2_policy": "inputs larger than L2: ring of %d distinct frames (%.0f MB) resident in HBM"
                          % (args.ring, args.ring * (args.points * 16 + 1440 * 1920 * (1 if ids else 3)) / 1e6)}
@@ -270,7 +292,7 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     labels, names, colors = syn.class_setup(args.classes == 19)
     c = len(labels)
-    cam, cm, lane = camera_setup_1(), np.eye(c), names.index("lane")
+    cam, cm, lane = camera_setup_1(), update_matrix(args, labels), names.index("lane")
     dm = DeviceMapper(MAP_H, MAP_W, colors, cm, BOUNDARY, RESOLUTION, RANGE_MAX, True, lane, cameras=[cam], device=local_rank)
 
     if args.ordered:   # smap_clear re-arms the count update: undo that after every clear
@@ -370,7 +392,7 @@ def run_b200(args):
     achieved = bytes_per_frame / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")   # from the committed ncu --set full capture
-    if args.label_format == "rgb" and os.path.exists(tpath):
+    if args.label_format == "rgb" and args.workload == "cfg2" and not args.ordered and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("k_fuse_c%d" % args.classes)
 
@@ -451,7 +473,11 @@ def run_b200(args):
             "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_fuse<count> (register-prefetched cloud, float32 certified project+cull+lookup+update, one frame per launch)",
+                         "kernel": ("k_fuse<masks> (project+cull+lookup+RED.OR into the frame's cell masks, one frame per "
+                                    "launch); the ordered k_apply replay is apply_kernel_ms_per_frame"
+                                    if (args.workload == "cfg3" or args.ordered) else
+                                    "k_fuse<count> (register-prefetched cloud, float32 certified project+cull+lookup+update, "
+                                    "one frame per launch)"),
                          "kernel_ms": kernel_ms, "apply_kernel_ms_per_frame": apply_ms,
                          "step_frac": bytes_per_frame / (ms / args.steps * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_frame": bytes_per_frame,
@@ -466,6 +492,7 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    select_workload(args)
     if args.impl == "reference":
         run_reference(args)
     else:
