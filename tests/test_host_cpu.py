@@ -142,6 +142,26 @@ def test_replay_record_roundtrip(tmp_path):
     assert np.array_equal(replay_io.load_input_list(path)[0]["pcd"], odd["pcd"])
 
 
+def test_replay_record_with_class_id_planes(tmp_path):
+    """Frames that carry the network's class-id plane instead of (or next to) the painted image."""
+    frames = [syn.synthetic_frame(4, f, 300, height=48, width=64, with_ids=True) for f in range(3)]
+    frames[0].pop("semantic_image")                                   # ids only, full resolution
+    frames[1]["semantic_ids"] = frames[1]["semantic_ids"][::2, ::2].copy()   # ids only, half resolution
+    frames[1].pop("semantic_image")
+    frames[1]["image_size"] = (48, 64)
+    path = str(tmp_path / "input_list_0.npz")
+    replay_io.save_input_list(path, frames, compressed=True)
+    back = replay_io.load_input_list(path)
+    assert "semantic_image" not in back[0] and "semantic_image" not in back[1] and "semantic_image" in back[2]
+    for a, b in zip(frames, back):
+        assert b["semantic_ids"].dtype == np.uint8 and np.array_equal(a["semantic_ids"], b["semantic_ids"])
+    assert back[1]["image_size"] == (48, 64) and "image_size" not in back[0]
+    with pytest.raises(ValueError):
+        replay_io.save_input_list(path, [{k: v for k, v in frames[0].items() if k != "semantic_ids"}])
+    with pytest.raises(ValueError):
+        replay_io.save_input_list(path, [dict(frames[0], semantic_ids=np.zeros((2, 2, 3), np.uint8))])
+
+
 def test_shard_ranges_cover_every_frame_once():
     for n in (0, 1, 7, 100, 8000):
         for world in (1, 2, 3, 4, 8):

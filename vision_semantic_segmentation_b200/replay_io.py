@@ -7,6 +7,10 @@ The reference's live node appends one dictionary per camera frame to ``input_lis
 stored as one ``.npz`` per drive.  Clouds are written as (N, 4) float32 -- the ``float4`` layout the kernels
 read, and lossless for PointCloud2 data, whose fields are FLOAT32 -- unless a value is not
 float32-representable, in which case the float64 (4, N) array is kept.
+
+A frame may carry ``semantic_ids`` -- the network's (h, w) uint8 class-id plane -- instead of (or next to) the painted
+``semantic_image`` (``label_image.py``; a third of the bytes at full resolution, a twelfth at ``IMAGE_SCALE`` 0.5),
+with ``image_size`` (H, W) when the plane is smaller than the camera image.
 """
 import numpy as np
 
@@ -34,7 +38,17 @@ def save_input_list(path, input_list, compressed=False):
                 arrays["points_%d" % i] = np.ascontiguousarray(as32.T)
             else:
                 arrays["pcd_%d" % i] = pcd
-        arrays["image_%d" % i] = np.ascontiguousarray(fr["semantic_image"], dtype=np.uint8)
+        if fr.get("semantic_image") is None and fr.get("semantic_ids") is None:
+            raise ValueError("frame %d has neither semantic_image nor semantic_ids" % i)
+        if fr.get("semantic_image") is not None:
+            arrays["image_%d" % i] = np.ascontiguousarray(fr["semantic_image"], dtype=np.uint8)
+        if fr.get("semantic_ids") is not None:
+            ids = np.ascontiguousarray(fr["semantic_ids"], dtype=np.uint8)
+            if ids.ndim != 2:
+                raise ValueError("semantic_ids must be a 2-D class-id plane")
+            arrays["ids_%d" % i] = ids
+            if fr.get("image_size") is not None:
+                arrays["image_size_%d" % i] = np.array([int(v) for v in fr["image_size"]], dtype=np.int64)
         arrays["pose_%d" % i] = _pose_array(fr["pose"])
         arrays["frame_id_%d" % i] = np.array(str(fr["pcd_frame_id"]))
         arrays["camera_id_%d" % i] = np.array(int(fr.get("camera_id", 1)), dtype=np.int64)
@@ -53,8 +67,14 @@ def load_input_list(path):
     out = []
     with np.load(path, allow_pickle=False) as z:
         for i in range(int(z["n_frames"])):
-            fr = {"semantic_image": z["image_%d" % i], "pose": Pose.from_array(z["pose_%d" % i]),
+            fr = {"pose": Pose.from_array(z["pose_%d" % i]),
                   "pcd_frame_id": str(z["frame_id_%d" % i]), "camera_id": int(z["camera_id_%d" % i])}
+            if "image_%d" % i in z.files:
+                fr["semantic_image"] = z["image_%d" % i]
+            if "ids_%d" % i in z.files:
+                fr["semantic_ids"] = z["ids_%d" % i]
+                if "image_size_%d" % i in z.files:
+                    fr["image_size"] = tuple(int(v) for v in z["image_size_%d" % i])
             if "points_%d" % i in z.files:
                 fr["points"] = z["points_%d" % i]
             else:
