@@ -205,6 +205,19 @@ SMAP_API int smap_render_thresholds(const double *map_dev, int mh, int mw, int c
                            const int32_t *priority_host, const double *thresholds_host, uint8_t *rgb_dev,
                            int device, void *stream);
 
+/* ---- evaluation: the step after rendering ------------------------------------------------------
+ * convert_labels (test/test_semantic_mapping.py:6-18) of the rendered map fused with the sums of Test.iou
+ * (:127-161) against the ground-truth label map slice truth[shift_rows : shift_rows + mh, shift_cols : shift_cols + mw]
+ * (Test.test_single_map, :117-125).  truth: (truth_rows, truth_cols) uint8 labels 0 unknown, 1 road, 2 crosswalk,
+ * 3 lane; mask: optional (mask_rows, mask_cols) uint8 validity mask applied to the map as convert_labels does
+ * (NULL: none).  counts_dev receives 12 int64 (zeroed by the call):
+ *   [0..2] intersection, [3..5] ground-truth pixels, [6..8] map pixels of classes 1, 2, 3;
+ *   [9] known ground truth, [10] known and mapped, [11] map == ground truth where known.
+ * Integer sums, exact; IoU = [k] / ([3+k] + [6+k] - [k]), missing rate = 1 - [10] / [9], accuracy = [11] / [9]. */
+SMAP_API int smap_eval_counts(const uint8_t *rgb_dev, int mh, int mw, const uint8_t *truth_dev, int truth_rows,
+                     int truth_cols, int shift_rows, int shift_cols, const uint8_t *mask_dev, int mask_rows,
+                     int mask_cols, int64_t *counts_dev, int device, void *stream);
+
 /* ---- grid access ------------------------------------------------------------------------------- */
 SMAP_API int smap_map_ptr(smap_handle *h, double **map_dev, int64_t *n_elements);
 SMAP_API int smap_clear(smap_handle *h, void *stream);            /* self.map = np.zeros(...)  src/mapping_replay.py:181 */

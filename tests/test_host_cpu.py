@@ -229,3 +229,30 @@ def test_frame_sharding_world_size_2_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+def test_evaluation_host_functions_known_answers():
+    """convert_labels / Test.iou (test/test_semantic_mapping.py:6-18,127-161) on a hand-made map, and the same scores
+    from the twelve sums the device kernel returns (scores_from_counts): no GPU needed for either."""
+    from vision_semantic_segmentation_b200 import evaluation as ev
+    colors = {1: (128, 64, 128), 2: (140, 140, 200), 3: (255, 255, 255), 4: (244, 35, 232), 5: (107, 142, 35)}
+    want = np.array([[1, 1, 2, 0], [3, 3, 4, 5], [0, 2, 2, 1]])
+    rgb = np.zeros(want.shape + (3,), dtype=np.uint8)
+    for k, col in colors.items():
+        rgb[want == k] = col
+    rgb[0, 3] = (128, 64, 129)            # one channel off: not a class
+    assert np.array_equal(ev.convert_labels(rgb), want)
+    mask = np.ones((5, 6))
+    mask[0, 0] = 0
+    masked = ev.convert_labels(rgb, mask)
+    assert masked[0, 0] == 0 and np.array_equal(masked.ravel()[1:], want.ravel()[1:])
+    truth = np.array([[1, 2, 2, 0], [3, 0, 0, 3], [1, 2, 3, 1]], dtype=np.float64)
+    t = ev.Test.__new__(ev.Test)
+    t.class_lists, t.d, t.logger = [1, 2, 3], {0: "road", 1: "crosswalk", 2: "lane"}, None
+    ious, miss = t.iou(truth, want.astype(np.float64))
+    assert ious == [2 / 4, 2 / 4, 1 / 4]                   # road 2/(3+3-2), crosswalk 2/(3+3-2), lane 1/(3+2-1)
+    assert miss == 1 - 8 / 9
+    counts = [2, 2, 1, 3, 3, 3, 3, 3, 2, 9, 8, 5]
+    ious2, accs, accuracy, miss2 = ev.scores_from_counts(counts)
+    assert ious2 == ious and miss2 == miss and accs == [2 / 3, 2 / 3, 1 / 3] and accuracy == 5 / 9
+    assert all(np.isnan(v) for v in ev.scores_from_counts([0] * 12)[0])

@@ -22,7 +22,7 @@ EXPORTS = [
     "smap_abi_version", "smap_last_error", "smap_device_count", "smap_device_info", "smap_create",
     "smap_destroy", "smap_set_camera", "smap_set_classes", "smap_set_label_palette", "smap_project", "smap_update", "smap_integrate",
     "smap_integrate_batch", "smap_integrate_host", "smap_apply_filter", "smap_render", "smap_filter_render",
-    "smap_render_thresholds", "smap_map_ptr", "smap_clear", "smap_notify_map_modified", "smap_download", "smap_upload", "smap_get_stats", "smap_set_profiling", "smap_debug_set_frame_tag", "smap_debug_fast32",
+    "smap_render_thresholds", "smap_eval_counts", "smap_map_ptr", "smap_clear", "smap_notify_map_modified", "smap_download", "smap_upload", "smap_get_stats", "smap_set_profiling", "smap_debug_set_frame_tag", "smap_debug_fast32",
     "smap_debug_nearest_map",
 ]
 
@@ -113,6 +113,8 @@ def load():
     L.smap_filter_render.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp]
     L.smap_render_thresholds.restype = i32
     L.smap_render_thresholds.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
+    L.smap_eval_counts.restype = i32
+    L.smap_eval_counts.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp]
     L.smap_map_ptr.restype = i32
     L.smap_map_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     L.smap_clear.restype = i32

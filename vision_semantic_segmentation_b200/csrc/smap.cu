@@ -1215,6 +1215,30 @@ int smap_debug_fast32(const smap_config* cfg, const smap_frame* frame, const dou
     return rc;
 }
 
+int smap_eval_counts(const uint8_t* rgb, int mh, int mw, const uint8_t* truth, int truth_rows, int truth_cols,
+                     int shift_rows, int shift_cols, const uint8_t* mask, int mask_rows, int mask_cols, int64_t* counts,
+                     int device, void* stream) {
+    if (!rgb || !truth || !counts) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (mh <= 0 || mw <= 0) return fail(SMAP_ERR_INVALID, "empty map");
+    if (shift_rows < 0 || shift_cols < 0 || (int64_t)shift_rows + mh > truth_rows || (int64_t)shift_cols + mw > truth_cols)
+        return fail(SMAP_ERR_INVALID, "the shifted map does not lie inside the ground-truth label map");
+    if (mask && (mask_rows < mh || mask_cols < mw)) return fail(SMAP_ERR_INVALID, "the mask is smaller than the map");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(SMAP_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    EvalParams p;
+    p.mh = mh; p.mw = mw; p.truth_ld = truth_cols; p.shift_r = shift_rows; p.shift_c = shift_cols;
+    p.mask_ld = mask ? mask_cols : 0;
+    CK(cudaMemsetAsync(counts, 0, sizeof(int64_t) * 12, st));
+    int sms = 148;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    int64_t grid = ceil_div((int64_t)mh * mw, kThreads);
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;   // grid-stride: 8 resident blocks of 256 threads per SM
+    k_eval_counts<<<(unsigned)grid, kThreads, 0, st>>>(rgb, truth, mask, p, reinterpret_cast<unsigned long long*>(counts));
+    CK(cudaGetLastError());
+    return SMAP_OK;
+}
+
 int smap_debug_nearest_map(int dst, int src, uint16_t* tab_out, uint32_t* mul, uint32_t* shift) {
     if (!tab_out || !mul || !shift) return fail(SMAP_ERR_INVALID, "NULL argument");
     if (dst <= 0 || src <= 0 || dst > 65535 || src > 65535) return fail(SMAP_ERR_INVALID, "sizes must be in 1..65535");

@@ -617,4 +617,55 @@ k_render_thresholds(const double* __restrict__ map, int64_t cells, int c, const 
     o[0] = r; o[1] = g; o[2] = b;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K7: evaluation counts -- convert_labels (test/test_semantic_mapping.py:6-18) fused with the sums of Test.iou
+// (:127-161) for the rendered map against the ground-truth label map (the slice the reference takes at :123-124).
+//   counts[0..2]  pixels where ground truth and map both hold class 1 (road), 2 (crosswalk), 3 (lane)
+//   counts[3..5]  ground-truth pixels of the class          counts[6..8]  map pixels of the class
+//   counts[9]     known ground truth (g > 0)                 counts[10]    known and mapped (g > 0 and m > 0)
+//   counts[11]    map equals ground truth where it is known
+// Integer sums: exact in any order; the host turns them into IoU / accuracy / missing rate as the reference does.
+struct EvalParams {
+    int mh, mw;            // rendered map (rows, columns)
+    int truth_ld;          // row stride of the ground-truth label map (uint8)
+    int shift_r, shift_c;  // the map's (0, 0) sits at ground truth (shift_r, shift_c)   (Test.shift_w, Test.shift_h)
+    int mask_ld;           // row stride of the validity mask, 0: no mask (convert_labels(gmap) with mask=None)
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_eval_counts(const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ truth, const uint8_t* __restrict__ mask,
+              const __grid_constant__ EvalParams p, unsigned long long* __restrict__ counts) {
+    uint32_t n[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) n[i] = 0u;
+    const int64_t cells = (int64_t)p.mh * p.mw;
+    for (int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cell < cells; cell += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(cell / p.mw), c = (int)(cell - (int64_t)r * p.mw);
+        const uint8_t* px = rgb + 3 * cell;
+        const uint32_t R = px[0], G = px[1], B = px[2];
+        uint32_t m = 0u;   // convert_labels: all three channels must match
+        if (R == 128u && G == 64u && B == 128u) m = 1u;         // road
+        else if (R == 140u && G == 140u && B == 200u) m = 2u;   // crosswalk
+        else if (R == 255u && G == 255u && B == 255u) m = 3u;   // lane
+        else if (R == 244u && G == 35u && B == 232u) m = 4u;    // sidewalk
+        else if (R == 107u && G == 142u && B == 35u) m = 5u;    // vegetation
+        if (p.mask_ld > 0 && mask[(int64_t)r * p.mask_ld + c] == 0u) m = 0u;
+        const uint32_t g = truth[(int64_t)(r + p.shift_r) * p.truth_ld + (c + p.shift_c)];
+#pragma unroll
+        for (uint32_t k = 1; k <= 3; ++k) {
+            n[k - 1] += (g == k && m == k);
+            n[k + 2] += (g == k);
+            n[k + 5] += (m == k);
+        }
+        n[9] += (g > 0u);
+        n[10] += (g > 0u && m > 0u);
+        n[11] += (g > 0u && g == m);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const uint32_t w = __reduce_add_sync(0xffffffffu, n[i]);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(counts + i, (unsigned long long)w);
+    }
+}
+
 }  // namespace smap

@@ -302,6 +302,7 @@ class SemanticMapping(object):
             color_map, filtered = filter_and_render(dm.map, self.label_colors, return_filtered=True)
             dm.map.copy_(filtered)  # self.map = apply_filter(self.map)
         dm.notify_map_modified()
+        color_map_dev = color_map
         color_map = color_map.cpu().numpy()
 
         if write_image and rank == 0:
@@ -312,7 +313,8 @@ class SemanticMapping(object):
             imwrite(output_file, color_map)
         if self.ground_truth_dir != "" and rank == 0:
             from .evaluation import Test
-            Test(ground_truth_dir=self.ground_truth_dir, logger=self.logger).test_single_map(color_map)
+            # scored where it was rendered (smap_eval_counts): src/mapping_replay.py:208-210
+            Test(ground_truth_dir=self.ground_truth_dir, logger=self.logger).test_single_map(color_map_dev)
         return color_map
 
     def mapping_replay_dir(self):
