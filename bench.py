@@ -55,6 +55,17 @@ def update_matrix(args, labels):
     return np.log(sub / np.sum(sub, axis=1)[:, np.newaxis])
 
 
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout at
+    the first collective unless told otherwise, and NCCL_DEBUG_FILE above is only a default the environment may
+    override): hand file descriptor 1 over to stderr for the rest of the process and keep a private duplicate of the
+    real stdout for the line."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -261,7 +272,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
 
 
 def workload_config(args, world):
@@ -484,7 +495,7 @@ def run_b200(args):
                          "N": n_pts, "M": M, "K_cells": Kc, "U_elements": U},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -492,6 +503,7 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    args.out = claim_stdout()
     select_workload(args)
     if args.impl == "reference":
         run_reference(args)
