@@ -51,7 +51,6 @@ def device_counts(color_map, truth, shift_w=0, shift_h=0, mask=None):
     """The twelve integer sums behind ``Test.iou`` for a rendered (H, W, 3) colour map against the ground-truth label
     map slice ``truth[shift_w : H + shift_w, shift_h : W + shift_h]`` (``test_single_map``), computed by
     ``smap_eval_counts`` on the GPU.  Returns a list of 12 ints (layout: ``include/smap.h``)."""
-    import ctypes
     from . import _native
     torch = _native.require_cuda()
     lib = _native.load()
