@@ -100,7 +100,9 @@ typedef struct smap_frame {
     double world_to_velodyne[16]; /* row-major 4x4 = inv(T_base_to_origin(pose) @ T_velodyne_to_baselink) */
     int32_t ids_width;        /* SMAP_IMG_CLASS_IDS: shape (ids_height, ids_width) of the class-id plane; 0 = W, H. */
     int32_t ids_height;       /* Pixel (u, v) reads ids[min(floor(v * fy), h - 1), min(floor(u * fx), w - 1)] with
-                               * fx = 1.0 / ((double)W / w): cv2.resize's INTER_NEAREST index map, in double as OpenCV */
+                               * fx = 1.0 / ((double)W / w): cv2.resize's INTER_NEAREST index map, in double as OpenCV.
+                               * The handle caches the map of the most recent (W, H, w, h); a new shape costs a host
+                               * tabulation and, when the map needs its table form, a device synchronisation. */
 } smap_frame;
 
 /* counters of the most recent frame(s); see smap_get_stats */
