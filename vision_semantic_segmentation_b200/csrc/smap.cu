@@ -582,7 +582,8 @@ int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp,
     f.nn_tab = nullptr;
     f.nn_mx = f.nn_my = f.nn_sx = f.nn_sy = 0;
     f.src_w = fr->image_width;
-    f.pad_f = 0;
+    f.pf_bytes = 0;
+    f.pf_image = nullptr;
     if (fr->image_format == SMAP_IMG_CLASS_IDS) {
         if (!h->palette_set) return fail(SMAP_ERR_STATE, "class-id plane without a palette (smap_set_label_palette)");
         if ((int64_t)ids_w(fr) * ids_h(fr) >= ((int64_t)1 << kFidShift))
@@ -706,6 +707,20 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         cudaStream_t ls = fork ? h->aux[lane_stream] : st;
         int rc = fill_fuse_frame(h, frames + i, fps[i], mode, used, fb->f[0]);
         if (rc) return rc;
+#if SMAP_FUSE_PF_IMAGE
+        {   // the label image of the second non-empty frame after this one (the next one runs beside this launch)
+            int seen = 0;
+            for (int k = i + 1; k < n_frames && fork; ++k) {
+                if (frames[k].n_points == 0 || ++seen < 2) continue;
+                const smap_frame& nx = frames[k];
+                fb->f[0].pf_image = nx.image_dev;
+                fb->f[0].pf_bytes = nx.image_format == SMAP_IMG_CLASS_IDS
+                                        ? (uint32_t)((int64_t)ids_w(&nx) * ids_h(&nx))
+                                        : (uint32_t)((int64_t)nx.image_width * nx.image_height * 3);
+                break;
+            }
+        }
+#endif
         int64_t gx = 0;
         rc = fuse_grid(h, fb->f, 1, fork ? SMAP_FUSE_GRID_DIV : 1, &gx);
         if (rc) return rc;

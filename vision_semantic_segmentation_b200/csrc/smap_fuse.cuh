@@ -81,7 +81,8 @@ struct FuseFrame {
     uint32_t nn_mx, nn_my; // nn(u) = (u * nn_mx) >> nn_sx when nn_tab == nullptr
     uint32_t nn_sx, nn_sy;
     int32_t src_w;
-    int32_t pad_f;
+    uint32_t pf_bytes;     // SMAP_FUSE_PF_IMAGE: size of the label image at pf_image (0: nothing to prefetch)
+    const uint8_t* pf_image;   // SMAP_FUSE_PF_IMAGE: label image of a LATER frame of the batch, pulled into L2 by this launch
 };
 
 // Index of the label byte(s) of camera pixel (iu, iv): the pixel itself for an RGB image, the nearest-neighbour source
@@ -228,6 +229,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #define SMAP_FUSE_STAGES 2
 #endif
 constexpr int kFStages = SMAP_FUSE_TMA ? SMAP_FUSE_STAGES : 0;
+// Experiments prepared from the stall samples of profiles/r1k_stall_breakdown.md (both off by default, not yet measured):
+//   SMAP_FUSE_PF_IMAGE=1   every launch pulls the label image of the frame that will run after the one running beside
+//                          it into L2 (one prefetch.global.L2 per lane at kernel start): the label gather then waits
+//                          for L2 instead of DRAM, and the image costs sequential lines instead of scattered sectors
+//   SMAP_FUSE_PF_CLOUD=D   lanes 0..7 prefetch the 1 KB of round r + D into L2 (D >= 2; round r + 1 is already on its
+//                          way into registers): cull-only rounds are shorter than the DRAM latency
+#ifndef SMAP_FUSE_PF_IMAGE
+#define SMAP_FUSE_PF_IMAGE 0
+#endif
+#ifndef SMAP_FUSE_PF_CLOUD
+#define SMAP_FUSE_PF_CLOUD 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 #ifndef SMAP_FUSE_GATHER
 #define SMAP_FUSE_GATHER 2
 #endif
@@ -351,6 +367,14 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
     if (threadIdx.x < NF) box_reset(s_box[threadIdx.x]);
     __syncthreads();
 
+#if SMAP_FUSE_PF_IMAGE
+    if (NF == 1 && B.f[0].pf_bytes) {
+        const uint32_t lines = (B.f[0].pf_bytes + 127u) >> 7;
+        const uint32_t lanes = gridDim.x * (uint32_t)kFThreads;
+        for (uint32_t l = (uint32_t)gw * 32u + (uint32_t)lane; l < lines; l += lanes)
+            prefetch_l2(B.f[0].pf_image + (size_t)l * 128u);
+    }
+#endif
     const uint32_t c1 = (uint32_t)gp.c + 1u;
     const uint32_t lane_bit = (gp.use_intensity && gp.lane >= 0) ? (1u << gp.lane) : 0u;
 
@@ -632,6 +656,11 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
                 for (int j = 0; j < kFRound; ++j)
                     nxt[j] = (kFRoundPts + j * 32 + lane < left) ? __ldcs(gp_pts + (r + 1) * kFRoundPts + j * 32)
                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+#if SMAP_FUSE_PF_CLOUD
+                if (lane < kFRoundPts * 16 / 128 && (r + SMAP_FUSE_PF_CLOUD) * kFRoundPts < w_pts)
+                    prefetch_l2(reinterpret_cast<const char*>(gp_pts - lane) +
+                                (size_t)(r + SMAP_FUSE_PF_CLOUD) * (kFRoundPts * 16) + lane * 128);
+#endif
 #pragma unroll
                 for (int j = 0; j < kFRound; ++j) {
                     const float4 w = buf[j];
