@@ -3,7 +3,7 @@
 # usage: tools/build_variants.sh NAME "-DSMAP_FUSE_MINB=3 -DSMAP_FUSE_GATHER=4 ..." [NAME2 "..."]  -> csrc/variants/NAME.so
 # knobs: SMAP_FUSE_MINB / ROUND / GATHER, SMAP_FUSE_TMA (+ STAGES, GROUP), SMAP_FUSE_PERSISTENT, SMAP_FUSE_GRID_DIV,
 #        SMAP_AUX_STREAMS, SMAP_TAG_MAX_PLANES, SMAP_FUSE_STATS, SMAP_ABL_NO_{DRAIN,GATHER,SCATTER,DEFER},
-#        SMAP_FUSE_PF_IMAGE, SMAP_FUSE_PF_CLOUD (L2 prefetch experiments, profiles/r1k_stall_breakdown.md)
+#        SMAP_FUSE_PF_IMAGE, SMAP_FUSE_PF_LABEL, SMAP_FUSE_PF_CLOUD (prefetch experiments, profiles/r1k_stall_breakdown.md)
 set -e
 cd "$(dirname "$0")/../vision_semantic_segmentation_b200/csrc"
 mkdir -p variants

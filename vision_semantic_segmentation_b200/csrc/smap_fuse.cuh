@@ -235,6 +235,12 @@ constexpr int kFStages = SMAP_FUSE_TMA ? SMAP_FUSE_STAGES : 0;
 //                          for L2 instead of DRAM, and the image costs sequential lines instead of scattered sectors
 //   SMAP_FUSE_PF_CLOUD=D   lanes 0..7 prefetch the 1 KB of round r + D into L2 (D >= 2; round r + 1 is already on its
 //                          way into registers): cull-only rounds are shorter than the DRAM latency
+//   SMAP_FUSE_PF_LABEL=1|2 a record's label bytes are prefetched (1: into L2, 2: into L1) when the float32 decision
+//                          pushes the record, one to two passes before the gather loads them (+1 instruction per
+//                          batch of 32 survivors)
+#ifndef SMAP_FUSE_PF_LABEL
+#define SMAP_FUSE_PF_LABEL 0
+#endif
 #ifndef SMAP_FUSE_PF_IMAGE
 #define SMAP_FUSE_PF_IMAGE 0
 #endif
@@ -243,6 +249,9 @@ constexpr int kFStages = SMAP_FUSE_TMA ? SMAP_FUSE_STAGES : 0;
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 #ifndef SMAP_FUSE_GATHER
 #define SMAP_FUSE_GATHER 2
@@ -457,6 +466,12 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
                 fby0 = fminf(fby0, tc.y); fby1 = fmaxf(fby1, tc.y);
             }
         }
+#if SMAP_FUSE_PF_LABEL
+        if (have) {
+            const uint8_t* lp = B.f[f].image + (FMT == 1 ? (size_t)pix : (size_t)pix * 3u);
+            if (SMAP_FUSE_PF_LABEL == 2) prefetch_l1(lp); else prefetch_l2(lp);
+        }
+#endif
         push_record(have, pix | ((uint32_t)f << kFidShift), cell, w.w);
         const unsigned dballot = __ballot_sync(0xffffffffu, defer_me);
 #ifdef SMAP_FUSE_STATS
