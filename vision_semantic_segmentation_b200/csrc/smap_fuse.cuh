@@ -672,7 +672,8 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
                     nxt[j] = (kFRoundPts + j * 32 + lane < left) ? __ldcs(gp_pts + (r + 1) * kFRoundPts + j * 32)
                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
 #if SMAP_FUSE_PF_CLOUD
-                if (lane < kFRoundPts * 16 / 128 && (r + SMAP_FUSE_PF_CLOUD) * kFRoundPts < w_pts)
+                // only lines that start inside this warp's slice (a prefetch is a hint, but it is kept in bounds anyway)
+                if (lane < kFRoundPts * 16 / 128 && (r + SMAP_FUSE_PF_CLOUD) * kFRoundPts + lane * 8 < w_pts)
                     prefetch_l2(reinterpret_cast<const char*>(gp_pts - lane) +
                                 (size_t)(r + SMAP_FUSE_PF_CLOUD) * (kFRoundPts * 16) + lane * 128);
 #endif
