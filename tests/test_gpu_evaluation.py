@@ -1,6 +1,8 @@
-"""GPU: the evaluation step -- smap_eval_counts against the numpy restatement of the reference's
-``convert_labels`` + ``Test.iou`` (test/test_semantic_mapping.py:6-18,127-161).  Integer sums, so every score must be
-the same float, not merely close."""
+"""GPU: the evaluation step -- smap_eval_counts against what the REFERENCE's own ``convert_labels`` +
+``Test.iou`` / ``test_single_map`` (test/test_semantic_mapping.py:6-18,117-161) returned, printed and raised on the
+same seeded inputs (tests/golden/eval.json, written by oracle/make_golden_eval.py from the unmodified file), and
+against the host-array form of the same functions.  Integer sums, so every score must be the same float, not merely
+close."""
 import numpy as np
 import pytest
 
@@ -37,12 +39,56 @@ def test_device_counts_match_numpy_iou(shape, truth_shape, shift, with_mask):
         counts = ev.device_counts(color_map, truth, shift[0], shift[1], mask=mask)
         ious, accs, accuracy, miss = ev.scores_from_counts(counts)
         want_ious, want_miss = host_scores(rgb, truth, shift[0], shift[1], mask)
-        assert all((a == b) or (np.isnan(a) and np.isnan(b)) for a, b in zip(ious, want_ious))
+        assert all(_same(a, b) for a, b in zip(ious, want_ious))
         assert miss == want_miss
     generated = ev.convert_labels(rgb, mask)
     gmap = truth[shift[0]:shape[0] + shift[0], shift[1]:shape[1] + shift[1]]
     assert counts[9] == int(np.sum(gmap > 0)) and counts[11] == int(np.sum((gmap == generated)[gmap > 0]))
     assert counts[6:9] == [int(np.sum(generated == k)) for k in (1, 2, 3)]
+
+
+def _dec(v):
+    return float(v) if isinstance(v, str) else v
+
+
+def _same(a, b):
+    return a == b or (a != a and b != b)
+
+
+@pytest.mark.parametrize("name", ["grid_2000", "grid_2000_mask", "small", "odd", "no_crosswalk", "no_truth",
+                                  "golden_render"])
+def test_device_counts_match_the_reference(name):
+    """smap_eval_counts -> scores == what the reference's own functions produced (tests/golden/eval.json)."""
+    import json
+    import os
+    from oracle.make_golden_eval import make_inputs
+    from tests.common import GOLDEN
+    with open(os.path.join(GOLDEN, "eval.json")) as f:
+        spec = json.load(f)["cases"][name]
+    rgb, truth, mask = make_inputs(name, spec)
+    counts = ev.device_counts(torch.from_numpy(rgb).cuda(), truth, spec["shift"][0], spec["shift"][1], mask=mask)
+    # convert_labels: the label histogram of the converted map (classes 1..3 are counted by the kernel)
+    assert counts[6:9] == spec["labels_hist"][1:4]
+    if spec.get("raises") == "ZeroDivisionError":
+        with pytest.raises(ZeroDivisionError):
+            ev.scores_from_counts(counts)
+        return
+    ious, accs, accuracy, miss = ev.scores_from_counts(counts)
+    assert all(_same(a, _dec(b)) for a, b in zip(ious, spec["iou"])), (ious, spec["iou"])
+    assert _same(miss, _dec(spec["miss"]))
+    # the accuracies only exist in the line the reference prints ('{}'.format of the float: repr, round-trips)
+    assert all(_same(a, _dec(b)) for a, b in zip(accs, spec["acc"])), (accs, spec["acc"])
+    assert _same(accuracy, _dec(spec["accuracy"]))
+    if mask is None:
+        # Test.test_single_map end to end: the very lines the reference printed
+        t = ev.Test.__new__(ev.Test)
+        t.class_lists, t.d, t.logger = [1, 2, 3], {0: "road", 1: "crosswalk", 2: "lane"}, None
+        t.shift_w, t.shift_h = spec["shift"]
+        t.ground_truth_mask, t.mask = truth, None
+        said = []
+        t._say = said.append
+        t.test_single_map(torch.from_numpy(rgb).cuda())
+        assert said == spec["printed"]
 
 
 def test_device_counts_errors():

@@ -255,4 +255,37 @@ def test_evaluation_host_functions_known_answers():
     counts = [2, 2, 1, 3, 3, 3, 3, 3, 2, 9, 8, 5]
     ious2, accs, accuracy, miss2 = ev.scores_from_counts(counts)
     assert ious2 == ious and miss2 == miss and accs == [2 / 3, 2 / 3, 1 / 3] and accuracy == 5 / 9
-    assert all(np.isnan(v) for v in ev.scores_from_counts([0] * 12)[0])
+    with pytest.raises(ZeroDivisionError):   # an empty union: the reference divides two Python floats (:140-141)
+        ev.scores_from_counts([0] * 12)
+
+
+# ---------------------------------------------------------------------------------------------- evaluation (N3)
+@pytest.mark.parametrize("name", ["grid_2000_mask", "small", "odd", "no_crosswalk", "no_truth", "golden_render"])
+def test_evaluation_host_functions_match_the_reference(name):
+    """convert_labels / Test.iou on host arrays == the reference's own functions on the same seeded inputs
+    (tests/golden/eval.json, from test/test_semantic_mapping.py:6-18,117-161 run unmodified)."""
+    import json
+    import os
+    from oracle.make_golden_eval import make_inputs
+    from tests.common import GOLDEN
+    from vision_semantic_segmentation_b200 import evaluation as ev
+    with open(os.path.join(GOLDEN, "eval.json")) as f:
+        spec = json.load(f)["cases"][name]
+    rgb, truth, mask = make_inputs(name, spec)
+    generated = ev.convert_labels(rgb, mask)
+    assert [int(np.sum(generated == k)) for k in range(6)] == spec["labels_hist"]
+    t = ev.Test.__new__(ev.Test)
+    t.class_lists, t.d, t.logger = [1, 2, 3], {0: "road", 1: "crosswalk", 2: "lane"}, None
+    said = []
+    t._say = said.append
+    gmap = truth[spec["shift"][0]:generated.shape[0] + spec["shift"][0], spec["shift"][1]:generated.shape[1] + spec["shift"][1]]
+    if spec.get("raises") == "ZeroDivisionError":
+        with pytest.raises(ZeroDivisionError):
+            t.iou(gmap, generated)
+        return
+    ious, miss = t.iou(gmap, generated, verbose=True)
+    dec = lambda v: float(v) if isinstance(v, str) else v
+    same = lambda a, b: a == b or (a != a and b != b)
+    assert all(same(a, dec(b)) for a, b in zip(ious, spec["iou"]))
+    assert same(miss, dec(spec["miss"]))
+    assert said == spec["printed"]

@@ -3,7 +3,9 @@
 Follows the reference's ``test/test_semantic_mapping.py`` (``convert_labels`` ``:6-18``, ``Test.iou``
 ``:127-161``, ``Test.test_single_map`` ``:117-125``): the rendered colour map is converted back to integer
 labels and IoU / accuracy / missing rate are reported for road, crosswalk and lane.  The reference file
-does not parse (a second ``else:`` at ``:70``); the logic below is the intended one.
+does not parse (a second ``else:`` at ``:70``), but ``convert_labels`` and the two ``Test`` methods are complete on
+their own: ``oracle/make_golden_eval.py`` slices those lines out of the unmodified file, runs them, and
+``tests/golden/eval.json`` pins this module (and ``smap_eval_counts``) to what they return, print and raise.
 
 ``Test.test_single_map`` -- what ``mapping_replay`` calls on the rendered map -- counts on the device
 (``smap_eval_counts``: colour -> label and every sum of ``iou`` in one pass over the image, integer counts, exact), so
@@ -84,16 +86,22 @@ def device_counts(color_map, truth, shift_w=0, shift_h=0, mask=None):
 
 
 def scores_from_counts(counts):
-    """(ious, accs, accuracy, miss) from the sums, with the reference's formulas (``Test.iou``)."""
+    """(ious, accs, accuracy, miss) from the sums, with the reference's formulas AND its division behaviour
+    (``Test.iou``, test/test_semantic_mapping.py:134-145): ``iou = intersection / union`` divides two Python floats, so
+    a class absent from both maps raises ``ZeroDivisionError``; the other quotients are numpy divisions (an empty
+    denominator gives nan, silently here, with numpy's RuntimeWarning in the reference).  Pinned to the reference's own
+    output by tests/golden/eval.json (oracle/make_golden_eval.py)."""
     ious, accs = [], []
-    for k in range(3):
-        inter, g, m = float(counts[k]), counts[3 + k], counts[6 + k]
-        union = float(g + m - inter)
-        ious.append(inter / union if union else float("nan"))
-        accs.append(inter / g if g else float("nan"))
-    known = counts[9]
-    miss = 1 - counts[10] / max(known, 1)
-    accuracy = counts[11] / max(known, 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for k in range(3):
+            inter = float(counts[k])
+            g, m = np.int64(counts[3 + k]), np.int64(counts[6 + k])
+            union = float(g + m - inter)
+            ious.append(inter / union)          # ZeroDivisionError on an empty union, as the reference
+            accs.append(inter / g)
+        known = np.int64(counts[9])
+        miss = 1 - np.int64(counts[10]) / known
+        accuracy = np.int64(counts[11]) / known
     return ious, accs, accuracy, miss
 
 
@@ -119,24 +127,27 @@ class Test(object):
 
     def test_single_map(self, global_map):
         """Score a rendered map (numpy or CUDA tensor, (H, W, 3)) against the ground truth; counts on the device."""
-        if getattr(self, "_truth_dev", None) is None:
-            self._truth_dev = _as_device_u8(self.ground_truth_mask, _cuda_device_of(global_map), "the ground-truth label map")
-        counts = device_counts(global_map, self._truth_dev, self.shift_w, self.shift_h)
+        dev = _cuda_device_of(global_map)
+        cache = self.__dict__.setdefault("_truth_dev", {})   # one copy of the ground truth per GPU
+        if dev not in cache:
+            cache[dev] = _as_device_u8(self.ground_truth_mask, dev, "the ground-truth label map")
+        counts = device_counts(global_map, cache[dev], self.shift_w, self.shift_h)
         ious, accs, accuracy, miss = scores_from_counts(counts)
         self._report(ious, accs, accuracy, miss)
         return ious, miss
 
     def iou(self, gmap, generate_map, latex_mode=False, verbose=False):
-        ious, accs = [], []
-        for cls in self.class_lists:
+        """Host-array form of the reference's ``Test.iou`` (label maps in, ``(iou_lists, miss)`` out): the same twelve
+        sums, taken with numpy, through the same ``scores_from_counts``."""
+        counts = [0] * 12
+        for k, cls in enumerate(self.class_lists):
             g, m = gmap == cls, generate_map == cls
-            inter = float(np.sum(g & m))
-            union = float(np.sum(g) + np.sum(m) - inter)
-            ious.append(inter / union if union else float("nan"))
-            accs.append(inter / np.sum(g) if np.sum(g) else float("nan"))
+            counts[k], counts[3 + k], counts[6 + k] = int(np.sum(g & m)), int(np.sum(g)), int(np.sum(m))
         known = gmap > 0
-        miss = 1 - np.sum(known & (generate_map > 0)) / max(np.sum(known), 1)
-        accuracy = np.sum((gmap == generate_map)[known]) / max(np.sum(known), 1)
+        counts[9] = int(np.sum(known))
+        counts[10] = int(np.sum(known & (generate_map > 0)))
+        counts[11] = int(np.sum((gmap == generate_map)[known]))
+        ious, accs, accuracy, miss = scores_from_counts(counts)
         if verbose:
             self._report(ious, accs, accuracy, miss)
         return ious, miss
