@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""TEST / BASELINE INFRASTRUCTURE ONLY -- builds ``oracle/_ref/``: the reference's own mapping modules, byte-compiled.
+
+The reference is pure Python, so "compiling it from the sources where they lie" means ``py_compile``: this recipe
+imports the UNMODIFIED reference through ``oracle/ref_shim.py`` (which stubs the absent third-party packages), notes
+every module that import pulled in from ``/root/reference``, and byte-compiles each of those files into a sourceless
+``oracle/_ref/<same relative path>.pyc``.  No reference source text is copied; the outputs are binaries, ``oracle/_ref/``
+is git-ignored (it stays out of history) but not gpurun-ignored, so it travels to the GPU box like the built ``.so``
+files.  There ``ref_shim`` imports the same modules from the ``.pyc`` tree (same interpreter: the box runs this
+image), which is what lets ``bench.py --impl reference`` and the ``cpu_baseline`` leg time the reference ITSELF
+(``cpu_baseline.kind = "reference"``) on the box's host cores.
+
+    python -m oracle.build_ref          # in the build container (needs /root/reference); __graft_entry__.build() calls it
+"""
+import os
+import py_compile
+import shutil
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+OUT = os.path.join(ROOT, "oracle", "_ref")
+SRC = "/root/reference"
+
+
+def build(force=False):
+    """Returns the list of compiled modules, or None when the reference tree is absent (GPU box: uses what was built)."""
+    if not os.path.isfile(os.path.join(SRC, "src", "mapping_replay.py")):
+        return None
+    stamp = os.path.join(OUT, "BUILT_FROM")
+    if not force and os.path.exists(stamp):
+        return open(stamp).read().split("\n")[1:]
+    os.environ["SMAP_REFERENCE_DIR"] = SRC
+    from oracle import ref_shim
+    ref_shim.REF = SRC
+    ref_shim._loaded = None
+    ref_shim.load_reference()
+    files = sorted({os.path.realpath(m.__file__) for m in list(sys.modules.values())
+                    if isinstance(m.__dict__.get("__file__"), str) and m.__file__.endswith(".py")
+                    and os.path.realpath(m.__file__).startswith(SRC + os.sep)})
+    if os.path.isdir(OUT):
+        shutil.rmtree(OUT)
+    done = []
+    for path in files:
+        rel = os.path.relpath(path, SRC)
+        dst = os.path.join(OUT, rel + "c")
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        # dfile: the path tracebacks show; it names the reference file, it does not have to exist on the box
+        py_compile.compile(path, cfile=dst, dfile=os.path.join("reference", rel), doraise=True)
+        done.append(rel)
+    with open(stamp, "w") as f:
+        f.write("byte-compiled by oracle/build_ref.py from %s (python %s)\n" % (SRC, sys.version.split()[0]))
+        f.write("\n".join(done))
+    return done
+
+
+if __name__ == "__main__":
+    mods = build(force=True)
+    print("reference tree absent: nothing built" if mods is None else "oracle/_ref: %d modules\n  " % len(mods) + "\n  ".join(mods))

@@ -36,11 +36,28 @@ import types
 
 import numpy as np
 
-REF = os.environ.get("SMAP_REFERENCE_DIR", "/root/reference")
+_BUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py: sourceless .pyc tree
+
+
+def _pick_reference():
+    env = os.environ.get("SMAP_REFERENCE_DIR")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/src/mapping_replay.py"):
+        return "/root/reference"
+    return _BUILT   # the GPU box: the byte-compiled copy that travelled with the repo snapshot
+
+
+REF = _pick_reference()
 
 
 def reference_available():
-    return os.path.isfile(os.path.join(REF, "src", "mapping_replay.py"))
+    return any(os.path.isfile(os.path.join(REF, "src", "mapping_replay" + ext)) for ext in (".py", ".pyc"))
+
+
+def reference_kind():
+    """'source' (the tree under /root/reference) or 'bytecode' (oracle/_ref, byte-compiled from it)."""
+    return "source" if os.path.isfile(os.path.join(REF, "src", "mapping_replay.py")) else "bytecode"
 
 
 # --------------------------------------------------------------------------- #
