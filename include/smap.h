@@ -32,7 +32,7 @@ extern "C" {
 #define SMAP_API
 #endif
 
-#define SMAP_ABI_VERSION 2
+#define SMAP_ABI_VERSION 3
 #define SMAP_MAX_CLASSES 31 /* C class bits + 1 intensity-boost bit in a 32-bit cell mask */
 #define SMAP_MAX_CAMERAS 8
 
@@ -42,7 +42,8 @@ enum {
     SMAP_ERR_CUDA = -2,     /* a CUDA runtime call failed */
     SMAP_ERR_NOMEM = -3,    /* allocation failed */
     SMAP_ERR_STATE = -4,    /* call order: classes / camera not set */
-    SMAP_ERR_NO_DEVICE = -5 /* no usable sm_100 device */
+    SMAP_ERR_NO_DEVICE = -5, /* no usable sm_100 device */
+    SMAP_ERR_COMM = -6       /* NCCL: library not found, or a call failed */
 };
 
 /* point-cloud layouts accepted by the kernels */
@@ -187,10 +188,20 @@ SMAP_API int smap_integrate(smap_handle *h, const smap_frame *frame, void *strea
  * smap_integrate.  Frames of one call must share a point layout. */
 SMAP_API int smap_integrate_batch(smap_handle *h, const smap_frame *frames_host, int n_frames, void *stream);
 
-/* Same as smap_integrate with HOST buffers: points (layout as in frame) and image are copied to the
- * device through the handle's staging ring inside the call (async on `stream`; pass pinned memory
- * for overlap).  frame->points_dev / image_dev hold HOST pointers here. */
+/* Same as smap_integrate with HOST buffers: frame->points_dev / image_dev hold HOST pointers here.  Points (layout as
+ * in frame) and image are copied through the handle's two-stage device ring on an INTERNAL copy stream, and the
+ * kernels -- queued on `stream` -- wait for their frame's copies only: frame i + 1 crosses PCIe while frame i is
+ * integrated, nothing synchronises the host.  Pass pinned memory (pageable memory makes cudaMemcpyAsync block) and keep
+ * the buffers unchanged until `stream` has passed this call (synchronising `stream` implies the copies are done). */
 SMAP_API int smap_integrate_host(smap_handle *h, const smap_frame *frame_with_host_ptrs, void *stream);
+
+/* The reference's cloud layout, (4, N) float64 rows with stride ld (SMAP_PTS_F64_SOA), converted on the device to the
+ * float4 layout of the fast kernel.  *flag_dev (int32, zeroed by the CALLER) is OR-ed with 1 when some coordinate or
+ * intensity is not float32-representable -- the caller then keeps the float64 layout for that cloud, so results never
+ * change.  PointCloud2 fields are FLOAT32 (src/mapping.py:178-180 copies them into a float64 buffer): recorded clouds
+ * normally convert losslessly. */
+SMAP_API int smap_cloud_to_f32x4(const double *soa_dev, int64_t ld, int64_t n_points, void *out_f32x4_dev,
+                                 int32_t *flag_dev, int device, void *stream);
 
 /* ---- rendering: free functions of src/renderer.py, any grid ------------------------------------ */
 /* apply_filter: cv2.filter2D 3x3 box, BORDER_REFLECT_101 (src/renderer.py:175-189). src != dst. */
@@ -219,6 +230,46 @@ SMAP_API int smap_render_thresholds(const double *map_dev, int mh, int mw, int c
 SMAP_API int smap_eval_counts(const uint8_t *rgb_dev, int mh, int mw, const uint8_t *truth_dev, int truth_rows,
                      int truth_cols, int shift_rows, int shift_cols, const uint8_t *mask_dev, int mask_rows,
                      int mask_cols, int64_t *counts_dev, int device, void *stream);
+
+/* ---- multi-GPU: frames sharded over the ranks, grids summed ------------------------
+ * update_map only ever ADDS frame-determined constants to the grid (src/mapping_replay.py:281,294), so the ranks of
+ * a job integrate disjoint blocks of frames into their own full-size grids and sum them once.  One handle per GPU /
+ * process; NCCL is resolved at run time (the libnccl.so.2 already loaded in the process, else the loader's; override
+ * with the environment variable SMAP_NCCL_LIB), so single-GPU users never need it.
+ *
+ * The exchange moves only the union window of the cells any rank touched since its last smap_clear (tracked on the
+ * device by the update kernels), and a grid of counts (count update: small non-negative integers) travels packed --
+ * two uint16 per word while the global sum provably stays below 2^16 (3 per integrated frame), else uint32 -- which
+ * is EXACT and 4x / 2x fewer bytes than float64; log-likelihood grids travel as float64 (summation order across
+ * ranks differs from the sequential reference: <= 1e-5 relative by north_star, ~1e-15 in practice). */
+#define SMAP_COMM_ID_BYTES 128
+typedef struct smap_comm_info {
+    int32_t n_ranks, rank;
+    int32_t window[4];   /* last exchange: rows window[0]..window[1], columns window[2]..window[3] (empty: [1] < [0]) */
+    int32_t pack;        /* last exchange: 0 = uint16 pairs, 1 = uint32, 2 = float64 */
+    int32_t reserved;
+    int64_t bytes;       /* last exchange: payload bytes this rank handed to NCCL */
+    int64_t grid_bytes;  /* size of the whole float64 grid, for comparison */
+    int64_t exchanges;   /* exchanges so far */
+} smap_comm_info;
+/* rank 0: a fresh NCCL unique id, to be distributed to all ranks by the caller (MPI, torch.distributed, a file...). */
+SMAP_API int smap_comm_unique_id(uint8_t id_out[SMAP_COMM_ID_BYTES]);
+/* Collective over all ranks: creates the handle's communicator (ncclCommInitRank on the handle's device). */
+SMAP_API int smap_comm_init(smap_handle *h, int n_ranks, int rank, const uint8_t id[SMAP_COMM_ID_BYTES]);
+/* Or: use an ncclComm_t the caller owns (passed as void*; not destroyed by the handle). */
+SMAP_API int smap_comm_attach(smap_handle *h, void *nccl_comm);
+SMAP_API int smap_comm_destroy(smap_handle *h);
+/* Collective: every rank's grid becomes the sum of all ranks' grids.  Enqueues on `stream` but SYNCHRONISES it once
+ * (the ranks first agree on the window with an 8-int all-reduce whose result sizes the exchange). */
+SMAP_API int smap_allreduce(smap_handle *h, void *stream);
+/* Collective, for maps too large to filter / render on every rank: the summed grid is scattered by rows.  With
+ * per = ceil(MH / n_ranks), rank r receives rows [r0, r1) = [r per, min((r+1) per, MH)) plus one halo row from each
+ * neighbouring tile (top / bottom = 0 or 1), written to tile_dev as (top + r1 - r0 + bottom, MW, C) float64 (rows in
+ * grid order; tile_rows_cap >= per + 2 is enough); the handle's own grid is left as it was.  The 3x3 filter of the
+ * tile then sees real neighbours across the seams and BORDER_REFLECT_101 only at true map edges. */
+SMAP_API int smap_reduce_scatter_rows(smap_handle *h, double *tile_dev, int64_t tile_rows_cap, int32_t *r0, int32_t *r1,
+                                      int32_t *top, int32_t *bottom, void *stream);
+SMAP_API int smap_comm_get_info(smap_handle *h, smap_comm_info *out);
 
 /* ---- grid access ------------------------------------------------------------------------------- */
 SMAP_API int smap_map_ptr(smap_handle *h, double **map_dev, int64_t *n_elements);

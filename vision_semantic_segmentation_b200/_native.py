@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMAP_LIB_PATH") or os.path.join(_HERE, "csrc", "libsmap_b200.so")  # env: kernel-variant sweeps
 
-ABI_VERSION = 2   # SMAP_ABI_VERSION of include/smap.h this binding was written against
+ABI_VERSION = 3   # SMAP_ABI_VERSION of include/smap.h this binding was written against
 SMAP_PTS_F32X4 = 0
 SMAP_PTS_F64_SOA = 1
 SMAP_IMG_RGB = 0
@@ -23,8 +23,11 @@ EXPORTS = [
     "smap_destroy", "smap_set_camera", "smap_set_classes", "smap_set_label_palette", "smap_project", "smap_update", "smap_integrate",
     "smap_integrate_batch", "smap_integrate_host", "smap_apply_filter", "smap_render", "smap_filter_render",
     "smap_render_thresholds", "smap_eval_counts", "smap_map_ptr", "smap_clear", "smap_notify_map_modified", "smap_download", "smap_upload", "smap_get_stats", "smap_set_profiling", "smap_debug_set_frame_tag", "smap_debug_fast32",
-    "smap_debug_nearest_map",
+    "smap_debug_nearest_map", "smap_cloud_to_f32x4",
+    "smap_comm_unique_id", "smap_comm_init", "smap_comm_attach", "smap_comm_destroy", "smap_allreduce",
+    "smap_reduce_scatter_rows", "smap_comm_get_info",
 ]
+SMAP_COMM_ID_BYTES = 128
 
 
 class SmapConfig(ctypes.Structure):
@@ -51,6 +54,12 @@ class SmapStats(ctypes.Structure):
     _fields_ = [("frames", ctypes.c_int64), ("points", ctypes.c_int64), ("touched_cells", ctypes.c_int64),
                 ("kernel_launches", ctypes.c_int64), ("profiled_frames", ctypes.c_int64),
                 ("stream_kernel_ms", ctypes.c_double), ("apply_kernel_ms", ctypes.c_double)]
+
+
+class SmapCommInfo(ctypes.Structure):
+    _fields_ = [("n_ranks", ctypes.c_int32), ("rank", ctypes.c_int32), ("window", ctypes.c_int32 * 4),
+                ("pack", ctypes.c_int32), ("reserved", ctypes.c_int32), ("bytes", ctypes.c_int64),
+                ("grid_bytes", ctypes.c_int64), ("exchanges", ctypes.c_int64)]
 
 
 class SmapError(RuntimeError):
@@ -136,6 +145,23 @@ def load():
     L.smap_upload.argtypes = [vp, vp]
     L.smap_get_stats.restype = i32
     L.smap_get_stats.argtypes = [vp, ctypes.POINTER(SmapStats)]
+    L.smap_cloud_to_f32x4.restype = i32
+    L.smap_cloud_to_f32x4.argtypes = [vp, i64, i64, vp, vp, i32, vp]
+    L.smap_comm_unique_id.restype = i32
+    L.smap_comm_unique_id.argtypes = [vp]
+    L.smap_comm_init.restype = i32
+    L.smap_comm_init.argtypes = [vp, i32, i32, vp]
+    L.smap_comm_attach.restype = i32
+    L.smap_comm_attach.argtypes = [vp, vp]
+    L.smap_comm_destroy.restype = i32
+    L.smap_comm_destroy.argtypes = [vp]
+    L.smap_allreduce.restype = i32
+    L.smap_allreduce.argtypes = [vp, vp]
+    L.smap_reduce_scatter_rows.restype = i32
+    L.smap_reduce_scatter_rows.argtypes = [vp, vp, i64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp]
+    L.smap_comm_get_info.restype = i32
+    L.smap_comm_get_info.argtypes = [vp, ctypes.POINTER(SmapCommInfo)]
     _lib = L
     return L
 

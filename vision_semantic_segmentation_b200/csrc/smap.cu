@@ -11,6 +11,7 @@
 #include "../../include/smap.h"
 #include "smap_kernels.cuh"
 #include "smap_fuse.cuh"
+#include "smap_comm.cuh"
 
 #ifndef SMAP_AUX_STREAMS
 #define SMAP_AUX_STREAMS 4      // internal streams the per-frame k_fuse launches of a batch alternate over
@@ -21,9 +22,6 @@
 #ifndef SMAP_FUSE_GRID_DIV
 #define SMAP_FUSE_GRID_DIV 2    // > 1: inside a batch a frame's launch fills only 1/DIV of the resident block slots, so
 #endif                          // that the launches of DIV frames (on different internal streams) run side by side
-#ifndef SMAP_FUSE_PERSISTENT
-#define SMAP_FUSE_PERSISTENT 0  // 1: one persistent k_fuse launch per batch (measured alternative, see smap_fuse.cuh)
-#endif
 
 using namespace smap;
 
@@ -91,8 +89,23 @@ struct smap_handle {
     cudaStream_t aux[kAux > 0 ? kAux : 1] = {};
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_join[kAux > 0 ? kAux : 1] = {};
-    FuseBatchT<1> fuse_one;               // parameter block of the next k_fuse launch
-    FuseBatchT<kMaxBatch> fuse_batch;     // the same for the persistent variant (about 14 KB)
+    FuseLaunch fuse_one;                  // parameter block of the next k_fuse launch
+    // union window of every cell touched since the last clear (device; maintained by k_fuse / k_apply / k_clear_masks):
+    // what a multi-GPU exchange has to move.  ubox_full: the grid was written from outside, assume all of it.
+    FrameBox* ubox = nullptr;
+    bool ubox_full = false;
+    int64_t value_bound = 0;              // no grid element exceeds this while integer_grid holds (3 per frame)
+    // multi-GPU exchange (smap_comm_* / smap_allreduce / smap_reduce_scatter_rows)
+    ncclComm_t comm = nullptr;
+    bool own_comm = false;
+    int n_ranks = 1, rank = 0;
+    void* xbuf = nullptr;                 // packed window
+    size_t xbuf_cap = 0;
+    void* xbuf2 = nullptr;                // reduce-scatter: the received tile, all-gather of the halo rows
+    size_t xbuf2_cap = 0;
+    int* xch_dev = nullptr;               // kCommWords ints the ranks agree on before an exchange
+    int* xch_host = nullptr;              // pinned
+    smap_comm_info comm_last = {};
     // class tables
     double* cm_dev = nullptr;
     uint8_t colors[SMAP_MAX_CLASSES * 3];
@@ -126,6 +139,8 @@ struct smap_handle {
     size_t stage_pts_cap[kStages] = {};
     size_t stage_img_cap[kStages] = {};
     cudaEvent_t stage_done[kStages] = {};
+    cudaEvent_t stage_copied[kStages] = {};
+    cudaStream_t copy_stream = nullptr;
     int stage_next = 0;
     // profiling (smap_set_profiling): three events per smap_integrate_batch chunk, harvested lazily
     bool profiling = false;
@@ -429,7 +444,7 @@ int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st)
     unsigned long long* ntt = h->touched + (h->parity ^ 1);
     const unsigned grid = (unsigned)h->sm_count * 8;
     const int lane = h->cfg.lane_index, mw = h->cfg.map_width;
-#define SMAP_LAUNCH_APPLY(NJ) k_apply<NJ><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->cm_dev, c, lane, mw)
+#define SMAP_LAUNCH_APPLY(NJ) k_apply<NJ><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->ubox, h->cm_dev, c, lane, mw)
     if (c <= 8) SMAP_LAUNCH_APPLY(1);
     else if (c <= 16) SMAP_LAUNCH_APPLY(2);
     else if (c <= 24) SMAP_LAUNCH_APPLY(3);
@@ -450,7 +465,7 @@ int launch_clear(smap_handle* h, int n_slots_used, cudaStream_t st) {
     const dim3 grid((unsigned)h->sm_count, kMaxBatch);
     k_clear_masks<<<grid, kThreads, 0, st>>>(ap, h->boxes + (size_t)h->parity * kMaxBatch,
                                              h->boxes + (size_t)(h->parity ^ 1) * kMaxBatch, h->touched + (h->parity ^ 1),
-                                             h->cfg.map_width);
+                                             h->ubox, h->cfg.map_width);
     CK(cudaGetLastError());
     h->parity ^= 1;
     h->stats.kernel_launches += 1;
@@ -575,19 +590,29 @@ int ensure_nearest_map(smap_handle* h, int W, int H, int w, int hh) {
 inline int ids_w(const smap_frame* f) { return f->ids_width > 0 ? f->ids_width : f->image_width; }
 inline int ids_h(const smap_frame* f) { return f->ids_height > 0 ? f->ids_height : f->image_height; }
 
-int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp, int mode, int slot, FuseFrame& f) {
+// Everything about the float4 frames of a chunk that can be checked WITHOUT launching anything: run for the whole
+// chunk before its first launch, so that a bad frame never leaves half a batch integrated (mask slots and boxes are
+// only consistent between complete batches).
+int validate_fuse_frame(const smap_handle* h, const smap_frame* fr) {
     if (fr->layout != SMAP_PTS_F32X4) return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
-    if ((int64_t)fr->image_width * fr->image_height >= ((int64_t)1 << kFidShift))
+    if ((int64_t)fr->image_width * fr->image_height >= ((int64_t)1 << 28))
         return fail(SMAP_ERR_INVALID, "label image has 2^28 pixels or more");
+    if (fr->n_points >= ((int64_t)1 << 40)) return fail(SMAP_ERR_INVALID, "cloud too large for one launch");
+    if (fr->image_format == SMAP_IMG_CLASS_IDS) {
+        if (!h->palette_set) return fail(SMAP_ERR_STATE, "class-id plane without a palette (smap_set_label_palette)");
+        const int64_t w = fr->ids_width > 0 ? fr->ids_width : fr->image_width;
+        const int64_t hh = fr->ids_height > 0 ? fr->ids_height : fr->image_height;
+        if (w * hh >= ((int64_t)1 << 28)) return fail(SMAP_ERR_INVALID, "class-id plane has 2^28 pixels or more");
+    }
+    return SMAP_OK;
+}
+
+int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp, int mode, int slot, FuseFrame& f) {
     f.nn_tab = nullptr;
     f.nn_mx = f.nn_my = f.nn_sx = f.nn_sy = 0;
     f.src_w = fr->image_width;
-    f.pf_bytes = 0;
-    f.pf_image = nullptr;
+    f.pad = 0;
     if (fr->image_format == SMAP_IMG_CLASS_IDS) {
-        if (!h->palette_set) return fail(SMAP_ERR_STATE, "class-id plane without a palette (smap_set_label_palette)");
-        if ((int64_t)ids_w(fr) * ids_h(fr) >= ((int64_t)1 << kFidShift))
-            return fail(SMAP_ERR_INVALID, "class-id plane has 2^28 pixels or more");
         int rc = ensure_nearest_map(h, fr->image_width, fr->image_height, ids_w(fr), ids_h(fr));
         if (rc) return rc;
         f.nn_tab = h->nn.use_tab ? h->nn.tab_dev : nullptr;
@@ -606,83 +631,56 @@ int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp,
     return SMAP_OK;
 }
 
-// persistent grid: as many blocks as stay resident, never more than the largest cloud has block-rounds
-int fuse_grid(const smap_handle* h, FuseFrame* f, int n, int div, int64_t* gx_out) {
-    int64_t n_max = 0;
-    for (int k = 0; k < n; ++k) n_max = f[k].n > n_max ? f[k].n : n_max;
+// persistent grid: as many blocks as stay resident, never more than the cloud has block-rounds
+int64_t fuse_grid(const smap_handle* h, FuseFrame* f, int div) {
     int64_t gx = (int64_t)h->sm_count * SMAP_FUSE_MINB / div;
-    const int64_t rounds = ceil_div(n_max, kFBlockRoundPts);
+    const int64_t rounds = ceil_div(f->n, kFBlockRoundPts);
     if (gx > rounds) gx = rounds;
-    for (int k = 0; k < n; ++k) {
-        const int64_t per = ceil_div(f[k].n, gx * kFWarps);
-        if (per >= ((int64_t)1 << 31)) return fail(SMAP_ERR_INVALID, "cloud too large for one launch");
-        f[k].per_warp = (int32_t)per;
-    }
-    *gx_out = gx;
-    return SMAP_OK;
+    if (gx < 1) gx = 1;
+    f->per_warp = (int32_t)ceil_div(f->n, gx * kFWarps);   // n < 2^40 (validate_fuse_frame): fits
+    return gx;
 }
 
-// Queue the float4 frames of a batch.  Count update: nothing else to do afterwards; otherwise frame i of the
-// non-empty ones scatters into mask slot i and *slots_used tells k_apply how many there are.
+template <int MODE, int FMT>
+cudaError_t set_fuse_smem() {
+    return cudaFuncSetAttribute(k_fuse<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(MODE));
+}
+
+template <int MODE, int FMT>
+void launch_k_fuse(const FuseLaunch& fb, const GridParams& gp, FrameBox* boxes, double* map, int64_t gx, cudaStream_t ls) {
+    k_fuse<MODE, FMT><<<(unsigned)gx, kFThreads, fuse_block_smem(MODE), ls>>>(fb, gp, boxes, map);
+}
+
+// Queue the float4 frames of a batch (validated by the caller), one launch per frame, alternating over the internal
+// streams (fork / join with events around the batch).  Count update: nothing else to do afterwards; otherwise frame i
+// of the non-empty ones scatters into mask slot i and *slots_used tells k_apply / k_clear_masks how many there are.
+// The join is queued even when a launch fails, and *slots_used is valid then too, so that the caller can restore the
+// "slots all zero between batches" invariant before it reports the error.
 // mode: 0 ordered update (masks, k_apply afterwards), 1 count update with tags, 2 count update through the masks
 // (k_clear_masks afterwards)
 int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps, int n_frames, int mode,
                 cudaStream_t st, int* slots_used) {
     int used = 0;
+    *slots_used = 0;
     const bool count_atomics = mode == 1;
     if (count_atomics) {
-        int rc = ensure_tags(h, SMAP_FUSE_PERSISTENT ? kMaxBatch : (smap_handle::kAux > 0 ? smap_handle::kAux : 1));
+        int rc = ensure_tags(h, smap_handle::kAux > 0 ? smap_handle::kAux : 1);
         if (rc) return rc;
-        if (h->frame_tag > 0xffffffffu - (uint32_t)n_frames - 1u) {   // tag space exhausted: start over
+    }
+    {
+        // the tag counter is advanced by every launch, whatever the mode: start over before it can wrap
+        if (h->frame_tag > 0xffffffffu - (uint32_t)n_frames - 1u) {
             CK(cudaDeviceSynchronize());
-            CK(cudaMemset(h->tags, 0, sizeof(uint32_t) * (size_t)h->cells * (size_t)(h->cfg.num_classes + 1) * h->n_tag_planes));
+            if (h->tags)
+                CK(cudaMemset(h->tags, 0, sizeof(uint32_t) * (size_t)h->cells * (size_t)(h->cfg.num_classes + 1) * h->n_tag_planes));
             h->frame_tag = 0;
         }
     }
-    if (!h->fuse_attr_set) {   // the per-warp TMA stages + stacks need more than the default 48 KB
-        CK(cudaFuncSetAttribute(k_fuse<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
-        CK(cudaFuncSetAttribute(k_fuse<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
-        CK(cudaFuncSetAttribute(k_fuse<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
-        CK(cudaFuncSetAttribute(k_fuse<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
-        CK(cudaFuncSetAttribute(k_fuse<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
-        CK(cudaFuncSetAttribute(k_fuse<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(1)));
-        CK(cudaFuncSetAttribute(k_fuse<2, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
-        CK(cudaFuncSetAttribute(k_fuse<0, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
-        CK(cudaFuncSetAttribute(k_fuse<1, kMaxBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_block_smem(kMaxBatch)));
+    if (!h->fuse_attr_set) {   // the per-warp stacks need more than the default 48 KB per block
+        CK((set_fuse_smem<0, 0>())); CK((set_fuse_smem<1, 0>())); CK((set_fuse_smem<2, 0>()));
+        CK((set_fuse_smem<0, 1>())); CK((set_fuse_smem<1, 1>())); CK((set_fuse_smem<2, 1>()));
         h->fuse_attr_set = true;
     }
-#if SMAP_FUSE_PERSISTENT
-    const int per_launch = mode == 1 ? h->n_tag_planes : kMaxBatch;
-    FuseBatchT<kMaxBatch>* fb = &h->fuse_batch;
-    int i = 0;
-    while (i < n_frames) {
-        int in_launch = 0;
-        const int first_slot = used;
-        for (; i < n_frames && in_launch < per_launch; ++i) {
-            if (frames[i].n_points == 0) continue;
-            if (frames[i].image_format != SMAP_IMG_RGB) return fail(SMAP_ERR_INVALID, "class-id planes: not in the persistent-launch build");
-            int rc = fill_fuse_frame(h, frames + i, fps[i], mode, used, fb->f[in_launch]);
-            if (rc) return rc;
-            ++in_launch;
-            ++used;
-        }
-        if (in_launch == 0) break;
-        int64_t gx = 0;
-        int rc = fuse_grid(h, fb->f, in_launch, 1, &gx);
-        if (rc) return rc;
-        fb->tags = count_atomics ? h->tags : nullptr;
-        fb->id_lut = nullptr;
-        fb->n_frames = in_launch;
-        fb->tag_planes = h->n_tag_planes > 0 ? h->n_tag_planes : 1;
-        FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + first_slot;
-        if (mode == 1) k_fuse<1, kMaxBatch><<<(unsigned)gx, kFThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
-        else if (mode == 2) k_fuse<2, kMaxBatch><<<(unsigned)gx, kFThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
-        else k_fuse<0, kMaxBatch><<<(unsigned)gx, kFThreads, fuse_block_smem(kMaxBatch), st>>>(*fb, h->gp, boxes, h->map);
-        CK(cudaGetLastError());
-        h->stats.kernel_launches += 1;
-    }
-#else
-    // one launch per frame, alternating over the internal streams (fork / join with events around the batch)
     int n_nonempty = 0;
     for (int i = 0; i < n_frames; ++i) n_nonempty += frames[i].n_points > 0;
     const bool fork = smap_handle::kAux > 0 && n_nonempty > 1 && !h->profiling;
@@ -698,59 +696,41 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         for (int a = 0; a < smap_handle::kAux; ++a) CK(cudaStreamWaitEvent(h->aux[a], h->ev_fork, 0));
     }
     const size_t plane_words = (size_t)h->cells * (size_t)(h->cfg.num_classes + 1);
-    FuseBatchT<1>* fb = &h->fuse_one;
-    for (int i = 0; i < n_frames; ++i) {
+    FuseLaunch* fb = &h->fuse_one;
+    int rc = SMAP_OK;
+    for (int i = 0; i < n_frames && !rc; ++i) {
         if (frames[i].n_points == 0) continue;
         // tagged count update: never more streams than tag planes (two frames on one plane must not overlap)
         const int n_streams = (mode == 1 && h->n_tag_planes < smap_handle::kAux) ? h->n_tag_planes : smap_handle::kAux;
         const int lane_stream = fork ? used % n_streams : 0;
         cudaStream_t ls = fork ? h->aux[lane_stream] : st;
-        int rc = fill_fuse_frame(h, frames + i, fps[i], mode, used, fb->f[0]);
-        if (rc) return rc;
-#if SMAP_FUSE_PF_IMAGE
-        {   // the label image of the second non-empty frame after this one (the next one runs beside this launch)
-            int seen = 0;
-            for (int k = i + 1; k < n_frames && fork; ++k) {
-                if (frames[k].n_points == 0 || ++seen < 2) continue;
-                const smap_frame& nx = frames[k];
-                fb->f[0].pf_image = nx.image_dev;
-                fb->f[0].pf_bytes = nx.image_format == SMAP_IMG_CLASS_IDS
-                                        ? (uint32_t)((int64_t)ids_w(&nx) * ids_h(&nx))
-                                        : (uint32_t)((int64_t)nx.image_width * nx.image_height * 3);
-                break;
-            }
-        }
-#endif
-        int64_t gx = 0;
-        rc = fuse_grid(h, fb->f, 1, fork ? SMAP_FUSE_GRID_DIV : 1, &gx);
-        if (rc) return rc;
+        rc = fill_fuse_frame(h, frames + i, fps[i], mode, used, fb->f);
+        if (rc) break;
+        const int64_t gx = fuse_grid(h, &fb->f, fork ? SMAP_FUSE_GRID_DIV : 1);
         // one tag plane per launching stream; a frame's tag is larger than every tag written to its plane before
         fb->tags = count_atomics ? h->tags + plane_words * (size_t)lane_stream : nullptr;
-        fb->n_frames = 1;
-        fb->tag_planes = 1;
-        FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch + used;
         fb->id_lut = h->id_lut_dev;
-        if (frames[i].image_format == SMAP_IMG_CLASS_IDS) {
-            if (mode == 1) k_fuse<1, 1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
-            else if (mode == 2) k_fuse<2, 1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
-            else k_fuse<0, 1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
-        }
-        else if (mode == 1) k_fuse<1, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
-        else if (mode == 2) k_fuse<2, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
-        else k_fuse<0, 1><<<(unsigned)gx, kFThreads, fuse_block_smem(1), ls>>>(*fb, h->gp, boxes, h->map);
-        CK(cudaGetLastError());
+        // mode 1: the union window itself; otherwise the frame's own box (folded into the window by k_apply / k_clear_masks)
+        FrameBox* boxes = mode == 1 ? h->ubox : h->boxes + (size_t)h->parity * kMaxBatch + used;
+        const bool ids = frames[i].image_format == SMAP_IMG_CLASS_IDS;
+        if (mode == 1) ids ? launch_k_fuse<1, 1>(*fb, h->gp, boxes, h->map, gx, ls) : launch_k_fuse<1, 0>(*fb, h->gp, boxes, h->map, gx, ls);
+        else if (mode == 2) ids ? launch_k_fuse<2, 1>(*fb, h->gp, boxes, h->map, gx, ls) : launch_k_fuse<2, 0>(*fb, h->gp, boxes, h->map, gx, ls);
+        else ids ? launch_k_fuse<0, 1>(*fb, h->gp, boxes, h->map, gx, ls) : launch_k_fuse<0, 0>(*fb, h->gp, boxes, h->map, gx, ls);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = fail(SMAP_ERR_CUDA, "k_fuse launch: %s", cudaGetErrorString(e)); break; }
         h->stats.kernel_launches += 1;
         ++used;
     }
+    *slots_used = used;
     if (fork) {
         for (int a = 0; a < smap_handle::kAux; ++a) {
-            CK(cudaEventRecord(h->ev_join[a], h->aux[a]));
-            CK(cudaStreamWaitEvent(st, h->ev_join[a], 0));
+            if (cudaEventRecord(h->ev_join[a], h->aux[a]) != cudaSuccess || cudaStreamWaitEvent(st, h->ev_join[a], 0) != cudaSuccess) {
+                cudaGetLastError();
+                if (!rc) rc = fail(SMAP_ERR_CUDA, "joining the internal streams failed");
+            }
         }
     }
-#endif
-    *slots_used = used;
-    return SMAP_OK;
+    return rc;
 }
 
 int harvest_profile(smap_handle* h) {
@@ -782,12 +762,100 @@ int launch_render(const double* map, int mh, int mw, int c, const uint8_t* color
     RenderColors rc;
     memset(&rc, 0, sizeof rc);
     if (colors_host) memcpy(rc.rgb, colors_host, (size_t)c * 3);
-    dim3 grid((unsigned)ceil_div(mw, kTileX), (unsigned)ceil_div(mh, kTileY));
-    size_t smem = FILTER ? sizeof(double) * (size_t)(kTileY + 2) * (kTileX + 2) * c : 0;
-    if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_render<FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_render<FILTER><<<grid, kTileX * kTileY, smem, st>>>(map, mh, mw, c, rc, rgb, filtered);
+    const int cs = c | 1;                                    // cells padded to an odd number of doubles in shared memory
+    const uint32_t div_c = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)c - 1) / (uint64_t)c);   // umulhi(e, div_c) = e / c, e < 2^16
+    // fewer than 8 classes: strips of 4 cells, one running class sum; otherwise strips of 2 and numpy's eight partial sums
+    const bool small = c < 8;
+    const int r = small ? 4 : 2;
+    const size_t smem = render_smem_bytes(FILTER, r, cs);
+    dim3 grid((unsigned)ceil_div(mw, kRX), (unsigned)ceil_div(mh, render_tile_rows(r)));
+    if (grid.y > 65535u) return fail(SMAP_ERR_INVALID, "grid has too many rows for the render kernel");
+    if (small) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_render<FILTER, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_render<FILTER, 4, 1><<<grid, kRThreads, smem, st>>>(map, mh, mw, c, cs, div_c, rc, rgb, filtered);
+    } else {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_render<FILTER, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_render<FILTER, 2, 8><<<grid, kRThreads, smem, st>>>(map, mh, mw, c, cs, div_c, rc, rgb, filtered);
+    }
     CK(cudaGetLastError());
+    return SMAP_OK;
+}
+
+#define NCCLCK(expr)                                                                                     \
+    do {                                                                                                 \
+        ncclResult_t r__ = (expr);                                                                       \
+        if (r__ != ncclSuccess) return fail(SMAP_ERR_COMM, "%s: %s", #expr, nccl_api().GetErrorString(r__)); \
+    } while (0)
+
+int ensure_bytes(void** buf, size_t* cap, size_t need) {
+    if (need <= *cap) return SMAP_OK;
+    if (*buf) { CK(cudaDeviceSynchronize()); cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    const size_t want = need + need / 8 + 256;
+    CK(cudaMalloc(buf, want));
+    *cap = want;
+    return SMAP_OK;
+}
+
+// The ranks agree on the exchange: union window, value bound, integer or not (element-wise MAX of kCommWords ints).
+// Synchronises `st` (the host sizes the NCCL calls from the result).
+int comm_agree(smap_handle* h, cudaStream_t st, int out[kCommWords]) {
+    NcclApi& N = nccl_api();
+    const int vb = h->value_bound > 0x7fffffffll ? 0x7fffffff : (int)h->value_bound;
+    k_comm_prep<<<1, 32, 0, st>>>(h->ubox, h->ubox_full ? 1 : 0, h->cfg.map_height, h->cfg.map_width, vb,
+                                  h->integer_grid ? 0 : 1, h->xch_dev);
+    CK(cudaGetLastError());
+    NCCLCK(N.AllReduce(h->xch_dev, h->xch_dev, kCommWords, ncclInt32, ncclMax, h->comm, st));
+    CK(cudaMemcpyAsync(h->xch_host, h->xch_dev, sizeof(int) * kCommWords, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < kCommWords; ++i) out[i] = h->xch_host[i];
+    return SMAP_OK;
+}
+
+int pick_pack(const smap_handle* h, const int agreed[kCommWords], int64_t* bound_total) {
+    *bound_total = (int64_t)h->n_ranks * (int64_t)agreed[4];
+    if (agreed[5]) return kPackF64;
+    if (*bound_total < 65536) return kPackU16;
+    if (*bound_total < ((int64_t)1 << 32)) return kPackU32;
+    return kPackF64;
+}
+
+inline dim3 window_grid(int units, int rows) {
+    int gx = (int)ceil_div(units, (int64_t)kThreads * 4);
+    if (gx < 1) gx = 1;
+    if (gx > 32) gx = 32;
+    return dim3((unsigned)gx, (unsigned)rows);
+}
+
+// rows [row0, row0 + rows) of the packed buffer <- grid rows of the same index, columns [y0, y0 + cols);
+// grid rows outside [wx0, wx1] are written as zeros
+int launch_pack(const smap_handle* h, int pack, int row0, int rows, int wx0, int wx1, int y0, int cols, void* out,
+                cudaStream_t st) {
+    const int c = h->cfg.num_classes, run = cols * c, run_words = pack == kPackU16 ? (run + 1) / 2 : run;
+    const size_t row_bytes = pack == kPackF64 ? (size_t)run * 8 : (size_t)run_words * 4;
+    for (int done = 0; done < rows; done += 32768) {
+        const int n = rows - done < 32768 ? rows - done : 32768;
+        void* o = static_cast<char*>(out) + (size_t)done * row_bytes;
+        const dim3 g = window_grid(pack == kPackU16 ? run_words : run, n);
+        if (pack == kPackU16) k_pack_window<kPackU16><<<g, kThreads, 0, st>>>(h->map, wx0, wx1, h->cfg.map_width, c, row0 + done, y0, run, run_words, o);
+        else if (pack == kPackU32) k_pack_window<kPackU32><<<g, kThreads, 0, st>>>(h->map, wx0, wx1, h->cfg.map_width, c, row0 + done, y0, run, run_words, o);
+        else k_pack_window<kPackF64><<<g, kThreads, 0, st>>>(h->map, wx0, wx1, h->cfg.map_width, c, row0 + done, y0, run, run_words, o);
+        CK(cudaGetLastError());
+    }
+    return SMAP_OK;
+}
+
+// rows [dst_row0, dst_row0 + rows) of a (*, dst_mw, C) float64 array <- rows [src_row0, ...) of the packed buffer
+int launch_unpack(const smap_handle* h, int pack, double* dst, int dst_mw, int dst_row0, int rows, int y0, int cols,
+                  const void* in, int src_row0, cudaStream_t st) {
+    const int c = h->cfg.num_classes, run = cols * c, run_words = pack == kPackU16 ? (run + 1) / 2 : run;
+    for (int done = 0; done < rows; done += 32768) {
+        const int n = rows - done < 32768 ? rows - done : 32768;
+        const dim3 g = window_grid(pack == kPackU16 ? run_words : run, n);
+        if (pack == kPackU16) k_unpack_window<kPackU16><<<g, kThreads, 0, st>>>(dst, dst_mw, c, dst_row0 + done, y0, run, run_words, in, src_row0 + done);
+        else if (pack == kPackU32) k_unpack_window<kPackU32><<<g, kThreads, 0, st>>>(dst, dst_mw, c, dst_row0 + done, y0, run, run_words, in, src_row0 + done);
+        else k_unpack_window<kPackF64><<<g, kThreads, 0, st>>>(dst, dst_mw, c, dst_row0 + done, y0, run, run_words, in, src_row0 + done);
+        CK(cudaGetLastError());
+    }
     return SMAP_OK;
 }
 
@@ -869,12 +937,15 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->slot_words);
     if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->slot_words);
     if (e == cudaSuccess) h->n_slots = 1;
-    if (e == cudaSuccess) e = cudaMalloc(&h->boxes, sizeof(FrameBox) * 2 * kMaxBatch);
+    if (e == cudaSuccess) e = cudaMalloc(&h->boxes, sizeof(FrameBox) * (2 * kMaxBatch + 1));
     if (e == cudaSuccess) {
-        FrameBox init[2 * kMaxBatch];
-        for (int i = 0; i < 2 * kMaxBatch; ++i) { init[i].x0 = 0x7fffffff; init[i].x1 = -1; init[i].y0 = 0x7fffffff; init[i].y1 = -1; }
+        FrameBox init[2 * kMaxBatch + 1];
+        for (int i = 0; i < 2 * kMaxBatch + 1; ++i) { init[i].x0 = 0x7fffffff; init[i].x1 = -1; init[i].y0 = 0x7fffffff; init[i].y1 = -1; }
         e = cudaMemcpy(h->boxes, init, sizeof init, cudaMemcpyHostToDevice);
+        h->ubox = h->boxes + 2 * kMaxBatch;
     }
+    // a caller-owned grid that is not declared zero may hold anything anywhere
+    h->ubox_full = cfg->map_dev && !cfg->map_is_zero;
     if (e == cudaSuccess) e = cudaMalloc(&h->touched, sizeof(unsigned long long) * 2);
     if (e == cudaSuccess) e = cudaMemset(h->touched, 0, sizeof(unsigned long long) * 2);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -899,6 +970,9 @@ int smap_destroy(smap_handle* h) {
     if (h->own_map) cudaFree(h->map);
     cudaFree(h->mask); cudaFree(h->tags); cudaFree(h->boxes); cudaFree(h->touched); cudaFree(h->cm_dev); cudaFree(h->total_dev);
     cudaFree(h->id_lut_dev); cudaFree(h->nn.tab_dev);
+    if (h->comm && h->own_comm && nccl_api().lib) nccl_api().CommDestroy(h->comm);
+    cudaFree(h->xbuf); cudaFree(h->xbuf2); cudaFree(h->xch_dev);
+    if (h->xch_host) cudaFreeHost(h->xch_host);
     cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
     if (h->ev_fork) {
         cudaEventDestroy(h->ev_fork);
@@ -911,7 +985,9 @@ int smap_destroy(smap_handle* h) {
         cudaFree(h->stage_pts[i]);
         cudaFree(h->stage_img[i]);
         if (h->stage_done[i]) cudaEventDestroy(h->stage_done[i]);
+        if (h->stage_copied[i]) cudaEventDestroy(h->stage_copied[i]);
     }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaGetLastError();
     delete h;
     return SMAP_OK;
@@ -1007,7 +1083,10 @@ int smap_update(smap_handle* h, double* map_dev, const double* pcd, int64_t ld, 
     CK(cudaGetLastError());
     h->stats.kernel_launches += 1;
     h->last_stream = st;
-    if (!map_dev || map_dev == h->map) h->integer_grid = h->integer_grid && h->identity_cm;
+    if (!map_dev || map_dev == h->map) {
+        h->integer_grid = h->integer_grid && h->identity_cm;
+        h->value_bound += 3;
+    }
     h->last_update_counted = true;
     return launch_apply(h, map_dev ? map_dev : h->map, 1, st);
 }
@@ -1022,13 +1101,24 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
     FrameParams fps[kMaxBatch];
     for (int begin = 0; begin < n_frames;) {
         const int chunk = (n_frames - begin < kMaxBatch) ? n_frames - begin : kMaxBatch;
+        // ---- validate the whole chunk before anything is launched: a bad frame must not leave half a batch behind
+        int first = -1;   // the first non-empty frame decides the kernel (empty frames carry no layout that matters)
         for (int i = 0; i < chunk; ++i) {
             int rc = fill_frame_params(h, frames + begin + i, fps[i]);
             if (rc) return rc;
-            h->stats.frames += 1;
-            h->stats.points += frames[begin + i].n_points;
+            if (first < 0 && frames[begin + i].n_points > 0) first = i;
         }
-        const bool f4 = frames[begin].layout == SMAP_PTS_F32X4;
+        const bool f4 = first < 0 || frames[begin + first].layout == SMAP_PTS_F32X4;
+        for (int i = 0; i < chunk; ++i) {
+            const smap_frame* fr = frames + begin + i;
+            if (fr->n_points == 0) continue;
+            if (f4) {
+                int rc = validate_fuse_frame(h, fr);
+                if (rc) return rc;
+            } else if (fr->layout != SMAP_PTS_F64_SOA) {
+                return fail(SMAP_ERR_INVALID, "frames of one batch must share a point layout");
+            }
+        }
         // the count update on a grid of integer-valued counts may add its increments with float64 atomics (exact
         // in any order): de-duplicated with per-(cell, class) frame tags when there are few classes, through the
         // per-frame cell masks otherwise; everything else goes through the ordered apply
@@ -1037,25 +1127,34 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
         const int mode = !count_atomics ? 0 : (h->cfg.num_classes + 1 <= SMAP_TAG_MAX_PLANES ? 1 : 2);
         if (!h->identity_cm) h->integer_grid = false;
         int rc = mode == 1 ? SMAP_OK : ensure_slots(h, chunk);
+        if (rc) return rc;
         int used = 0;
         smap_handle::ProfRec* pr = nullptr;
-        if (!rc && h->profiling) {
+        if (h->profiling) {
             if (h->n_prof_pending == 64) rc = harvest_profile(h);
-            if (!rc) {
-                pr = &h->prof_pending[h->n_prof_pending++];
-                pr->frames = 0;
-                for (int k = 0; k < 3; ++k) CK(cudaEventCreate(&pr->e[k]));
-                CK(cudaEventRecord(pr->e[0], st));
-            }
+            if (rc) return rc;
+            pr = &h->prof_pending[h->n_prof_pending++];
+            pr->frames = 0;
+            for (int k = 0; k < 3; ++k) CK(cudaEventCreate(&pr->e[k]));
+            CK(cudaEventRecord(pr->e[0], st));
         }
-        if (!rc) rc = f4 ? launch_fuse(h, frames + begin, fps, chunk, mode, st, &used)
-                         : launch_stream(h, frames + begin, fps, chunk, st, &used);
-        if (pr) { pr->frames = used; CK(cudaEventRecord(pr->e[1], st)); }
-        if (!rc && used > 0 && mode == 0) rc = launch_apply(h, h->map, used, st);
-        if (!rc && used > 0 && mode == 2) rc = launch_clear(h, used, st);
+        rc = f4 ? launch_fuse(h, frames + begin, fps, chunk, mode, st, &used)
+                : launch_stream(h, frames + begin, fps, chunk, st, &used);
+        if (pr) { pr->frames = used; cudaEventRecord(pr->e[1], st); }
+        // also after a failed launch: the frames queued so far are applied / their slots cleared, so that the slots are
+        // all zero and the boxes reset when the call returns (the error is still reported)
+        int rc2 = SMAP_OK;
+        if (used > 0 && mode == 0) rc2 = launch_apply(h, h->map, used, st);
+        if (used > 0 && mode == 2) rc2 = launch_clear(h, used, st);
         h->last_update_counted = mode == 0;
-        if (pr) CK(cudaEventRecord(pr->e[2], st));
+        if (pr) cudaEventRecord(pr->e[2], st);
+        for (int i = 0; i < chunk; ++i) {
+            h->stats.frames += 1;
+            h->stats.points += frames[begin + i].n_points;
+        }
+        h->value_bound += 3 * (int64_t)used;
         if (rc) return rc;
+        if (rc2) return rc2;
         begin += chunk;
     }
     return SMAP_OK;
@@ -1071,14 +1170,23 @@ int smap_integrate_host(smap_handle* h, const smap_frame* f, void* stream) {
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (f->n_points < 0 || f->image_width <= 0 || f->image_height <= 0) return fail(SMAP_ERR_INVALID, "bad frame sizes");
+    if (f->layout != SMAP_PTS_F32X4 && f->layout != SMAP_PTS_F64_SOA) return fail(SMAP_ERR_INVALID, "unknown point layout");
     const size_t pts_bytes = f->layout == SMAP_PTS_F32X4 ? (size_t)f->n_points * 16 : (size_t)f->ld * 4 * sizeof(double);
     const size_t img_bytes = f->image_format == SMAP_IMG_CLASS_IDS ? (size_t)ids_w(f) * (size_t)ids_h(f)
                                                                    : (size_t)f->image_width * f->image_height * 3;
+    if (f->n_points > 0 && (!f->points_dev || !f->image_dev)) return fail(SMAP_ERR_INVALID, "NULL points / image");
     const int s = h->stage_next;
     h->stage_next = (s + 1) % smap_handle::kStages;
-    if (!h->stage_done[s]) CK(cudaEventCreateWithFlags(&h->stage_done[s], cudaEventDisableTiming));
-    // the kernels of the frame that last used this stage must be finished before it is overwritten
-    CK(cudaStreamWaitEvent(st, h->stage_done[s], 0));
+    if (!h->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < smap_handle::kStages; ++i) {
+            CK(cudaEventCreateWithFlags(&h->stage_done[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->stage_copied[i], cudaEventDisableTiming));
+        }
+    }
+    // The copies run on an internal stream: frame i + 1 crosses PCIe while frame i's kernel runs on `stream`.  The
+    // kernels of the frame that last used this stage must be finished before it is overwritten.
+    CK(cudaStreamWaitEvent(h->copy_stream, h->stage_done[s], 0));
     if (pts_bytes > h->stage_pts_cap[s]) {
         CK(cudaEventSynchronize(h->stage_done[s]));
         cudaFree(h->stage_pts[s]);
@@ -1093,14 +1201,53 @@ int smap_integrate_host(smap_handle* h, const smap_frame* f, void* stream) {
         CK(cudaMalloc(&h->stage_img[s], img_bytes));
         h->stage_img_cap[s] = img_bytes;
     }
-    if (pts_bytes) CK(cudaMemcpyAsync(h->stage_pts[s], f->points_dev, pts_bytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->stage_img[s], f->image_dev, img_bytes, cudaMemcpyHostToDevice, st));
+    if (pts_bytes) CK(cudaMemcpyAsync(h->stage_pts[s], f->points_dev, pts_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(h->stage_img[s], f->image_dev, img_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->stage_copied[s], h->copy_stream));
+    CK(cudaStreamWaitEvent(st, h->stage_copied[s], 0));
     smap_frame dev = *f;
     dev.points_dev = h->stage_pts[s];
     dev.image_dev = h->stage_img[s];
     int rc = smap_integrate(h, &dev, stream);
-    if (rc) return rc;
+    // recorded even after a failed launch: the stage must become reusable
     CK(cudaEventRecord(h->stage_done[s], st));
+    return rc;
+}
+
+// The reference's own cloud layout -> the float4 layout of the fast kernel, with the check that makes it legal:
+// PointCloud2 fields are FLOAT32 (src/mapping.py:178-180 fills a float64 buffer from them), so the (4, N) float64
+// rows of a recorded frame normally hold float32-representable values and the conversion loses nothing; *flag is
+// raised (atomicOr 1) when some value is not, and the caller keeps the float64 path for that cloud.
+__global__ void __launch_bounds__(kThreads)
+k_soa_to_f32x4(const double* __restrict__ soa, int64_t ld, int64_t n, float4* __restrict__ out, int* __restrict__ flag) {
+    bool bad = false;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double x = __ldcs(soa + k), y = __ldcs(soa + ld + k), z = __ldcs(soa + 2 * ld + k), w = __ldcs(soa + 3 * ld + k);
+        const float4 p = make_float4((float)x, (float)y, (float)z, (float)w);
+        // NaN stays NaN (dropped by either kernel, as by the reference); everything else must survive the round trip
+        bad |= !(((double)p.x == x) | (x != x)) | !(((double)p.y == y) | (y != y)) | !(((double)p.z == z) | (z != z)) |
+               !(((double)p.w == w) | (w != w));
+        out[k] = p;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+int smap_cloud_to_f32x4(const double* soa_dev, int64_t ld, int64_t n_points, void* out_f32x4_dev, int32_t* flag_dev,
+                        int device, void* stream) {
+    if (n_points < 0 || ld < n_points) return fail(SMAP_ERR_INVALID, "bad point count / stride");
+    if (n_points > 0 && (!soa_dev || !out_f32x4_dev)) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (!flag_dev) return fail(SMAP_ERR_INVALID, "NULL flag");
+    if (reinterpret_cast<uintptr_t>(out_f32x4_dev) & 15u) return fail(SMAP_ERR_INVALID, "float4 cloud must be 16-byte aligned");
+    if (n_points == 0) return SMAP_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(SMAP_ERR_CUDA, "cudaSetDevice failed");
+    int sms = 148;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    int64_t grid = ceil_div(n_points, kThreads);
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    k_soa_to_f32x4<<<(unsigned)grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        soa_dev, ld, n_points, static_cast<float4*>(out_f32x4_dev), flag_dev);
+    CK(cudaGetLastError());
     return SMAP_OK;
 }
 
@@ -1166,6 +1313,10 @@ int smap_clear(smap_handle* h, void* stream) {
     if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
     DeviceGuard guard(h->cfg.device);
     CK(cudaMemsetAsync(h->map, 0, sizeof(double) * (size_t)h->cells * h->cfg.num_classes, static_cast<cudaStream_t>(stream)));
+    k_box_set<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->ubox, 0x7fffffff, -1, 0x7fffffff, -1);
+    CK(cudaGetLastError());
+    h->ubox_full = false;
+    h->value_bound = 0;
     h->stats.frames = 0;
     h->stats.points = 0;
     h->integer_grid = true;
@@ -1266,6 +1417,7 @@ int smap_debug_nearest_map(int dst, int src, uint16_t* tab_out, uint32_t* mul, u
 int smap_notify_map_modified(smap_handle* h) {
     if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
     h->integer_grid = false;
+    h->ubox_full = true;
     return SMAP_OK;
 }
 
@@ -1283,6 +1435,197 @@ int smap_upload(smap_handle* h, const double* map_host) {
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h->map, map_host, sizeof(double) * (size_t)h->cells * h->cfg.num_classes, cudaMemcpyHostToDevice));
     h->integer_grid = false;
+    h->ubox_full = true;
+    return SMAP_OK;
+}
+
+
+// ---- multi-GPU exchange --------------------------------------------------------------------------------------------
+int smap_comm_unique_id(uint8_t id_out[SMAP_COMM_ID_BYTES]) {
+    if (!id_out) return fail(SMAP_ERR_INVALID, "NULL argument");
+    static_assert(SMAP_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "smap.h and nccl.h disagree about the id size");
+    NcclApi& N = nccl_api();
+    if (!N.load()) return fail(SMAP_ERR_COMM, "libnccl.so.2 not found (set SMAP_NCCL_LIB)");
+    ncclUniqueId id;
+    NCCLCK(N.GetUniqueId(&id));
+    memcpy(id_out, id.internal, SMAP_COMM_ID_BYTES);
+    return SMAP_OK;
+}
+
+static int comm_scratch(smap_handle* h) {
+    if (!h->xch_dev) CK(cudaMalloc(&h->xch_dev, sizeof(int) * kCommWords));
+    if (!h->xch_host) CK(cudaHostAlloc(&h->xch_host, sizeof(int) * kCommWords, cudaHostAllocDefault));
+    return SMAP_OK;
+}
+
+int smap_comm_init(smap_handle* h, int n_ranks, int rank, const uint8_t id[SMAP_COMM_ID_BYTES]) {
+    if (!h || !id) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(SMAP_ERR_INVALID, "bad rank / n_ranks");
+    if (h->comm) return fail(SMAP_ERR_STATE, "the handle already has a communicator (smap_comm_destroy first)");
+    NcclApi& N = nccl_api();
+    if (!N.load()) return fail(SMAP_ERR_COMM, "libnccl.so.2 not found (set SMAP_NCCL_LIB)");
+    DeviceGuard guard(h->cfg.device);
+    int rc = comm_scratch(h);
+    if (rc) return rc;
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, SMAP_COMM_ID_BYTES);
+    NCCLCK(N.CommInitRank(&h->comm, n_ranks, uid, rank));
+    h->own_comm = true;
+    h->n_ranks = n_ranks;
+    h->rank = rank;
+    return SMAP_OK;
+}
+
+int smap_comm_attach(smap_handle* h, void* nccl_comm) {
+    if (!h || !nccl_comm) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (h->comm) return fail(SMAP_ERR_STATE, "the handle already has a communicator (smap_comm_destroy first)");
+    NcclApi& N = nccl_api();
+    if (!N.load()) return fail(SMAP_ERR_COMM, "libnccl.so.2 not found (set SMAP_NCCL_LIB)");
+    DeviceGuard guard(h->cfg.device);
+    int rc = comm_scratch(h);
+    if (rc) return rc;
+    ncclComm_t c = static_cast<ncclComm_t>(nccl_comm);
+    int n = 0, r = 0;
+    NCCLCK(N.CommCount(c, &n));
+    NCCLCK(N.CommUserRank(c, &r));
+    h->comm = c;
+    h->own_comm = false;
+    h->n_ranks = n;
+    h->rank = r;
+    return SMAP_OK;
+}
+
+int smap_comm_destroy(smap_handle* h) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    if (h->comm && h->own_comm) {
+        DeviceGuard guard(h->cfg.device);
+        cudaDeviceSynchronize();
+        NCCLCK(nccl_api().CommDestroy(h->comm));
+    }
+    h->comm = nullptr;
+    h->own_comm = false;
+    h->n_ranks = 1;
+    h->rank = 0;
+    return SMAP_OK;
+}
+
+int smap_comm_get_info(smap_handle* h, smap_comm_info* out) {
+    if (!h || !out) return fail(SMAP_ERR_INVALID, "NULL argument");
+    *out = h->comm_last;
+    out->n_ranks = h->n_ranks;
+    out->rank = h->rank;
+    out->grid_bytes = (int64_t)sizeof(double) * h->cells * h->cfg.num_classes;
+    return SMAP_OK;
+}
+
+int smap_allreduce(smap_handle* h, void* stream) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    if (!h->comm) return fail(SMAP_ERR_STATE, "no communicator (smap_comm_init / smap_comm_attach)");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    h->last_stream = st;
+    NcclApi& N = nccl_api();
+    int ag[kCommWords];
+    int rc = comm_agree(h, st, ag);
+    if (rc) return rc;
+    const int x0 = -ag[0], x1 = ag[1], y0 = -ag[2], y1 = ag[3];
+    int64_t bound_total = 0;
+    const int pack = pick_pack(h, ag, &bound_total);
+    h->comm_last.window[0] = x0; h->comm_last.window[1] = x1; h->comm_last.window[2] = y0; h->comm_last.window[3] = y1;
+    h->comm_last.pack = pack;
+    h->comm_last.bytes = 0;
+    h->comm_last.exchanges += 1;
+    if (ag[5]) h->integer_grid = false;          // some rank holds non-integer values: so will every rank's sum
+    h->value_bound = bound_total;
+    if (x1 < x0 || y1 < y0) return SMAP_OK;      // nobody touched anything
+    const int rows = x1 - x0 + 1, cols = y1 - y0 + 1, c = h->cfg.num_classes;
+    const int64_t run = (int64_t)cols * c;
+    if (run >= ((int64_t)1 << 31)) return fail(SMAP_ERR_INVALID, "grid row too long for the packed exchange");
+    const int64_t run_words = pack == kPackU16 ? (run + 1) / 2 : run;
+    const size_t count = (size_t)rows * (size_t)(pack == kPackF64 ? run : run_words);
+    const size_t bytes = count * (pack == kPackF64 ? 8 : 4);
+    rc = ensure_bytes(&h->xbuf, &h->xbuf_cap, bytes);
+    if (rc) return rc;
+    rc = launch_pack(h, pack, x0, rows, x0, x1, y0, cols, h->xbuf, st);
+    if (rc) return rc;
+    NCCLCK(N.AllReduce(h->xbuf, h->xbuf, count, pack == kPackF64 ? ncclFloat64 : ncclUint32, ncclSum, h->comm, st));
+    rc = launch_unpack(h, pack, h->map, h->cfg.map_width, x0, rows, y0, cols, h->xbuf, 0, st);
+    if (rc) return rc;
+    // every rank now holds the total inside the window, and only there
+    k_box_set<<<1, 32, 0, st>>>(h->ubox, x0, x1, y0, y1);
+    CK(cudaGetLastError());
+    h->ubox_full = false;
+    h->comm_last.bytes = (int64_t)bytes;
+    h->stats.kernel_launches += 3;
+    return SMAP_OK;
+}
+
+int smap_reduce_scatter_rows(smap_handle* h, double* tile_dev, int64_t tile_rows_cap, int32_t* r0_out, int32_t* r1_out,
+                             int32_t* top_out, int32_t* bottom_out, void* stream) {
+    if (!h || !tile_dev || !r0_out || !r1_out || !top_out || !bottom_out) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (!h->comm) return fail(SMAP_ERR_STATE, "no communicator (smap_comm_init / smap_comm_attach)");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    h->last_stream = st;
+    NcclApi& N = nccl_api();
+    const int mh = h->cfg.map_height, mw = h->cfg.map_width, c = h->cfg.num_classes, n = h->n_ranks;
+    const int per = (mh + n - 1) / n;
+    const int r0 = h->rank * per < mh ? h->rank * per : mh;
+    const int r1 = (h->rank + 1) * per < mh ? (h->rank + 1) * per : mh;
+    const int top = (r0 > 0 && r1 > r0) ? 1 : 0, bottom = (r1 < mh && r1 > r0) ? 1 : 0;
+    if (tile_rows_cap < (int64_t)(r1 - r0) + top + bottom) return fail(SMAP_ERR_INVALID, "tile too small (per + 2 rows are enough)");
+    *r0_out = r0; *r1_out = r1; *top_out = top; *bottom_out = bottom;
+    int ag[kCommWords];
+    int rc = comm_agree(h, st, ag);
+    if (rc) return rc;
+    const int x0 = -ag[0], x1 = ag[1], y0 = -ag[2], y1 = ag[3];
+    int64_t bound_total = 0;
+    const int pack = pick_pack(h, ag, &bound_total);
+    h->comm_last.window[0] = x0; h->comm_last.window[1] = x1; h->comm_last.window[2] = y0; h->comm_last.window[3] = y1;
+    h->comm_last.pack = pack;
+    h->comm_last.bytes = 0;
+    h->comm_last.exchanges += 1;
+    const int tile_rows = r1 - r0 + top + bottom;
+    if (tile_rows > 0) CK(cudaMemsetAsync(tile_dev, 0, sizeof(double) * (size_t)tile_rows * mw * c, st));
+    if (x1 < x0 || y1 < y0) return SMAP_OK;
+    const int cols = y1 - y0 + 1;
+    const int64_t run = (int64_t)cols * c;
+    if (run >= ((int64_t)1 << 31)) return fail(SMAP_ERR_INVALID, "grid row too long for the packed exchange");
+    const int64_t run_words = pack == kPackU16 ? (run + 1) / 2 : run;
+    const size_t row_count = (size_t)(pack == kPackF64 ? run : run_words);
+    const size_t esize = pack == kPackF64 ? 8 : 4;
+    const ncclDataType_t dt = pack == kPackF64 ? ncclFloat64 : ncclUint32;
+    // send buffer: per * n rows (the grid padded with zero rows), window columns; afterwards reused for the halo rows
+    size_t need = (size_t)per * n * row_count * esize;
+    if (need < (size_t)2 * n * row_count * esize) need = (size_t)2 * n * row_count * esize;
+    rc = ensure_bytes(&h->xbuf, &h->xbuf_cap, need);
+    if (rc) return rc;
+    rc = ensure_bytes(&h->xbuf2, &h->xbuf2_cap, (size_t)(per + 2) * row_count * esize);
+    if (rc) return rc;
+    rc = launch_pack(h, pack, 0, per * n, x0, x1, y0, cols, h->xbuf, st);
+    if (rc) return rc;
+    NCCLCK(N.ReduceScatter(h->xbuf, h->xbuf2, (size_t)per * row_count, dt, ncclSum, h->comm, st));
+    // halo exchange: everybody publishes the first and the last row of its tile (rows of an empty tile: whatever)
+    char* own = static_cast<char*>(h->xbuf2);
+    char* edge = own + (size_t)per * row_count * esize;
+    const int last = r1 > r0 ? r1 - r0 - 1 : 0;
+    CK(cudaMemcpyAsync(edge, own, row_count * esize, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(edge + row_count * esize, own + (size_t)last * row_count * esize, row_count * esize, cudaMemcpyDeviceToDevice, st));
+    NCCLCK(N.AllGather(edge, h->xbuf, 2 * row_count, dt, h->comm, st));
+    if (top) {   // last row of the tile above
+        rc = launch_unpack(h, pack, tile_dev, mw, 0, 1, y0, cols, h->xbuf, 2 * ((r0 - 1) / per) + 1, st);
+        if (rc) return rc;
+    }
+    if (r1 > r0) {
+        rc = launch_unpack(h, pack, tile_dev, mw, top, r1 - r0, y0, cols, h->xbuf2, 0, st);
+        if (rc) return rc;
+    }
+    if (bottom) {   // first row of the tile below
+        rc = launch_unpack(h, pack, tile_dev, mw, top + (r1 - r0), 1, y0, cols, h->xbuf, 2 * (r1 / per), st);
+        if (rc) return rc;
+    }
+    h->comm_last.bytes = (int64_t)((size_t)per * n * row_count * esize);
+    h->stats.kernel_launches += 4;
     return SMAP_OK;
 }
 

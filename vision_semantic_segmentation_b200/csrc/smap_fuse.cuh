@@ -22,6 +22,11 @@
 //                 certified  <=>  |us - RN(us)| < 1/2 - g   (implies |q2~| > 4 E_2, see smap.cu)
 //   range         |d~ - vx_ref| <= E_d(rho);  certified inside  <=>  |d~ - R/2| < R/2 - E_d
 //   cell          ts = fma(xl, fl32(1/res), f0) ~ gx_ref - I0 - 1/2,  |ts - ...| <= 3.5 u rho / res + c
+//
+// Variants measured and NOT kept (numbers in profiles/r1*_ncu_summary.md, profiles/r2_sweep*.log; the code is in the
+// history up to commit cf06422): a per-warp TMA stage ring for the cloud, one persistent launch per batch, launches
+// with blockIdx.y = frame, register-carried software pipelines of the label loads / atomics, L2 / L1 prefetch hints
+// for the label image, the cloud and the records' label bytes.
 // ------------------------------------------------------------------------------------------------
 #pragma once
 #include "smap_kernels.cuh"
@@ -29,8 +34,7 @@
 namespace smap {
 
 // Per-frame constants of the float32 path.  float2 members are operand pairs of the packed FFMA2 / FADD2
-// instructions (two rows per instruction); as kernel parameters they live in the constant bank and reach the
-// packed instructions through uniform registers.
+// instructions (two rows per instruction); as kernel parameters they live in the constant bank.
 struct Fast32 {
     // ---- conservative cull, world coordinates: rows {velodyne x, q2} and {q0, q1}, columns x, y, z, 1
     float2 c_dc[4];
@@ -62,13 +66,13 @@ struct Fast32 {
 
 constexpr float kMagic32 = 12582912.0f;   // 1.5 * 2^23: adding it rounds |t| < 2^22 to the nearest integer
 
-// One frame of a batch.
+// One frame = one launch: every per-frame constant below is a kernel parameter at a fixed offset of the constant bank.
 struct FuseFrame {
     FrameParams fp;        // float64 constants (deferred points only)
     Fast32 fk;
     const float4* pts;
     const uint8_t* image;
-    uint32_t* mask;        // MODE 0: this frame's mask slot
+    uint32_t* mask;        // MODE 0 / 2: this frame's mask slot
     int64_t n;
     int32_t per_warp;      // points per warp: ceil(n / (gridDim.x * kFWarps)), computed by the host
     int32_t img64;         // label image readable with aligned 8-byte loads (base aligned, size a multiple of 8)
@@ -81,8 +85,7 @@ struct FuseFrame {
     uint32_t nn_mx, nn_my; // nn(u) = (u * nn_mx) >> nn_sx when nn_tab == nullptr
     uint32_t nn_sx, nn_sy;
     int32_t src_w;
-    uint32_t pf_bytes;     // SMAP_FUSE_PF_IMAGE: size of the label image at pf_image (0: nothing to prefetch)
-    const uint8_t* pf_image;   // SMAP_FUSE_PF_IMAGE: label image of a LATER frame of the batch, pulled into L2 by this launch
+    int32_t pad;
 };
 
 // Index of the label byte(s) of camera pixel (iu, iv): the pixel itself for an RGB image, the nearest-neighbour source
@@ -104,27 +107,12 @@ __device__ __forceinline__ uint32_t label_index(const FuseFrame& F, uint32_t iu,
     return sy * (uint32_t)F.src_w + sx;
 }
 
-// Kernel parameter of k_fuse<MODE, NF>: the NF frames a launch walks.
-//   NF == 1          one launch per frame (on alternating internal streams, so that the ramp-up and tail of one
-//                    launch overlap the next one's body); every per-frame constant then sits at a fixed offset of the
-//                    constant bank.  This is what the library uses (13.4 us / frame on the benchmark workload; 17.2
-//                    at the time of the comparison below).
-//   NF == kMaxBatch  ONE persistent launch walks all the frames of a batch: frame f + 1's cloud is already in flight
-//                    while frame f's last survivors are decided, records and deferred points carry their frame
-//                    index, nothing is flushed between frames.  Kept as a measured alternative (SMAP_FUSE_PERSISTENT):
-//                    18.4 - 19.0 us / frame -- the run-time frame index turns every constant operand into an indexed LDC,
-//                    which costs more than the per-launch ramp it saves.  (A third variant, one launch per batch with
-//                    frame = blockIdx.y, measured 21.4 us / frame.)
-template <int NF>
-struct FuseBatchT {
-    FuseFrame f[NF];
-    uint32_t* tags;        // MODE 1: (cells * (C + 1), tag_planes) uint32; frame f of the launch uses plane f
+// Kernel parameter of k_fuse.
+struct FuseLaunch {
+    FuseFrame f;
+    uint32_t* tags;           // MODE 1: this launch's tag plane, cells * (C + 1) uint32
     const uint32_t* id_lut;   // FMT 1: class bits of the 256 class ids (palette x cfg.LABEL_COLORS, folded by the host)
-    int32_t n_frames;
-    int32_t tag_planes;    // plane stride (>= n_frames)
 };
-
-constexpr int kFidShift = 28;   // a record's pixel index carries the frame index above bit 28
 
 #ifndef SMAP_FUSE_ROUND
 #define SMAP_FUSE_ROUND 2
@@ -140,20 +128,12 @@ constexpr int kFWarps = kFThreads / 32;
 constexpr int kFRound = SMAP_FUSE_ROUND;
 constexpr int kFRoundPts = 32 * kFRound;
 constexpr int kFBlockRoundPts = kFWarps * kFRoundPts;
-#ifndef SMAP_FUSE_GROUP
-#define SMAP_FUSE_GROUP SMAP_FUSE_ROUND   // chunks culled back to back (unrolled) before the survivor stack is looked at
-#endif
-constexpr int kFGroup = SMAP_FUSE_GROUP;
-static_assert(kFRound % kFGroup == 0, "a round is a whole number of groups");
-#if !defined(SMAP_FUSE_TMA) || !SMAP_FUSE_TMA
-static_assert(kFGroup == kFRound, "the register-prefetch path culls a whole round before it looks at the stack");
-#endif
-constexpr int kFQueueCap = 32 * kFGroup + 32;      // survivor stack: < 32 left over + one group
+constexpr int kFQueueCap = 32 * kFRound + 32;      // survivor stack: < 32 left over + one round
 constexpr int kFDeferCap = 64;
 constexpr uint32_t kNone = 0xffffffffu;
 
 #ifdef SMAP_FUSE_STATS   // diagnostic builds only (tools/fuse_stats.py): how the points were routed
-__device__ unsigned long long g_fuse_stats[4];   // survivors of the cull, deferred to float64, float32-accepted, unused
+__device__ unsigned long long g_fuse_stats[4];   // survivors of the cull, deferred to float64, float32-accepted, updates
 #endif
 
 // The conservative cull: false only when the reference rule is CERTAIN to drop the point.
@@ -173,16 +153,11 @@ __device__ __forceinline__ bool cull32(const Fast32& k, float x, float y, float 
 
 // A deferred point: the float64 certified path (fast_project / fast_cell, exact chain behind them).  Returns
 // {pixel index, cell index}; cell == kNone: dropped.  About 3 % of the cull's survivors come here.
-// Inlined on purpose: with one frame per launch `fp` and `gp` are kernel parameters at fixed offsets, so the float64
-// instructions take their constants straight from the constant bank; behind a call they were ~40 dependent generic
-// loads per point.  Only the exact chains (a few points per 10 000) stay out of line.
+// Inlined on purpose: `fp` and `gp` are kernel parameters at fixed offsets, so the float64 instructions take their
+// constants straight from the constant bank; behind a call they were ~40 dependent generic loads per point.  Only
+// the exact chains (a few points per 10 000) stay out of line.
 template <int FMT>
-#ifdef SMAP_FUSE_DECIDE64_CALL
-__device__ __noinline__
-#else
-__device__ __forceinline__
-#endif
-uint2 fuse_decide64(const FuseFrame& F, const GridParams& gp, float4 w) {
+__device__ __forceinline__ uint2 fuse_decide64(const FuseFrame& F, const GridParams& gp, float4 w) {
     const FrameParams& fp = F.fp;
     const double x = (double)w.x, y = (double)w.y, z = (double)w.z;
     const bool coords_ok = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fabsf(w.z)) < (float)kCoordBound;
@@ -202,72 +177,24 @@ uint2 fuse_decide64(const FuseFrame& F, const GridParams& gp, float4 w) {
                       (uint32_t)cx * (uint32_t)gp.mw + (uint32_t)cy);
 }
 
-// ---- TMA (bulk async copy) + mbarrier plumbing of the per-warp cloud pipeline
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0u;
-}
-// (the bulk copies themselves -- cp.async.bulk global -> shared, 16-byte granular, completion counted in bytes on
-// the stage's mbarrier, evict-first in L2 because the cloud is read once -- are issued inline in k_fuse)
-
-// How the cloud reaches the cull.  Default: the next round is prefetched into registers with plain LDG.128 while the
-// current one is processed.  -DSMAP_FUSE_TMA=1: a private ring of SMAP_FUSE_STAGES shared-memory stages per warp filled
-// by TMA bulk copies (cp.async.bulk + mbarrier complete_tx, L2 evict-first), one LDS.128 per point.  Both keep one
-// round per warp in flight; the TMA ring costs 52 instructions of round set-up per 64 points (elect, expect_tx,
-// descriptor operands through uniform registers, try_wait) against 25 for the register prefetch, and its stages push
-// the block over a shared-memory carve-out step: 15.3 vs 14.5 us / frame (profiles/r1_sweep27.log).
-#ifndef SMAP_FUSE_TMA
-#define SMAP_FUSE_TMA 0
-#endif
-#ifndef SMAP_FUSE_STAGES
-#define SMAP_FUSE_STAGES 2
-#endif
-constexpr int kFStages = SMAP_FUSE_TMA ? SMAP_FUSE_STAGES : 0;
-// Experiments prepared from the stall samples of profiles/r1k_stall_breakdown.md (both off by default, not yet measured):
-//   SMAP_FUSE_PF_IMAGE=1   every launch pulls the label image of the frame that will run after the one running beside
-//                          it into L2 (one prefetch.global.L2 per lane at kernel start): the label gather then waits
-//                          for L2 instead of DRAM, and the image costs sequential lines instead of scattered sectors
-//   SMAP_FUSE_PF_CLOUD=D   lanes 0..7 prefetch the 1 KB of round r + D into L2 (D >= 2; round r + 1 is already on its
-//                          way into registers): cull-only rounds are shorter than the DRAM latency
-//   SMAP_FUSE_PF_LABEL=1|2 a record's label bytes are prefetched (1: into L2, 2: into L1) when the float32 decision
-//                          pushes the record, one to two passes before the gather loads them (+1 instruction per
-//                          batch of 32 survivors)
-#ifndef SMAP_FUSE_PF_LABEL
-#define SMAP_FUSE_PF_LABEL 0
-#endif
-#ifndef SMAP_FUSE_PF_IMAGE
-#define SMAP_FUSE_PF_IMAGE 0
-#endif
-#ifndef SMAP_FUSE_PF_CLOUD
-#define SMAP_FUSE_PF_CLOUD 0
-#endif
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
 #ifndef SMAP_FUSE_GATHER
 #define SMAP_FUSE_GATHER 2
 #endif
-constexpr int kFGather = SMAP_FUSE_GATHER;         // records per lane in one label-lookup + update pass
+#ifndef SMAP_FUSE_UPDATE
+#define SMAP_FUSE_UPDATE 1
+#endif
+constexpr int kFGather = SMAP_FUSE_GATHER;         // records per lane in one label-lookup pass
+constexpr int kFUpdate = SMAP_FUSE_UPDATE;         // updates per lane in one tag + add pass (MODE 1)
 constexpr int kFRecCap = 32 * kFGather + 64;       // record stack: < 32 * kFGather left over + 32 (float32) + 32 (float64)
-// dynamic shared memory of k_fuse, per warp: kFStages cloud stages, the survivor stack, the deferred stack, the
-// record stack, the deferred points' frame indices, the stages' mbarriers; then the two colour tables of the block
-// (the deferred points' frame indices are only needed when a launch walks several frames.)  Keeping this small
-// matters beyond occupancy: the unified L1 / shared memory is carved in steps, and a block size that pushes the SM
-// from the 196 KB to the 228 KB carve-out (28 KB of L1 left) costs 20 % on the label gather.
-__host__ __device__ constexpr int fuse_warp_smem(int nf) {
-    return (kFStages * kFRoundPts + kFQueueCap + kFDeferCap) * 16 + kFRecCap * 8 + (nf > 1 ? kFDeferCap : 0) +
-           (kFStages * 8 + 15) / 16 * 16;
+constexpr int kFUpdCap = 32 * kFUpdate + 32 * kFGather;   // update stack: < 32 * kFUpdate left over + one lookup pass
+// dynamic shared memory of k_fuse, per warp: the survivor stack, the deferred stack, the record stack, the update
+// stack; then the two colour tables of the block.  Keeping this small matters beyond occupancy: the unified L1 /
+// shared memory is carved in steps, and a block size that pushes the SM from the 196 KB to the 228 KB carve-out
+// (28 KB of L1 left) cost 20 % in round 1.
+__host__ __device__ constexpr int fuse_warp_smem(int mode) {
+    return (kFQueueCap + kFDeferCap) * 16 + kFRecCap * 8 + (mode == 1 ? kFUpdCap * 8 : 0);
 }
-__host__ __device__ constexpr int fuse_block_smem(int nf) { return kFWarps * fuse_warp_smem(nf) + 2 * 256 * 4; }
+__host__ __device__ constexpr int fuse_block_smem(int mode) { return kFWarps * fuse_warp_smem(mode) + 2 * 256 * 4; }
 
 // ------------------------------------------------------------------------------------------------
 // MODE 0: masks only (RED.OR into the frame's slot, bounding box) -- k_apply replays the frames in order.
@@ -276,146 +203,100 @@ __host__ __device__ constexpr int fuse_block_smem(int nf) { return kFWarps * fus
 //         bit 2.0 to map[cell, lane]) with a float64 RED; k_clear_masks zeroes the touched windows afterwards.  One
 //         word per cell whatever the number of classes: used when C + 1 > 8, where MODE 1's per-class tags would
 //         double the scattered traffic (C = 19: 45 us -> see DESIGN.md).
-// MODE 1: count update (matrix == np.eye(C), grid of integer-valued counts): one uint32 tag per (cell, class, frame
-//         of the batch) and one per (cell, boost, frame); ATOM.MAX with the frame's tag returns an older tag exactly
-//         once per frame, and that lane adds 1.0 (boost: 2.0 on the lane class; src/mapping_replay.py:281,294) with a
-//         float64 RED.  Sums of small integers are exact in any order.  Nothing to clear, no second kernel.  The
-//         frames of a batch use different tag planes (interleaved: the planes of one element share a sector), so
-//         warps may be at different frames without any synchronisation.
+// MODE 1: count update (matrix == np.eye(C), grid of integer-valued counts): one uint32 tag per (cell, class) and one
+//         per (cell, boost); ATOM.MAX with the frame's tag returns an older tag exactly once per frame, and that lane
+//         adds 1.0 (boost: 2.0 on the lane class; src/mapping_replay.py:281,294) with a float64 RED.  Sums of small
+//         integers are exact in any order.  Nothing to clear, no second kernel.  Launches that may overlap (different
+//         internal streams) use different tag planes.
 //
-// Every warp is autonomous (no block barrier after the prologue).  Per frame a warp owns a contiguous, equally sized
-// slice of the cloud, which it walks in rounds of kFRoundPts points:
+// Every warp is autonomous (no block barrier after the prologue).  A warp owns a contiguous, equally sized slice of
+// the cloud, which it walks in rounds of kFRoundPts points:
 //   cloud     the next round is prefetched into registers (LDG.128, streaming) while the current one is processed;
-//             -DSMAP_FUSE_TMA=1 selects a per-warp ring of shared-memory stages filled by TMA bulk copies instead
-//             (measured: more round set-up instructions than it saves, see above);
 //   cull      conservative float32 test (cull32), survivors (~36 %) pushed on the warp's stack (ballot + popc);
 //   decide    whenever >= 32 survivors are stacked, pop 32 -- one per lane, all lanes busy: float32 decisions; the
 //             undecided points go to the deferred stack (decided in float64, 32 at a time), the accepted ones to
-//             the record stack as {pixel | frame, cell | intensity flag};
-//   gather    whenever >= 32 * kFGather records are stacked: label lookup + update in straight-line code, all the
-//             label bytes requested before the first is used, all the tag atomics issued before the first result
-//             is used -- the two memory round trips are paid once per 32 * kFGather records.  (A software pipeline
-//             that carried loads and atomics across loop iterations was tried first: ptxas puts every carried
-//             operation on one scoreboard and waits for it at the loop head, which serialised everything.)
+//             the record stack as {pixel, cell | intensity flag};
+//   lookup    whenever >= 32 * kFGather records are stacked: all their label bytes are requested before the first is
+//             used, class bits from the shared tables.  MODE 0 / 2 update the mask word right here.  MODE 1 pushes
+//             the records whose pixel is a MAPPED class (5 of the 19 classes by default: a quarter of them) on the
+//             update stack -- a third compaction, so that
+//   update    (MODE 1) the tag atomics and the float64 REDs run with all 32 lanes busy instead of a quarter of them
+//             (the divergent region cost the same ~75 instructions per pass whatever the number of active lanes),
+//             and their round trip to L2 is paid once per 32 * kFUpdate updates, decoupled from the label loads'.
 // ------------------------------------------------------------------------------------------------
 //
 // FMT 0: RGB label image, class bits = tabR[R] & tabG[G].  FMT 1: class-id plane (1 byte per network pixel), class
 // bits = id_lut[id]; the only other difference is the label index (label_index<FMT>).
-template <int MODE, int NF, int FMT = 0>
+//
+// `boxes`: MODE 0 / 2 the frame's bounding box (consumed and reset by k_apply / k_clear_masks, which also fold it into
+// the handle's union window); MODE 1 the union window itself (never reset by a kernel: smap_clear does).
+template <int MODE, int FMT = 0>
 __global__ void __launch_bounds__(kFThreads, SMAP_FUSE_MINB)
-k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridParams gp, FrameBox* __restrict__ boxes,
+k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams gp, FrameBox* __restrict__ boxes,
        double* __restrict__ map) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    __shared__ int s_box[NF][4];
+    __shared__ int s_box[4];
 
+    const FuseFrame& F = B.f;
+    const Fast32& fk = B.f.fk;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    constexpr int kFWarpSmem = fuse_warp_smem(NF);
+    constexpr int kFWarpSmem = fuse_warp_smem(MODE);
     unsigned char* const wbase = s_dyn + (size_t)warp * kFWarpSmem;
-    float4* const stages = reinterpret_cast<float4*>(wbase);
-    float4* const queue = stages + kFStages * kFRoundPts;
+    float4* const queue = reinterpret_cast<float4*>(wbase);
     float4* const defer = queue + kFQueueCap;
     uint2* const recs = reinterpret_cast<uint2*>(defer + kFDeferCap);
-    uint8_t* const defer_f = reinterpret_cast<uint8_t*>(recs + kFRecCap);   // NF > 1 only
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(defer_f + (NF > 1 ? kFDeferCap : 0));
-    (void)bars;
+    uint2* const upds = recs + kFRecCap;   // MODE 1 only
     uint32_t* const s_tab_r = reinterpret_cast<uint32_t*>(s_dyn + (size_t)kFWarps * kFWarpSmem);
     uint32_t* const s_tab_g = s_tab_r + 256;
 
-    const int nf = (NF == 1) ? 1 : B.n_frames;   // NF == 1: every B.f[f] below is B.f[0], a fixed constant-bank offset
     const int64_t gw = (int64_t)blockIdx.x * kFWarps + warp;   // this warp's index in the grid
-    // this warp's slice of frame f: [gw * per_warp, ...) clipped to the cloud
-    auto slice_pts = [&](int f) -> int {
-        const int64_t left = B.f[f].n - gw * B.f[f].per_warp;
-        return left <= 0 ? 0 : (left < B.f[f].per_warp ? (int)left : B.f[f].per_warp);
-    };
-
-#if SMAP_FUSE_TMA
-    // ---- TMA producer state (meaningful in lane 0): frame, source and points left of the next round to issue
-    uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    const uint32_t stg0 = smem_u32(stages), bar0 = smem_u32(bars);
-    int i_f = -1, i_left = 0;
-    const float4* i_src = nullptr;
-    uint32_t i_st = 0;
-    auto issue_round = [&]() {   // no-op once the batch is exhausted; issues exactly the rounds the consumer walks
-        while (i_left <= 0 && i_f + 1 < nf) {
-            ++i_f;
-            i_left = slice_pts(i_f);
-            i_src = B.f[i_f].pts + gw * B.f[i_f].per_warp;
-        }
-        if (i_left <= 0) return;
-        if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(i_left < kFRoundPts ? i_left : kFRoundPts) * 16u;
-            const uint32_t bar = bar0 + i_st * 8u;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                         ::"r"(stg0 + i_st * (uint32_t)(kFRoundPts * 16)), "l"(i_src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
-        }
-        i_src += kFRoundPts;
-        i_left -= kFRoundPts;
-        i_st = (i_st + 1u) % (uint32_t)kFStages;
-    };
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kFStages; ++s) mbar_init(bars + s, 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // this warp's slice of the cloud: [gw * per_warp, ...) clipped
+    int w_pts;
+    {
+        const int64_t left = F.n - gw * F.per_warp;
+        w_pts = left <= 0 ? 0 : (left < F.per_warp ? (int)left : F.per_warp);
     }
-    __syncwarp();
+    // the first round is on its way while the block builds its colour tables
+    const float4* gp_pts = F.pts + gw * F.per_warp + lane;
+    float4 buf[kFRound];
 #pragma unroll
-    for (int r = 0; r < kFStages - 1; ++r) issue_round();   // one more is issued at the top of every round
-    // the first rounds are on their way while the block builds its colour tables
-#endif
+    for (int j = 0; j < kFRound; ++j)
+        buf[j] = (j * 32 + lane < w_pts) ? __ldcs(gp_pts + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+
     if (FMT == 0) {
         build_color_tables(gp, s_tab_r, s_tab_g);
     } else {
         for (int i = threadIdx.x; i < 256; i += kFThreads) s_tab_r[i] = __ldg(B.id_lut + i);
     }
-    if (threadIdx.x < NF) box_reset(s_box[threadIdx.x]);
+    if (threadIdx.x == 0) box_reset(s_box);
     __syncthreads();
 
-#if SMAP_FUSE_PF_IMAGE
-    if (NF == 1 && B.f[0].pf_bytes) {
-        const uint32_t lines = (B.f[0].pf_bytes + 127u) >> 7;
-        const uint32_t lanes = gridDim.x * (uint32_t)kFThreads;
-        for (uint32_t l = (uint32_t)gw * 32u + (uint32_t)lane; l < lines; l += lanes)
-            prefetch_l2(B.f[0].pf_image + (size_t)l * 128u);
-    }
-#endif
     const uint32_t c1 = (uint32_t)gp.c + 1u;
     const uint32_t lane_bit = (gp.use_intensity && gp.lane >= 0) ? (1u << gp.lane) : 0u;
 
-    uint32_t qn = 0, dn = 0, rn = 0;   // entries on the survivor / deferred / record stacks (warp-uniform)
-    // MODE 0 / 2 bounding box of the current frame: magic-shifted floats (monotone in the cell coordinates)
+    uint32_t qn = 0, dn = 0, rn = 0, un = 0;   // entries on the survivor / deferred / record / update stacks (warp-uniform)
+    // bounding box of what this warp touched: magic-shifted floats (monotone in the cell coordinates)
     float fbx0 = 3.0e38f, fbx1 = -3.0e38f, fby0 = 3.0e38f, fby1 = -3.0e38f;
 
-    // a decided point -> record stack: {pixel index | frame << 28, cell index | intensity flag << 31}
-    auto push_record = [&](bool have, uint32_t pix_f, uint32_t cell, float it) {
+    // a decided point -> record stack: {pixel index, cell index | intensity flag << 31}
+    auto push_record = [&](bool have, uint32_t pix, uint32_t cell, float it) {
         const unsigned ballot = __ballot_sync(0xffffffffu, have);
         if (have) {
             const uint32_t extreme = (it < 2.0f || it > 14.0f) ? 0x80000000u : 0u;   // src/mapping_replay.py:290
-            recs[rn + __popc(ballot & lt_mask)] = make_uint2(pix_f, cell | extreme);
+            recs[rn + __popc(ballot & lt_mask)] = make_uint2(pix, cell | extreme);
         }
         rn += __popc(ballot);
     };
 
-    // float32 decisions for up to 32 stacked survivors of frame f, one per lane
-    auto decide32 = [&](int f, uint32_t count) {
-        const Fast32& fk = B.f[f].fk;
+    // float32 decisions for up to 32 stacked survivors, one per lane
+    auto decide32 = [&](uint32_t count) {
         const uint32_t first = qn - count;
         qn = first;
         bool defer_me = false, have = false;
         uint32_t pix = 0, cell = 0;
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-#ifdef SMAP_ABL_NO_DRAIN   // ablation builds (profiles/): streaming + cull + stack traffic alone
-        if ((uint32_t)lane < count) {
-            w = queue[first + lane];
-            if (w.x == 1234.5f) atomicOr(B.f[f].mask, (uint32_t)w.z);
-        }
-        count = 0;
-#endif
         if ((uint32_t)lane < count) {
             w = queue[first + lane];
             const float2 lxy = __fadd2_rn(make_float2(w.x, w.y), fk.n_ctr_xy);
@@ -455,24 +336,18 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             tp.x = fmaxf(tp.x, kMagic32); tp.y = fmaxf(tp.y, kMagic32);              // floor -1 -> pixel 0
             tc.x = fmaxf(tc.x, fk.clamp_c.x); tc.y = fmaxf(tc.y, fk.clamp_c.y);      // floor -1 -> cell 0
             if (FMT == 0) {
-                pix = __float_as_uint(tp.y) * (uint32_t)B.f[f].fp.img_w + __float_as_uint(tp.x) + fk.pix_k;
+                pix = __float_as_uint(tp.y) * (uint32_t)F.fp.img_w + __float_as_uint(tp.x) + fk.pix_k;
             } else {
                 constexpr uint32_t kMagicBits = 0x4B400000u;   // bits of kMagic32: RN(u - 1/2) = bits(tp) - kMagicBits
-                pix = label_index<1>(B.f[f], __float_as_uint(tp.x) - kMagicBits, __float_as_uint(tp.y) - kMagicBits);
+                pix = label_index<1>(F, __float_as_uint(tp.x) - kMagicBits, __float_as_uint(tp.y) - kMagicBits);
             }
             cell = __float_as_uint(tc.x) * (uint32_t)gp.mw + __float_as_uint(tc.y) + fk.cell_k;
-            if (MODE != 1 && have) {
+            if (have) {
                 fbx0 = fminf(fbx0, tc.x); fbx1 = fmaxf(fbx1, tc.x);
                 fby0 = fminf(fby0, tc.y); fby1 = fmaxf(fby1, tc.y);
             }
         }
-#if SMAP_FUSE_PF_LABEL
-        if (have) {
-            const uint8_t* lp = B.f[f].image + (FMT == 1 ? (size_t)pix : (size_t)pix * 3u);
-            if (SMAP_FUSE_PF_LABEL == 2) prefetch_l1(lp); else prefetch_l2(lp);
-        }
-#endif
-        push_record(have, pix | ((uint32_t)f << kFidShift), cell, w.w);
+        push_record(have, pix, cell, w.w);
         const unsigned dballot = __ballot_sync(0xffffffffu, defer_me);
 #ifdef SMAP_FUSE_STATS
         {
@@ -484,285 +359,242 @@ k_fuse(const __grid_constant__ FuseBatchT<NF> B, const __grid_constant__ GridPar
             }
         }
 #endif
-#ifndef SMAP_ABL_NO_DEFER   // ablation builds: deferred points are dropped (wrong results, timing only)
         if (dballot) {
-            if (defer_me) {
-                const uint32_t slot = dn + __popc(dballot & lt_mask);
-                defer[slot] = w;
-                if (NF > 1) defer_f[slot] = (uint8_t)f;
-            }
+            if (defer_me) defer[dn + __popc(dballot & lt_mask)] = w;
             dn += __popc(dballot);
         }
-#endif
     };
 
-    // float64 decisions for up to 32 deferred points (possibly of different frames)
+    // float64 decisions for up to 32 deferred points
     auto decide64 = [&](uint32_t count) {
         const uint32_t first = dn - count;
         dn = first;
         bool have = false;
         uint2 pc = make_uint2(0u, kNone);
         float it = 0.f;
-        uint32_t fid = 0;
         if ((uint32_t)lane < count) {
             const float4 w = defer[first + lane];
-            fid = (NF == 1) ? 0u : defer_f[first + lane];
             it = w.w;
-            pc = fuse_decide64<FMT>(B.f[fid], gp, w);
+            pc = fuse_decide64<FMT>(F, gp, w);
             have = pc.y != kNone;
-            if (MODE != 1 && have) {   // rare: straight into the block's box of that frame
+            if (have) {   // rare: straight into the block's box
                 const int cx = (int)(pc.y / (uint32_t)gp.mw), cy = (int)(pc.y - (uint32_t)cx * (uint32_t)gp.mw);
-                atomicMin(&s_box[fid][0], cx); atomicMax(&s_box[fid][1], cx);
-                atomicMin(&s_box[fid][2], cy); atomicMax(&s_box[fid][3], cy);
+                atomicMin(&s_box[0], cx); atomicMax(&s_box[1], cx);
+                atomicMin(&s_box[2], cy); atomicMax(&s_box[3], cy);
             }
         }
-        push_record(have, pc.x | (fid << kFidShift), pc.y, it);
+        push_record(have, pc.x, pc.y, it);
     };
 
-    // label lookup + update for up to 32 * kFGather records, kFGather per lane
-    auto gather = [&](uint32_t count) {
+    // MODE 1: tag atomics + float64 REDs for up to 32 * kFUpdate stacked updates {cell | boost << 31, class bits}
+    auto update = [&](uint32_t count) {
+        const uint32_t first = un - count;
+        un = first;
+        uint32_t elem[kFUpdate], old0[kFUpdate], old1[kFUpdate];
+        const uint32_t t = fk.tag;
+#pragma unroll
+        for (int k = 0; k < kFUpdate; ++k) {
+            const uint32_t i = (uint32_t)(k * 32 + lane);
+            elem[k] = 0u; old0[k] = t; old1[k] = t;
+            if (i < count) {
+                const uint2 u = upds[first + i];
+                const uint32_t cell = u.x & 0x7fffffffu, bits = u.y;
+                const bool boost = (bits & lane_bit) && (u.x >> 31);
+                // element indices fit 32 bits (checked by the host)
+                uint32_t* trow = B.tags + (size_t)(cell * c1);
+                if (bits & (bits - 1u)) {
+                    // several classes share this pixel's (R, G): rare, done in place
+                    double* row = map + cell * (uint32_t)gp.c;
+                    uint32_t b = bits;
+                    while (b) {
+                        const int c = __ffs(b) - 1;
+                        b &= b - 1u;
+                        if (atomicMax(trow + c, t) != t) atomicAdd(row + c, 1.0);
+                    }
+                    if (boost && atomicMax(trow + gp.c, t) != t) atomicAdd(row + gp.lane, 2.0);
+                } else {
+                    const uint32_t cls = (uint32_t)__ffs(bits) - 1u;
+                    old0[k] = atomicMax(trow + cls, t);
+                    if (boost) old1[k] = atomicMax(trow + gp.c, t);
+                    elem[k] = cell * (uint32_t)gp.c + cls;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kFUpdate; ++k) {
+            if (old0[k] != t) atomicAdd(map + elem[k], 1.0);
+            if (old1[k] != t) atomicAdd(map + elem[k], 2.0);
+        }
+    };
+
+    // label lookup for up to 32 * kFGather records, kFGather per lane; MODE 0 / 2: mask update as well
+    auto lookup = [&](uint32_t count) {
         const uint32_t first = rn - count;
         rn = first;
-        uint32_t cellf[kFGather], lr[kFGather], lg[kFGather], fid[kFGather];
+        uint32_t cellf[kFGather], lr[kFGather], lg[kFGather];
 #pragma unroll
         for (int k = 0; k < kFGather; ++k) {
             const uint32_t i = (uint32_t)(k * 32 + lane);
             cellf[k] = kNone;
-            lr[k] = 0; lg[k] = 0; fid[k] = 0;
+            lr[k] = 0; lg[k] = 0;
             if (i < count) {
                 const uint2 rec = recs[first + i];
                 cellf[k] = rec.y;
-                fid[k] = (NF == 1) ? 0u : (rec.x >> kFidShift);
-                const uint32_t pix = rec.x & ((1u << kFidShift) - 1u);
-#ifdef SMAP_ABL_NO_GATHER
-                lr[k] = (pix & 1u) ? 128u : 255u; lg[k] = (pix & 1u) ? 64u : 255u;
-#else
-                const uint8_t* img = B.f[fid[k]].image;
-                const size_t a = (size_t)pix * 3u;
+                const uint32_t pix = rec.x;
+                const uint8_t* img = F.image;
                 if (FMT == 1) {
                     lr[k] = __ldg(img + pix);   // the class id
-                } else
-#ifdef SMAP_FUSE_LABEL8
-                {
-                lr[k] = __ldg(img + a);
-                lg[k] = __ldg(img + a + 1);
-                }
-#else
-                if (B.f[fid[k]].img64) {
+                } else if (F.img64) {
                     // R and G from ONE aligned 8-byte load (a second one only when R is the last byte of its 8: one
                     // pixel in eight): the L1 sees one sector request per point instead of two
-                    const uint2 wv = __ldg(reinterpret_cast<const uint2*>(img + (a & ~(size_t)7)));
-                    const uint32_t sh = ((uint32_t)a & 7u) * 8u;
+                    const uint32_t a = pix * 3u;   // < 3 * 2^28
+                    const uint2 wv = __ldg(reinterpret_cast<const uint2*>(img + (a & ~7u)));
+                    const uint32_t sh = (a & 7u) * 8u;
                     const uint64_t v = (((uint64_t)wv.y << 32) | wv.x) >> sh;
                     lr[k] = (uint32_t)v & 0xffu;
                     lg[k] = (sh == 56u) ? __ldg(img + a + 1) : (((uint32_t)v >> 8) & 0xffu);
                 } else {
+                    const size_t a = (size_t)pix * 3u;
                     lr[k] = __ldg(img + a);
                     lg[k] = __ldg(img + a + 1);
                 }
-#endif
-#endif
             }
         }
-        uint32_t bits[kFGather], old0[kFGather], old1[kFGather], tag[kFGather];
+        uint32_t bits[kFGather];
 #pragma unroll
         for (int k = 0; k < kFGather; ++k) {
             if (FMT == 0) bits[k] = (cellf[k] != kNone) ? (s_tab_r[lr[k]] & s_tab_g[lg[k]]) : 0u;
             else bits[k] = (cellf[k] != kNone) ? s_tab_r[lr[k]] : 0u;
-            tag[k] = 0u; old0[k] = 0u; old1[k] = 0u;
-#ifdef SMAP_ABL_NO_SCATTER
-            if (bits[k] && cellf[k] == 0x7ffffff0u) atomicOr(B.f[0].mask, bits[k]);
-            bits[k] = 0;
-#endif
-            if (!bits[k]) continue;
-            const uint32_t cell = cellf[k] & 0x7fffffffu;
-            const bool boost = (bits[k] & lane_bit) && (cellf[k] >> 31);
-            if (MODE == 0) {
-                atomicOr(B.f[fid[k]].mask + cell, boost ? (bits[k] | (1u << gp.c)) : bits[k]);   // result unused: RED.OR
-                bits[k] = 0;
-            } else if (MODE == 2) {
-                tag[k] = boost ? (bits[k] | (1u << gp.c)) : bits[k];          // the bits this point wants set
-                old0[k] = atomicOr(B.f[fid[k]].mask + cell, tag[k]);          // what the frame had set before
-                bits[k] = cell;                                               // from here on: the cell
-            } else {
-                const uint32_t t = B.f[fid[k]].fk.tag;
-                // element indices fit 32 bits (checked by the host); the planes of one element are adjacent
-                uint32_t* trow = B.tags + ((size_t)(cell * c1) * (uint32_t)B.tag_planes + fid[k]);
-                const size_t tstride = (size_t)(uint32_t)B.tag_planes;
-                if (bits[k] & (bits[k] - 1u)) {
-                    // several classes share this pixel's (R, G): rare, done in place
-                    double* row = map + cell * (uint32_t)gp.c;
-                    uint32_t b = bits[k];
-                    while (b) {
-                        const int i = __ffs(b) - 1;
-                        b &= b - 1u;
-                        if (atomicMax(trow + i * tstride, t) != t) atomicAdd(row + i, 1.0);
-                    }
-                    if (boost && atomicMax(trow + gp.c * tstride, t) != t) atomicAdd(row + gp.lane, 2.0);
-                    bits[k] = 0;
+        }
+        if constexpr (MODE == 1) {
+            // third compaction: only the records of mapped classes go on
+#pragma unroll
+            for (int k = 0; k < kFGather; ++k) {
+                const unsigned ballot = __ballot_sync(0xffffffffu, bits[k] != 0u);
+                if (bits[k]) upds[un + __popc(ballot & lt_mask)] = make_uint2(cellf[k], bits[k]);
+                un += __popc(ballot);
+            }
+        } else {
+            uint32_t want[kFGather], old[kFGather];
+#pragma unroll
+            for (int k = 0; k < kFGather; ++k) {
+                want[k] = 0u; old[k] = 0u;
+                if (!bits[k]) continue;
+                const uint32_t cell = cellf[k] & 0x7fffffffu;
+                const bool boost = (bits[k] & lane_bit) && (cellf[k] >> 31);
+                want[k] = boost ? (bits[k] | (1u << gp.c)) : bits[k];          // the bits this point wants set
+                if (MODE == 0) {
+                    atomicOr(F.mask + cell, want[k]);                          // result unused: RED.OR
                 } else {
-                    const uint32_t cls = (uint32_t)__ffs(bits[k]) - 1u;
-                    tag[k] = t; old0[k] = t; old1[k] = t;
-                    old0[k] = atomicMax(trow + cls * tstride, t);
-                    if (boost) old1[k] = atomicMax(trow + gp.c * tstride, t);
-                    bits[k] = cell * (uint32_t)gp.c + cls;   // from here on: the grid element
+                    old[k] = atomicOr(F.mask + cell, want[k]);                 // what the frame had set before
+                    cellf[k] = cell;
                 }
             }
-        }
-        if (MODE == 1) {
+            if (MODE == 2) {
 #pragma unroll
-            for (int k = 0; k < kFGather; ++k) {
-                if (old0[k] != tag[k]) atomicAdd(map + bits[k], 1.0);
-                if (old1[k] != tag[k]) atomicAdd(map + bits[k], 2.0);
-            }
-        }
-        if (MODE == 2) {
-#pragma unroll
-            for (int k = 0; k < kFGather; ++k) {
-                uint32_t fresh = tag[k] & ~old0[k];   // inactive slots: tag == 0
-                if (!fresh) continue;
-                double* row = map + bits[k] * (uint32_t)gp.c;   // element indices fit 32 bits (checked by the host)
-                if (fresh >> gp.c) {   // boost bit newly set: +2 on the lane class (src/mapping_replay.py:294)
-                    atomicAdd(row + gp.lane, 2.0);
-                    fresh &= (1u << gp.c) - 1u;
-                }
-                while (fresh) {
-                    const int i = __ffs(fresh) - 1;
-                    fresh &= fresh - 1u;
-                    atomicAdd(row + i, 1.0);
+                for (int k = 0; k < kFGather; ++k) {
+                    uint32_t fresh = want[k] & ~old[k];   // inactive slots: want == 0
+                    if (!fresh) continue;
+                    double* row = map + cellf[k] * (uint32_t)gp.c;   // element indices fit 32 bits (checked by the host)
+                    if (fresh >> gp.c) {   // boost bit newly set: +2 on the lane class (src/mapping_replay.py:294)
+                        atomicAdd(row + gp.lane, 2.0);
+                        fresh &= (1u << gp.c) - 1u;
+                    }
+                    while (fresh) {
+                        const int i = __ffs(fresh) - 1;
+                        fresh &= fresh - 1u;
+                        atomicAdd(row + i, 1.0);
+                    }
                 }
             }
         }
     };
 
-    auto drain = [&](int f, uint32_t count) {
-        decide32(f, count);
+    auto drain = [&](uint32_t count) {
+        decide32(count);
         __syncwarp();
         if (dn >= 32u) {
             decide64(32u);
             __syncwarp();
         }
         if (rn >= 32u * kFGather) {
-            gather(32u * kFGather);
+            lookup(32u * kFGather);
             __syncwarp();
+            if (MODE == 1) {
+                while (un >= 32u * kFUpdate) {
+                    update(32u * kFUpdate);
+                    __syncwarp();
+                }
+            }
         }
     };
 
-#if SMAP_FUSE_TMA
-    uint32_t rr = 0;   // rounds consumed so far (all frames): stage = rr % kFStages, parity from rr / kFStages
-#endif
-    for (int f = 0; f < nf; ++f) {
-        const Fast32& fk = B.f[f].fk;
-        const int w_pts = slice_pts(f);
-        const int n_rounds = (w_pts + kFRoundPts - 1) / kFRoundPts;
-#if !SMAP_FUSE_TMA
-        // the next round is prefetched into registers (LDG.128, streaming) while the current one is processed
-        {
-            const float4* gp_pts = B.f[f].pts + gw * B.f[f].per_warp + lane;
-            float4 buf[kFRound];
+    // ---- the cloud, in rounds; the next round is prefetched into registers while the current one is processed
+    const int n_rounds = (w_pts + kFRoundPts - 1) / kFRoundPts;
+    for (int r = 0; r < n_rounds; ++r) {
+        const int left = w_pts - r * kFRoundPts;
+        const int pts = left < kFRoundPts ? left : kFRoundPts;
+        float4 nxt[kFRound];
 #pragma unroll
-            for (int j = 0; j < kFRound; ++j)
-                buf[j] = (j * 32 + lane < w_pts) ? __ldcs(gp_pts + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < n_rounds; ++r) {
-                const int left = w_pts - r * kFRoundPts;
-                const int pts = left < kFRoundPts ? left : kFRoundPts;
-                float4 nxt[kFRound];
+        for (int j = 0; j < kFRound; ++j)
+            nxt[j] = (kFRoundPts + j * 32 + lane < left) ? __ldcs(gp_pts + (r + 1) * kFRoundPts + j * 32)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < kFRound; ++j)
-                    nxt[j] = (kFRoundPts + j * 32 + lane < left) ? __ldcs(gp_pts + (r + 1) * kFRoundPts + j * 32)
-                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-#if SMAP_FUSE_PF_CLOUD
-                // only lines that start inside this warp's slice (a prefetch is a hint, but it is kept in bounds anyway)
-                if (lane < kFRoundPts * 16 / 128 && (r + SMAP_FUSE_PF_CLOUD) * kFRoundPts + lane * 8 < w_pts)
-                    prefetch_l2(reinterpret_cast<const char*>(gp_pts - lane) +
-                                (size_t)(r + SMAP_FUSE_PF_CLOUD) * (kFRoundPts * 16) + lane * 128);
-#endif
-#pragma unroll
-                for (int j = 0; j < kFRound; ++j) {
-                    const float4 w = buf[j];
-                    const bool pass = cull32(fk, w.x, w.y, w.z) & (j * 32 + lane < pts);
-                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                    if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
-                    qn += __popc(ballot);
-                }
-                __syncwarp();
-                while (qn >= 32u) drain(f, 32u);
-#pragma unroll
-                for (int j = 0; j < kFRound; ++j) buf[j] = nxt[j];
-            }
+        for (int j = 0; j < kFRound; ++j) {
+            const float4 w = buf[j];
+            const bool pass = cull32(fk, w.x, w.y, w.z) & (j * 32 + lane < pts);
+            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+            if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
+            qn += __popc(ballot);
         }
-#else
-        for (int r = 0; r < n_rounds; ++r, ++rr) {
-            // keep kFStages - 1 rounds in flight: the next one goes into the stage that the previous round used
-            // (every lane has consumed its reads of that stage, and the warp has re-converged since)
-            issue_round();
-            const uint32_t st = rr % (uint32_t)kFStages;
-            const uint32_t parity = (rr / (uint32_t)kFStages) & 1u;
-            while (!mbar_try_wait(bars + st, parity)) {}
-            const int left = w_pts - r * kFRoundPts;
-            const int pts = left < kFRoundPts ? left : kFRoundPts;
-            const float4* sp = stages + st * kFRoundPts + lane;
-#pragma unroll 1
-            for (int g = 0; g < kFRound; g += kFGroup) {
+        __syncwarp();
+        while (qn >= 32u) drain(32u);
 #pragma unroll
-                for (int j = 0; j < kFGroup; ++j) {
-                    const float4 w = sp[(g + j) * 32];
-                    const bool pass = cull32(fk, w.x, w.y, w.z) & ((g + j) * 32 + lane < pts);
-                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                    if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
-                    qn += __popc(ballot);
-                }
-                __syncwarp();
-                while (qn >= 32u) drain(f, 32u);
-            }
-        }
-#endif
-        // end of the frame for this warp: the survivors left over are decided with this frame's constants (records
-        // and deferred points carry their frame and stay stacked)
-        if (qn) drain(f, qn);
-        if (MODE != 1) {
-            // fold this frame's bounding box: lane -> warp -> block (shared atomics); flushed to the frame's box at the end
-            if (__any_sync(0xffffffffu, fbx1 >= fbx0)) {
-                // magic-shifted float -> cell coordinate: bits - (bits(magic) - I0); clamp_c = magic - I0
-                const int ox = (int)__float_as_uint(fk.clamp_c.x), oy = (int)__float_as_uint(fk.clamp_c.y);
-                const bool any = fbx1 >= fbx0;
-                const int a = __reduce_min_sync(0xffffffffu, any ? (int)__float_as_uint(fbx0) - ox : 0x7fffffff);
-                const int b = __reduce_max_sync(0xffffffffu, any ? (int)__float_as_uint(fbx1) - ox : -1);
-                const int c = __reduce_min_sync(0xffffffffu, any ? (int)__float_as_uint(fby0) - oy : 0x7fffffff);
-                const int d = __reduce_max_sync(0xffffffffu, any ? (int)__float_as_uint(fby1) - oy : -1);
-                if (lane == 0) {
-                    atomicMin(&s_box[f][0], a); atomicMax(&s_box[f][1], b);
-                    atomicMin(&s_box[f][2], c); atomicMax(&s_box[f][3], d);
-                }
-                fbx0 = 3.0e38f; fbx1 = -3.0e38f; fby0 = 3.0e38f; fby1 = -3.0e38f;
-            }
-        }
+        for (int j = 0; j < kFRound; ++j) buf[j] = nxt[j];
     }
-    // flush: the deferred points, then the records
+    // ---- flush: the survivors left over, the deferred points, the records, the updates
+    if (qn) drain(qn);
     if (dn) {
         decide64(dn);
         __syncwarp();
     }
     while (rn) {
-        gather(rn < 32u * kFGather ? rn : 32u * kFGather);
+        lookup(rn < 32u * kFGather ? rn : 32u * kFGather);
         __syncwarp();
     }
-
-    if (MODE != 1) {
-        __syncthreads();
-        if ((int)threadIdx.x < nf && s_box[threadIdx.x][1] >= s_box[threadIdx.x][0]) {
-            FrameBox* box = boxes + threadIdx.x;
-            atomicMin(&box->x0, s_box[threadIdx.x][0]); atomicMax(&box->x1, s_box[threadIdx.x][1]);
-            atomicMin(&box->y0, s_box[threadIdx.x][2]); atomicMax(&box->y1, s_box[threadIdx.x][3]);
+    if (MODE == 1) {
+        while (un) {
+            update(un < 32u * kFUpdate ? un : 32u * kFUpdate);
+            __syncwarp();
         }
+    }
+
+    // ---- bounding box: lane -> warp -> block (shared atomics) -> global
+    if (__any_sync(0xffffffffu, fbx1 >= fbx0)) {
+        // magic-shifted float -> cell coordinate: bits - (bits(magic) - I0); clamp_c = magic - I0
+        const int ox = (int)__float_as_uint(fk.clamp_c.x), oy = (int)__float_as_uint(fk.clamp_c.y);
+        const bool any = fbx1 >= fbx0;
+        const int a = __reduce_min_sync(0xffffffffu, any ? (int)__float_as_uint(fbx0) - ox : 0x7fffffff);
+        const int b = __reduce_max_sync(0xffffffffu, any ? (int)__float_as_uint(fbx1) - ox : -1);
+        const int c = __reduce_min_sync(0xffffffffu, any ? (int)__float_as_uint(fby0) - oy : 0x7fffffff);
+        const int d = __reduce_max_sync(0xffffffffu, any ? (int)__float_as_uint(fby1) - oy : -1);
+        if (lane == 0) {
+            atomicMin(&s_box[0], a); atomicMax(&s_box[1], b);
+            atomicMin(&s_box[2], c); atomicMax(&s_box[3], d);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_box[1] >= s_box[0]) {
+        atomicMin(&boxes->x0, s_box[0]); atomicMax(&boxes->x1, s_box[1]);
+        atomicMin(&boxes->y0, s_box[2]); atomicMax(&boxes->y1, s_box[3]);
     }
 }
 
-// After a MODE 2 batch: zero every frame slot inside its frame's bounding box, reset the boxes of the next batch.
-// blockIdx.y = slot; the blocks of a slot stride over the rows of its box.
+// After a MODE 2 batch: zero every frame slot inside its frame's bounding box, fold the boxes into the handle's union
+// window, reset the boxes of the next batch.  blockIdx.y = slot; the blocks of a slot stride over the rows of its box.
 __global__ void __launch_bounds__(kThreads)
 k_clear_masks(const __grid_constant__ ApplyParams ap, const FrameBox* __restrict__ boxes, FrameBox* __restrict__ next_boxes,
-              unsigned long long* __restrict__ next_touched_total, int mw) {
+              unsigned long long* __restrict__ next_touched_total, FrameBox* __restrict__ ubox, int mw) {
     const int f = blockIdx.y;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         box_reset(&next_boxes[f].x0);
@@ -771,6 +603,10 @@ k_clear_masks(const __grid_constant__ ApplyParams ap, const FrameBox* __restrict
     if (f >= ap.n_frames) return;
     const FrameBox b = boxes[f];
     if (b.x1 < b.x0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicMin(&ubox->x0, b.x0); atomicMax(&ubox->x1, b.x1);
+        atomicMin(&ubox->y0, b.y0); atomicMax(&ubox->y1, b.y1);
+    }
     uint32_t* const m = ap.mask[f];
     for (int x = b.x0 + (int)blockIdx.x; x <= b.x1; x += (int)gridDim.x) {
         uint32_t* row = m + (size_t)x * mw;

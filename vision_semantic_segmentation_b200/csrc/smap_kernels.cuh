@@ -5,6 +5,7 @@
 // addresses, and grid sizes that fill 148 SMs.
 #pragma once
 #include "smap_device.cuh"
+#include "smap_render.cuh"
 
 namespace smap {
 
@@ -239,8 +240,8 @@ template <int NJ>
 __global__ void __launch_bounds__(kThreads)
 k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameBox* __restrict__ boxes,
         FrameBox* __restrict__ next_boxes, unsigned long long* __restrict__ touched_total,
-        unsigned long long* __restrict__ next_touched_total, const double* __restrict__ cm, int c, int lane_cls,
-        int mw) {
+        unsigned long long* __restrict__ next_touched_total, FrameBox* __restrict__ ubox, const double* __restrict__ cm,
+        int c, int lane_cls, int mw) {
     constexpr int V = 2;
     extern __shared__ double s_cm[];  // C x C, transposed: s_cm[i * c + j] = cm[j * c + i] (column i contiguous)
     __shared__ FrameBox s_boxes[kMaxBatch];
@@ -263,6 +264,10 @@ k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameB
         y0 = min(y0, s_boxes[f].y0); y1 = max(y1, s_boxes[f].y1);
     }
     if (x1 < x0) return;   // block-uniform: nothing was touched
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // the handle's union window (what a multi-GPU exchange has to move)
+        atomicMin(&ubox->x0, x0); atomicMax(&ubox->x1, x1);
+        atomicMin(&ubox->y0, y0); atomicMax(&ubox->y1, y1);
+    }
     // a thread owns V = 2 horizontally adjacent cells whose linear index is even, so that the two words of a
     // slot come with one 8-byte load; columns outside [y0, y1] that such a pair drags in are ignored
     const uint32_t gcols = (uint32_t)(y1 - y0 + 1) / V + 2u;          // pairs per row, generous
@@ -475,17 +480,9 @@ k_compact(const void* __restrict__ pts, int64_t n, int64_t ld, const uint8_t* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// Rendering.  K4 (3x3 box, BORDER_REFLECT_101, acc = acc + kf*p row-major from 0; src/renderer.py:175-189),
-// K5 (first-argmax colour, zero-sum -> black; src/renderer.py:32-59) fused; a tile of the grid with
-// a one-cell halo is staged in shared memory with coalesced row-segment loads.
+// Rendering.  K4 + K5 (apply_filter + render_bev_map, fused) live in smap_render.cuh; below: the class-axis
+// reduction shared with K6 and K6 itself.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTileX = 32;
-constexpr int kTileY = 8;
-
-struct RenderColors {
-    uint8_t rgb[32 * 3];
-};
-
 // Streams the C values of one cell in ascending class order through `value(ch)` and returns the first
 // argmax (np.argmax semantics: a NaN wins and stops the scan) and the class-axis sum in numpy's order
 // (add.reduce over a contiguous axis = 0 + pairwise sum: fewer than 8 addends left to right, otherwise
@@ -537,56 +534,6 @@ __device__ __forceinline__ void argmax_and_npsum(int c, F value, int& best, doub
         }
     }
     total = res;
-}
-
-template <bool FILTER>
-__global__ void __launch_bounds__(kTileX * kTileY)
-k_render(const double* __restrict__ map, int mh, int mw, int c, const __grid_constant__ RenderColors colors,
-         uint8_t* __restrict__ rgb, double* __restrict__ filtered) {
-    extern __shared__ double s_tile[];  // (kTileY+2) x (kTileX+2) x C   (FILTER only)
-    const int x0 = blockIdx.x * kTileX, y0 = blockIdx.y * kTileY;
-    const int tx = threadIdx.x % kTileX, ty = threadIdx.x / kTileX;
-    const int rowlen = (kTileX + 2) * c;
-    if (FILTER) {
-        for (int r = 0; r < kTileY + 2; ++r) {
-            const int yy = y0 - 1 + r;
-            if (yy > mh) break;  // rows past the bottom halo are never read
-            const int ys = reflect101(yy, mh);
-            for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
-                const int col = x0 - 1 + e / c;
-                if (col > mw) break;
-                const int xs = reflect101(col, mw);
-                s_tile[r * rowlen + e] = map[((size_t)ys * mw + xs) * c + (e % c)];
-            }
-        }
-        __syncthreads();
-    }
-    const int x = x0 + tx, y = y0 + ty;
-    if (x >= mw || y >= mh) return;
-    const size_t cell = (size_t)y * mw + x;
-    const double kf = (double)(1.0f / 9.0f);
-    auto value = [&](int ch) -> double {
-        if constexpr (!FILTER) return map[cell * c + ch];
-        double acc = 0.0;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
-                acc = __dadd_rn(acc, __dmul_rn(kf, s_tile[(ty + dy) * rowlen + (tx + dx) * c + ch]));
-        if (filtered) filtered[cell * c + ch] = acc;
-        return acc;
-    };
-    int best;
-    double total;
-    argmax_and_npsum(c, value, best, total);
-    if (rgb) {
-        uint8_t* o = rgb + 3 * cell;
-        if (total == 0.0) {
-            o[0] = 0; o[1] = 0; o[2] = 0;
-        } else {
-            o[0] = colors.rgb[3 * best]; o[1] = colors.rgb[3 * best + 1]; o[2] = colors.rgb[3 * best + 2];
-        }
-    }
 }
 
 // K6: render_bev_map_with_thresholds (src/renderer.py:131-172)

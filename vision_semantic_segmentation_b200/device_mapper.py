@@ -149,7 +149,16 @@ class DeviceMapper(object):
         _native.check(self._lib.smap_integrate(self._h, ctypes.byref(frame), self._stream()))
 
     def integrate_host(self, frame):
+        """``smap_integrate_host``: the frame's tensors live in (pinned) host memory and the copies are asynchronous
+        (torch's caching host allocator knows nothing about copies issued by the library), so the frame stays
+        referenced here until an event recorded behind its kernels has completed."""
+        torch = _native.require_cuda()
         _native.check(self._lib.smap_integrate_host(self._h, ctypes.byref(frame), self._stream()))
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._keepalive.append((ev, frame))
+        while len(self._keepalive) > 2 and self._keepalive[0][0].query():
+            del self._keepalive[0]
 
     def integrate_batch(self, frames):
         arr = (SmapFrame * len(frames))(*frames)
@@ -193,6 +202,55 @@ class DeviceMapper(object):
         _native.check(self._lib.smap_update(self._h, target.data_ptr(), pcd.data_ptr(), pcd.stride(0) if m else 0,
                                             label.data_ptr(), label.stride(0) if m else 0, m, self._stream()))
         return target
+
+    # ------------------------------------------------------------------ multi-GPU
+    def init_comm(self, group=None):
+        """Collective over a ``torch.distributed`` process group: gives the handle its own NCCL communicator.  Rank 0
+        draws the unique id (``smap_comm_unique_id``), ``torch.distributed`` carries its 128 bytes to the other ranks
+        (plumbing), every rank calls ``smap_comm_init``.  After this ``allreduce`` / ``reduce_scatter_rows`` run
+        entirely under the C ABI (pack kernels + NCCL)."""
+        import torch.distributed as dist
+        if getattr(self, "_comm_ready", False):
+            return
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = (ctypes.c_uint8 * _native.SMAP_COMM_ID_BYTES)()
+        if rank == 0:
+            _native.check(self._lib.smap_comm_unique_id(ident))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (ctypes.c_uint8 * _native.SMAP_COMM_ID_BYTES).from_buffer_copy(box[0])
+        _native.check(self._lib.smap_comm_init(self._h, world, rank, ident))
+        self._comm_ready = True
+
+    def allreduce(self):
+        """Every rank's grid becomes the sum over the ranks (``smap_allreduce``: touched window only, counts packed)."""
+        _native.check(self._lib.smap_allreduce(self._h, self._stream()))
+
+    def reduce_scatter_rows(self):
+        """``smap_reduce_scatter_rows``: returns ``(tile, r0, r1, top, bottom)``; ``tile`` holds the summed rows
+        ``[r0 - top, r1 + bottom)`` of the map as a (rows, MW, C) float64 CUDA tensor."""
+        torch = _native.require_cuda()
+        info = self.comm_info()
+        per = -(-self.map_height // max(info["n_ranks"], 1))
+        with torch.cuda.device(self.device):
+            tile = torch.empty((per + 2, self.map_width, self.num_classes), dtype=torch.float64, device=self.device)
+        r0, r1, top, bottom = (ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32())
+        _native.check(self._lib.smap_reduce_scatter_rows(self._h, tile.data_ptr(), per + 2, ctypes.byref(r0), ctypes.byref(r1),
+                                                         ctypes.byref(top), ctypes.byref(bottom), self._stream()))
+        rows = r1.value - r0.value + top.value + bottom.value
+        return tile[:rows], r0.value, r1.value, top.value, bottom.value
+
+    def comm_info(self):
+        info = _native.SmapCommInfo()
+        _native.check(self._lib.smap_comm_get_info(self._h, ctypes.byref(info)))
+        return {"n_ranks": info.n_ranks, "rank": info.rank, "window": list(info.window), "pack": ("u16", "u32", "f64")[info.pack],
+                "bytes": info.bytes, "grid_bytes": info.grid_bytes, "exchanges": info.exchanges}
+
+    def cloud_to_f32x4(self, pcd, out, flag):
+        """(4, N) float64 CUDA cloud -> (N, 4) float32 ``out``; ``flag`` (int32 CUDA tensor of one element, zeroed by
+        the caller) is raised when a value is not float32-representable (``smap_cloud_to_f32x4``)."""
+        _native.check(self._lib.smap_cloud_to_f32x4(pcd.data_ptr(), pcd.stride(0) if pcd.shape[1] else 0, pcd.shape[1],
+                                                    out.data_ptr(), flag.data_ptr(), self.device.index, self._stream()))
 
     def notify_map_modified(self):
         """Call after writing into ``self.map`` from outside (``copy_``, arithmetic, ...): the grid may no longer hold
