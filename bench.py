@@ -3,17 +3,24 @@
 fraction of the HBM roofline, next to the CPU path timed on the same box).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W     # the reference's CPU algorithm (numpy port)
+    python bench.py --impl reference --steps K --warmup W     # the reference's own CPU code (oracle/_ref)
 
-A "step" is one frame of BASELINE.json configs[1]: a 2M-point local cloud + one 1920x1440
-19-class label image, count-based update into the default 2000x2000 BEV grid.  Inputs are a ring of
-distinct frames resident in HBM (ring >> L2), so every step streams its cloud and image from DRAM.
-Frames are handed to the C ABI 16 at a time (smap_integrate_batch: one fused kernel per frame; inside a batch a launch
-takes half of the resident block slots and the launches alternate over four internal streams, so two frames run side by
-side; the count update needs no second kernel).  `roofline.kernel_ms` is the same kernel launched alone with the full
-grid (the library's profiling mode serialises the launches on the caller's stream).
-N > 1: one process per GPU (torchrun), frames sharded by rank (weak scaling: every rank integrates K
-frames), one NCCL all-reduce of the grids at the end of the timed region.
+A "step" is one frame of the workload (default cfg2 = BASELINE.json configs[1]: a 2M-point local cloud + one 1920x1440
+19-class label image, count update into the default 2000x2000 BEV grid).  Inputs are a ring of distinct frames resident
+in HBM (ring >> L2), so every step streams its cloud and image from DRAM.  Frames are handed to the C ABI in batches
+(smap_integrate_batch: one fused kernel per frame; inside a batch a launch takes half of the resident block slots and
+the launches alternate over internal streams, so two frames run side by side).
+
+Timed region: R blocks of exactly K steps, back to back, R chosen so that the region lasts >= 50 ms (a 20-step block is
+0.3 ms); barrier + synchronize on both sides, CUDA events, max over ranks.  `ms_per_step` = region / (R K); the per-block
+figures (median / min / max) are printed next to it.
+N > 1: one process per GPU (torchrun), frames sharded by rank (weak scaling: every rank integrates K frames per block).
+Every block ends with one exchange of the ranks' increments (smap_exchange_async: touched window only, counts packed as
+uint16 pairs, NCCL all-reduce on an internal stream, overlapped with the next block's frames); the region ends when the
+last exchange has been added to every rank's grid.  After the timed region the exchanged grid is compared with a plain
+torch.distributed all-reduce of the per-rank grids (bit for bit in count mode).
+Workloads: cfg2 (default), cfg3 (log-likelihood update, 10^4 x 10^4 grid), cfg4 (8000 frames in total, sharded: strong
+scaling), cfg5 (cam1 + cam6 frames into a 10^4 x 10^4 grid, row-tiled filter + render + image gather inside the region).
 """
 import argparse
 import json
@@ -41,14 +48,24 @@ MAP_H = MAP_W = 2000
 def select_workload(args):
     """cfg2 (default, the configuration the metric is quoted on): count update, 2000 x 2000 grid at 0.1 m.
     cfg3 (BASELINE.json configs[2]): confusion-matrix log-likelihood update -- the ordered two-kernel path -- into a
-    0.2 m, 2 km x 2 km grid (10^4 x 10^4 cells; 4 GB of float64 at 5 classes)."""
+    0.2 m, 2 km x 2 km grid (10^4 x 10^4 cells; 4 GB of float64 at 5 classes).
+    cfg4 (configs[3]): cfg2's frames, --frames (8000) of them in total sharded over the ranks (strong scaling).
+    cfg5 (configs[4]): frames alternate between the cam1 and cam6 calibrations, count update into the 10^4 x 10^4 grid,
+    the map filtered + rendered by row tiles and the image gathered at the end of the region."""
     global BOUNDARY, RESOLUTION, MAP_H, MAP_W
-    if args.workload == "cfg3":
+    if args.workload in ("cfg3", "cfg5"):
         BOUNDARY, RESOLUTION, MAP_H, MAP_W = [[0, 2000], [0, 2000]], 0.2, 10000, 10000
+    if args.workload == "cfg4":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        args.steps = max(1, args.frames // world)
+
+
+def log_update(args):
+    return args.workload == "cfg3"
 
 
 def update_matrix(args, labels):
-    if args.workload != "cfg3":
+    if not log_update(args):
         return np.eye(len(labels))
     # src/mapping_replay.py:104-109 / src/data/confusion_matrix.py:43-48,59-63 on a synthetic strictly positive matrix
     sub = syn.synthetic_confusion_matrix(11)[np.ix_(labels, labels)]
@@ -69,20 +86,27 @@ def claim_stdout():
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=2000000)
     ap.add_argument("--classes", type=int, default=5, choices=[5, 19],
                     help="mapped classes: the reference's default 5 (LABELS=[2,1,8,10,3]) or all 19")
     ap.add_argument("--ring", type=int, default=16, help="distinct frames resident in HBM")
-    ap.add_argument("--batch", type=int, default=16, help="frames handed to smap_integrate_batch per call")
-    ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the cpu_baseline sample")
+    ap.add_argument("--batch", type=int, default=16, help="frames handed to smap_integrate_batch per call (at most)")
+    ap.add_argument("--repeats", type=int, default=0,
+                    help="blocks of --steps steps in the timed region (0: as many as make the region last >= 50 ms)")
+    ap.add_argument("--min-region-ms", type=float, default=50.0)
+    ap.add_argument("--frames", type=int, default=8000, help="cfg4: frames of the whole job, sharded over the ranks")
+    ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the cpu_baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=48, help="frames of the end-to-end legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+    ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2: BASELINE.json configs[1], the configuration the metric is quoted on (default); "
-                         "cfg3: configs[2], log-likelihood update into a 10^4 x 10^4 grid")
+                         "cfg3: configs[2], log-likelihood update into a 10^4 x 10^4 grid; cfg4: configs[3], 8000 frames "
+                         "sharded (strong scaling); cfg5: configs[4], two cameras, large map, row-tiled render")
     ap.add_argument("--label-format", default="rgb", choices=["rgb", "ids"],
                     help="rgb: the (1440, 1920, 3) colour-coded label image the reference consumes (default, the "
                          "BASELINE.json workload); ids: the network's (1440, 1920) uint8 class-id plane "
@@ -198,33 +222,81 @@ class ClockSampler(object):
                 "samples": len(sm), "source": "nvidia-smi"}
 
 
-def make_ring(args, rank):
-    """ring of distinct synthetic frames (host): points (N,4) f32, image (H,W,3) u8, T (4,4) f64"""
+def make_ring(args, rank, n=None):
+    """ring of distinct synthetic frames (host): dicts with points (N,4) f32, semantic_image (H,W,3) u8, semantic_ids,
+    pose, T (4,4) f64 world -> velodyne, camera slot (cfg5: cam1 / cam6 alternate)"""
     frames = []
-    for i in range(args.ring):
+    for i in range(args.ring if n is None else n):
         f = rank * 100000 + i
         fr = syn.synthetic_frame(SEED, f, args.points, blocky=(i % 2 == 1), as_float64=False, with_ids=True)
-        T = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
-        frames.append((fr["points"], fr["semantic_image"], T, fr["semantic_ids"]))
+        fr["T"] = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
+        fr["camera"] = (i % 2) if args.workload == "cfg5" else 0
+        fr["camera_id"] = 6 if fr["camera"] == 1 else 1
+        frames.append(fr)
     return frames
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the numpy restatement of the reference's CPU path (oracle/numpy_port.py)
+# reference arm / cpu_baseline: the reference's OWN code (oracle/_ref: byte-compiled from /root/reference by
+# oracle/build_ref.py, imported through oracle/ref_shim.py), the numpy restatement only if that tree is missing
 # --------------------------------------------------------------------------------------------------
-def cpu_frame_fn(args):
-    from oracle import numpy_port  # the ONLY place bench.py touches oracle/: the CPU baseline being timed
-    from vision_semantic_segmentation_b200.camera import camera_setup_1
+def make_cfg(cfg, args, tmp):
     labels, names, colors = syn.class_setup(args.classes == 19)
-    cam, cm = camera_setup_1(), update_matrix(args, labels)
+    cfg.OUTPUT_DIR = tmp
+    cfg.LABELS, cfg.LABELS_NAMES, cfg.LABEL_COLORS = labels, names, colors
+    cfg.MAPPING.BOUNDARY, cfg.MAPPING.RESOLUTION = BOUNDARY, RESOLUTION
+    cfg.MAPPING.PCD.RANGE_MAX, cfg.MAPPING.PCD.USE_INTENSITY = RANGE_MAX, True
+    if log_update(args):
+        path = os.path.join(tmp, "cm.npy")
+        np.save(path, syn.synthetic_confusion_matrix(11))
+        cfg.MAPPING.CONFUSION_MTX.LOAD_PATH = path
+    return cfg
+
+
+def cpu_frame_fn(args):
+    """-> (run(frame) -> points, render() -> seconds, kind): one frame through the CPU path -- project_pcd + update_map."""
+    import tempfile
+    from oracle import ref_shim   # bench.py touches oracle/ only here: the CPU baseline being timed
+    labels, names, colors = syn.class_setup(args.classes == 19)
+    if ref_shim.reference_available():
+        ref = ref_shim.load_reference()
+        sm = ref.SemanticMapping(make_cfg(ref.get_cfg_defaults(), args, tempfile.mkdtemp()))
+        grid = np.zeros((sm.map_height, sm.map_width, sm.map_depth))
+        cams = [sm.cam1, sm.cam6]
+
+        def run(fr, n_sub=None):
+            pcd = np.ascontiguousarray(fr["points"][:n_sub].T.astype(np.float64))   # the reference's frame format
+            masked, label = sm.project_pcd(pcd, "world", fr["semantic_image"], fr["pose"], cams[fr["camera"]])
+            sm.update_map(grid, masked, label)
+            return pcd.shape[1]
+
+        def render(crop=None):
+            g = grid if crop is None else np.ascontiguousarray(grid[:crop, :crop])
+            t0 = time.perf_counter()
+            ref.render_bev_map(ref.apply_filter(g), sm.label_colors)
+            return time.perf_counter() - t0
+        return run, render, "reference"
+    from oracle import numpy_port
+    from vision_semantic_segmentation_b200.camera import camera_setup_1, camera_setup_6
+    cams, cm = [camera_setup_1(), camera_setup_6()], update_matrix(args, labels)
     grid = np.zeros((MAP_H, MAP_W, len(labels)))
 
-    def run(points, image, T, ids=None):
-        pcd = np.ascontiguousarray(points.T.astype(np.float64))
-        masked, label, _, _ = numpy_port.project_pcd(pcd, T, cam.P, image, RANGE_MAX)
+    def run(fr, n_sub=None):
+        pcd = np.ascontiguousarray(fr["points"][:n_sub].T.astype(np.float64))
+        masked, label, _, _ = numpy_port.project_pcd(pcd, fr["T"], cams[fr["camera"]].P, fr["semantic_image"], RANGE_MAX)
         numpy_port.update_map(grid, masked, label, colors, cm, BOUNDARY, RESOLUTION, True, names)
-        return points.shape[0]
-    return run
+        return pcd.shape[1]
+    return run, None, "port"
+
+
+def set_blas_threads(n):
+    """Pin the BLAS pool explicitly: torchrun exports OMP_NUM_THREADS=1, which would otherwise turn the N > 1 baseline
+    into a single-threaded one."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=n, user_api="blas")
+    except Exception:
+        return None
 
 
 def blas_threads():
@@ -236,39 +308,49 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def time_cpu(run, frames, n_frames, n_sub=None):
+    run(frames[0], n_sub)  # warm-up
+    t0 = time.perf_counter()
+    pts = 0
+    for i in range(n_frames):
+        pts += run(frames[(1 + i) % len(frames)], n_sub)
+    return pts / (time.perf_counter() - t0)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    run = cpu_frame_fn(args)
+    set_blas_threads(os.cpu_count() or 1)
+    run, _, kind = cpu_frame_fn(args)
     # bounded sample: whole frames when a frame costs <~1 s, otherwise a fixed slice of each frame
-    ring = make_ring(argparse.Namespace(ring=min(args.ring, 4), points=args.points), 0)
+    ring = make_ring(args, 0, n=min(args.ring, 4))
     t0 = time.perf_counter()
-    run(*ring[0])
+    run(ring[0])
     t_frame = time.perf_counter() - t0
     budget = 150.0
     frac = min(1.0, budget / max(t_frame * (args.steps + args.warmup), 1e-9))
     n_sub = max(1000, int(args.points * frac))
-    sample = [(p[:n_sub], im, T) for p, im, T, _ in ring]
     for i in range(args.warmup):
-        run(*sample[i % len(sample)])
+        run(ring[i % len(ring)], n_sub)
     t0 = time.perf_counter()
     pts = 0
     for i in range(args.steps):
-        pts += run(*sample[i % len(sample)])
+        pts += run(ring[i % len(ring)], n_sub)
     dt = time.perf_counter() - t0
     value = pts / dt
     cores = blas_threads()
-    desc = ("numpy port of project_pcd+update_map, %d points of each %d-point frame per step, %d steps; "
-            "BLAS threads=%d of %d host cores (only the two dgemms are threaded, as in the reference)"
-            % (n_sub, args.points, args.steps, cores, os.cpu_count() or 1))
+    desc = ("%s project_pcd + update_map, %d points of each %d-point frame per step, %d steps; BLAS threads pinned to %d of %d "
+            "host cores (only the two dgemms are threaded, everything else in the reference is single-threaded numpy)"
+            % ("the reference's own src/mapping_replay.py (oracle/_ref, byte-compiled)" if kind == "reference" else
+               "numpy port (oracle/numpy_port.py) of", n_sub, args.points, args.steps, cores, os.cpu_count() or 1))
     line = {
         "impl": "reference", "metric": "points_fused_per_sec", "value": value, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "frames_per_sec": value / args.points,
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -277,25 +359,42 @@ def run_reference(args):
 
 def workload_config(args, world):
     ids = getattr(args, "label_format", "rgb") == "ids"
-    cfg3 = getattr(args, "workload", "cfg2") == "cfg3"
+    wl = getattr(args, "workload", "cfg2")
+    what = {"cfg2": "", "cfg3": "", "cfg4": ", %d frames in total sharded over the ranks" % args.frames,
+            "cfg5": ", cam1 / cam6 frames alternating, row-tiled filter + render + image gather at the end"}[wl]
     return {"workload": "mapping_replay %s: %d-point cloud + 1920x1440 19-class label image per frame%s, "
-                        "%s update, %d mapped classes, grid %dx%d @ %.1f m"
-                        % ("cfg3" if cfg3 else "cfg2", args.points, " (as uint8 class-id plane)" if ids else "",
-                           "confusion-matrix log-likelihood" if cfg3 else "count", args.classes, MAP_H, MAP_W, RESOLUTION),
+                        "%s update, %d mapped classes, grid %dx%d @ %.1f m%s"
+                        % (wl, args.points, " (as uint8 class-id plane)" if ids else "",
+                           "confusion-matrix log-likelihood" if log_update(args) else "count", args.classes, MAP_H, MAP_W,
+                           RESOLUTION, what),
             "points_per_frame": args.points, "image": [1440, 1920] if ids else [1440, 1920, 3], "mapped_classes": args.classes,
-            "grid": [MAP_H, MAP_W, args.classes], "update": "log-likelihood" if cfg3 else "count", "frames_per_rank": args.steps,
-            "parallelism": "frames sharded over %d rank(s), all-reduce(sum) of the grid at the end" % world,
+            "grid": [MAP_H, MAP_W, args.classes], "update": "log-likelihood" if log_update(args) else "count",
+            "frames_per_rank_per_block": args.steps,
+            "parallelism": ("single GPU" if world == 1 else
+                            "frames sharded over %d ranks; one exchange of the increments per block (touched window, packed "
+                            "counts, NCCL all-reduce on an internal stream, overlapped with the next block)" % world),
             "l2_policy": "inputs larger than L2: ring of %d distinct frames (%.0f MB) resident in HBM"
                          % (args.ring, args.ring * (args.points * 16 + 1440 * 1920 * (1 if ids else 3)) / 1e6)}
 
 
+def balanced(steps, cap):
+    """K steps in ceil(K / cap) batches of (almost) equal size: a 20-step block is 10 + 10, not 16 + 4."""
+    nb = -(-steps // cap)
+    base, extra = divmod(steps, nb)
+    return [base + (1 if i < extra else 0) for i in range(nb)]
+
+
 # --------------------------------------------------------------------------------------------------
 def run_b200(args):
+    import tempfile
     import torch
     import torch.distributed as dist
-    from vision_semantic_segmentation_b200 import frame_sharding, _native
-    from vision_semantic_segmentation_b200.camera import camera_setup_1
+    from vision_semantic_segmentation_b200 import frame_sharding
+    from vision_semantic_segmentation_b200.camera import camera_setup_1, camera_setup_6
+    from vision_semantic_segmentation_b200.config.base_cfg import get_cfg_defaults
     from vision_semantic_segmentation_b200.device_mapper import DeviceMapper
+    from vision_semantic_segmentation_b200.mapping_replay import SemanticMapping
+    from vision_semantic_segmentation_b200.renderer import filter_and_render
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
@@ -303,8 +402,11 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     labels, names, colors = syn.class_setup(args.classes == 19)
     c = len(labels)
-    cam, cm, lane = camera_setup_1(), update_matrix(args, labels), names.index("lane")
-    dm = DeviceMapper(MAP_H, MAP_W, colors, cm, BOUNDARY, RESOLUTION, RANGE_MAX, True, lane, cameras=[cam], device=local_rank)
+    cm, lane = update_matrix(args, labels), names.index("lane")
+    dm = DeviceMapper(MAP_H, MAP_W, colors, cm, BOUNDARY, RESOLUTION, RANGE_MAX, True, lane,
+                      cameras=[camera_setup_1(), camera_setup_6()], device=local_rank)
+    if world > 1:
+        dm.init_comm()
 
     if args.ordered:   # smap_clear re-arms the count update: undo that after every clear
         plain_clear = dm.clear
@@ -316,21 +418,22 @@ def run_b200(args):
         dm.notify_map_modified()
 
     ring_host = make_ring(args, rank)
-    ring_dev, ring_pinned = [], []
+    ring_dev = []
     if args.label_format == "ids":
         dm.set_label_palette(syn.COLORS_19)
-    for pts, img, T, ids in ring_host:
-        dp, di = torch.from_numpy(pts).to(dev), torch.from_numpy(ids if args.label_format == "ids" else img).to(dev)
-        ring_dev.append((dm.make_frame(dp, di, T, 0), dp, di))
+    for fr in ring_host:
+        dp = torch.from_numpy(fr["points"]).to(dev)
+        di = torch.from_numpy(fr["semantic_ids"] if args.label_format == "ids" else fr["semantic_image"]).to(dev)
+        ring_dev.append((dm.make_frame(dp, di, fr["T"], fr["camera"]), dp, di))
     torch.cuda.synchronize()
 
     # ---- algorithmic bytes per frame: N, M, U measured on the device path itself (outside timed regions)
     n_pts = args.points
     m_list, u_list, k_list = [], [], []
-    for frame, dp, di in ring_dev[: min(4, len(ring_dev))]:
+    for i, (frame, dp, di) in enumerate(ring_dev[: min(4, len(ring_dev))]):
         if args.label_format == "ids":   # the parity API takes RGB images: count the survivors with one
-            masked, _ = dm.project(dm.make_frame(dp, torch.from_numpy(ring_host[len(m_list)][1]).to(dev),
-                                                 ring_host[len(m_list)][2], 0))
+            masked, _ = dm.project(dm.make_frame(dp, torch.from_numpy(ring_host[i]["semantic_image"]).to(dev),
+                                                 ring_host[i]["T"], ring_host[i]["camera"]))
         else:
             masked, _ = dm.project(frame)
         m_list.append(masked.shape[1])
@@ -350,149 +453,293 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     ring_frames = [f for f, _, _ in ring_dev]
+    pos = [0]   # position in the ring: blocks continue where the previous one stopped
 
-    def device_loop(steps, reduce_at_end):
-        # frames go to the C ABI in batches (smap_integrate_batch: up to 16 frames per kernel launch)
-        done = 0
-        while done < steps:
-            take = min(args.batch, steps - done, len(ring_frames))
-            start = done % len(ring_frames)
-            chunk = (ring_frames + ring_frames)[start:start + take]
-            dm.integrate_batch(chunk)
-            done += take
-        if reduce_at_end and world > 1:
-            frame_sharding.sum_grids(dm.map)
+    def block(steps):
+        """exactly `steps` frames through smap_integrate_batch, in balanced batches"""
+        for take in balanced(steps, min(args.batch, len(ring_frames))):
+            start = pos[0] % len(ring_frames)
+            dm.integrate_batch((ring_frames + ring_frames)[start:start + take])
+            pos[0] += take
+
+    def render_tiles():
+        """cfg5: filter + render of this rank's row tile (one-row halos), image all-gathered"""
+        r0, r1 = frame_sharding.row_tile(MAP_H, rank, world)
+        top, bottom = (1 if r0 > 0 and r1 > r0 else 0), (1 if r1 < MAP_H and r1 > r0 else 0)
+        rgb_tile = frame_sharding.render_row_tile(dm.map[r0 - top:r1 + bottom], top, bottom, colors)
+        return frame_sharding.gather_rgb_rows(rgb_tile, MAP_H) if world > 1 else rgb_tile
+
+    # ---- warm-up: kernels, and for N > 1 the collectives at the size they will have (NCCL sets its channels up lazily)
+    if world > 1:
+        dm.set_streaming(True)
+    block(max(args.warmup, 3))
+    if world > 1:
+        for _ in range(3):
+            block(min(args.steps, 32))
+            dm.exchange_async()
+        dm.exchange_flush()
+    if args.workload == "cfg5":
+        render_tiles()
+    torch.cuda.synchronize()
+    # ---- how long is one block?  -> R blocks for a region of >= min_region_ms
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    block(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    est = max(e0.elapsed_time(e1), 1e-3)
+    repeats = args.repeats if args.repeats > 0 else int(min(2000, max(1, np.ceil(args.min_region_ms / est))))
+    if world > 1:   # every rank must run the same number of blocks
+        t = torch.tensor([repeats], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        repeats = int(t.item())
+        dm.exchange_async()
+        dm.exchange_flush()
+    dm.clear()
 
     # ---- device-resident throughput (`value`)
-    device_loop(args.warmup, False)
     launches_before = dm.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(repeats + 1)]
+    e_end = torch.cuda.Event(enable_timing=True)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    device_loop(args.steps, True)
-    e1.record()
+    for r in range(repeats):
+        marks[r].record()
+        block(args.steps)
+        if world > 1:
+            dm.exchange_async()
+    marks[repeats].record()
+    if world > 1:
+        dm.exchange_flush()
+    if args.workload == "cfg5":
+        rgb_full = render_tiles()
+    e_end.record()
     if rank == 0:
         sampler.sample_now()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = marks[0].elapsed_time(e_end)
+    block_ms = np.array([marks[r].elapsed_time(marks[r + 1]) for r in range(repeats)])
     clocks = sampler.stop() if rank == 0 else None
     launches = dm.stats()["kernel_launches"] - launches_before
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = world * args.steps * n_pts / (ms * 1e-3)
+    total_steps = repeats * args.steps
+    value = world * total_steps * n_pts / (ms * 1e-3)
+
+    # ---- N > 1: the exchange on its own, and parity of the exchanged grid against torch.distributed's all-reduce
+    collective = None
+    if world > 1:
+        info = dm.comm_info()
+        # one block, then the exchange alone (nothing to overlap with): agreement + pack + all-reduce + unpack, host included
+        dm.clear()
+        pos[0] = 0
+        block(args.steps)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        dm.exchange_async()
+        dm.exchange_flush()
+        torch.cuda.synchronize()
+        exch_ms = 1e3 * (time.perf_counter() - t0)
+        got = dm.map.clone()
+        dm.set_streaming(False)
+        dm.clear()
+        pos[0] = 0
+        block(args.steps)
+        want = dm.map.clone()
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        if log_update(args):
+            err = float(((got - want).abs() / want.abs().clamp_min(1e-300)).max().item())
+            parity = {"max_rel_err": err, "ok": bool(err <= 1e-5)}
+        else:
+            parity = {"bit_exact": bool(torch.equal(got, want)), "ok": bool(torch.equal(got, want))}
+        parity["checksum"] = float(want.sum().item())
+        tt = torch.tensor([exch_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        collective = {"exchange_alone_ms": float(tt.item()), "bytes_per_exchange": info["bytes"], "grid_bytes": info["grid_bytes"],
+                      "window": info["window"], "pack": info["pack"], "exchanges_in_region": repeats,
+                      "parity_vs_torch_all_reduce": parity,
+                      "note": "exchange_alone_ms: one exchange with nothing to overlap (agreement + pack + NCCL all-reduce + "
+                              "unpack-add, host time included); inside the region the exchanges run on an internal stream "
+                              "under the next block's frames"}
+        if not parity["ok"]:
+            raise SystemExit("exchanged grid differs from torch.distributed all_reduce of the per-rank grids: %r" % (parity,))
+        dm.clear()
 
     # ---- roofline of the dominant kernel (k_fuse: project + cull + lookup + update of one frame).
-    # Its launch duration is measured live with CUDA events recorded by the library on the launching stream
-    # (smap_set_profiling: the per-frame launches are then serialised on that stream); the algorithmic bytes are
-    # SURVEY.md 8d's  16 N + 3 M + 2*8 U  per frame with N, M, U measured above on the device path.
-    dm.clear()
-    device_loop(min(16, args.warmup + 3), False)
+    # kernel_ms: the launch shape of the timed region -- a batch's launches on the internal streams, two half-grid
+    # launches side by side -- timed with CUDA events around every smap_integrate_batch call of a pass (events recorded on
+    # the launching stream; the batch's fork / join hang off it), per frame.  kernel_alone_ms: the same kernel launched
+    # alone with the full grid (smap_set_profiling serialises the launches).  Algorithmic bytes: SURVEY.md 8d's
+    # 16 N + 3 M + 2*8 U per frame with N, M, U measured above on the device path.
+    pos[0] = 0
+    block(16)
     torch.cuda.synchronize()
+    n_b = max(4, min(64, total_steps // max(1, min(args.batch, len(ring_frames)))))
+    bsz = min(args.batch, len(ring_frames))
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_b + 1)]
+    for b in range(n_b):
+        evs[b].record()
+        block(bsz)
+    evs[n_b].record()
+    torch.cuda.synchronize()
+    kernel_ms = float(np.median([evs[b].elapsed_time(evs[b + 1]) for b in range(n_b)])) / bsz
+    dm.clear()
     dm.set_profiling(True)
-    device_loop(args.steps, False)
+    block(max(32, min(args.steps, 128)))
     st = dm.stats()
     dm.set_profiling(False)
-    kernel_ms = st["stream_kernel_ms"] / max(st["profiled_frames"], 1)
+    kernel_alone_ms = st["stream_kernel_ms"] / max(st["profiled_frames"], 1)
     apply_ms = st["apply_kernel_ms"] / max(st["profiled_frames"], 1)
     peak, peak_src = peaks()
     achieved = bytes_per_frame / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")   # from the committed ncu --set full capture
-    if args.label_format == "rgb" and args.workload == "cfg2" and not args.ordered and os.path.exists(tpath):
+    if args.label_format == "rgb" and args.workload in ("cfg2", "cfg4") and not args.ordered and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("k_fuse_c%d" % args.classes)
 
-    # ---- end to end through the host-buffer entry point: H2D of cloud + image and a D2H read every step
-    e2e = None
-    if not args.no_e2e:
-        dm.clear()
-        dm.set_label_palette(syn.COLORS_19)
-        ring_pinned_ids = []
-        for pts, img, T, ids in ring_host[: min(4, len(ring_host))]:
-            hp, hi = torch.from_numpy(pts).pin_memory(), torch.from_numpy(img).pin_memory()
-            ring_pinned.append((dm.make_frame(hp, hi, T, 0, host=True), hp, hi))
-            hd = torch.from_numpy(ids).pin_memory()
-            ring_pinned_ids.append((dm.make_frame(hp, hd, T, 0, host=True), hp, hd))
-        h2d = ring_pinned[0][1].numel() * 4 + ring_pinned[0][2].numel()
-        e2e_steps = min(args.steps, 50)
-        result = torch.zeros(1, dtype=torch.float64, device=dev)
-        host_result = torch.zeros(1, dtype=torch.float64).pin_memory()
+    # ---- render leg: apply_filter + render_bev_map of the whole grid (once per replay), HBM-bound
+    render = None
+    if not args.no_render:
+        pos[0] = 0
+        block(min(64, max(args.steps, 16)))
+        filter_and_render(dm.map, colors)
+        torch.cuda.synchronize()
+        revs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        for i in range(5):
+            revs[i].record()
+            filter_and_render(dm.map, colors)
+        revs[5].record()
+        torch.cuda.synchronize()
+        r_ms = float(np.median([revs[i].elapsed_time(revs[i + 1]) for i in range(5)]))
+        r_bytes = float(MAP_H) * MAP_W * c * 8 + float(MAP_H) * MAP_W * 3
+        render = {"kernel": "k_render<filter> (3x3 box filter + first-argmax colour, one pass)", "ms": r_ms,
+                  "algorithmic_bytes": r_bytes, "achieved": r_bytes / (r_ms * 1e-3) / 1e9, "unit": "GB/s",
+                  "frac": r_bytes / (r_ms * 1e-3) / 1e9 / peak}
 
-        def e2e_loop(steps, ring=ring_pinned):
-            for i in range(steps):
-                dm.integrate_host(ring[i % len(ring)][0])
-                # the step's "metric": evidence mass in the grid cell under the vehicle's first hit (8 bytes)
-                host_result.copy_(dm.map.view(-1)[:1], non_blocking=False)
-        e2e_loop(2)
-        barrier()
-        t0 = time.perf_counter()
-        e2e_loop(e2e_steps)
+    # ---- end to end through the reference-facing API: SemanticMapping.mapping_replay(input_list) with HOST frames in
+    # pinned memory.  Inside the timed region: clear, H2D of every frame's cloud + label image (pinned, multi-buffered,
+    # replay_feed), the fused kernels, filter + render, D2H of the rendered map.
+    e2e = None
+    if not args.no_e2e and args.workload in ("cfg2", "cfg3"):
+        tmp = tempfile.mkdtemp()
+        sm = SemanticMapping(make_cfg(get_cfg_defaults(), args, tmp), device=local_rank)
+        sm.set_label_palette(syn.COLORS_19)
+        k_e2e = max(8, min(args.e2e_steps, 4 * args.steps))
+        # N > 1: the API shards the list over the ranks itself, so every rank hands it the SAME list
+        src_frames = ring_host if world == 1 else make_ring(args, 0, n=min(8, args.ring))
+        rgb_frames, ids_frames, pcd_frames, keep = [], [], [], []
+        for fr in src_frames[: min(8, len(src_frames))]:
+            hp = torch.from_numpy(fr["points"]).pin_memory()
+            hi = torch.from_numpy(fr["semantic_image"]).pin_memory()
+            hd = torch.from_numpy(fr["semantic_ids"]).pin_memory()
+            h64 = torch.from_numpy(np.ascontiguousarray(fr["points"].T.astype(np.float64))).pin_memory()
+            keep.append((hp, hi, hd, h64))
+            base = {"pcd_frame_id": "world", "pose": fr["pose"], "camera_id": fr["camera_id"]}
+            rgb_frames.append(dict(base, points=hp.numpy(), semantic_image=hi.numpy()))
+            ids_frames.append(dict(base, points=hp.numpy(), semantic_ids=hd.numpy()))
+            pcd_frames.append(dict(base, pcd=h64.numpy(), semantic_image=hi.numpy()))   # src/mapping.py:309-312
+
+        def api_leg(which, frames):
+            input_list = [frames[i % len(frames)] for i in range(k_e2e)]
+            sm.mapping_replay(input_list[:8], "warm", write_image=False)
+            barrier()
+            t0 = time.perf_counter()
+            rgb = sm.mapping_replay(input_list, "bench", write_image=False)
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            first = input_list[0]
+            img = first["semantic_image"] if "semantic_image" in first else first["semantic_ids"]
+            cloud = first["points"] if "points" in first else first["pcd"]
+            return {"value": k_e2e * n_pts / float(tt.item()), "unit": "points/s",
+                    "h2d_bytes_per_step": int(cloud.nbytes + img.nbytes), "d2h_bytes_per_step": int(rgb.nbytes // k_e2e),
+                    "steps": k_e2e, "ms_per_step": 1e3 * float(tt.item()) / k_e2e,
+                    "pcie_gbs": (cloud.nbytes + img.nbytes) * k_e2e / world / float(tt.item()) / 1e9,
+                    "note": which}, rgb
+
+        e2e, rgb_a = api_leg("SemanticMapping.mapping_replay(input_list): frames as host dictionaries in pinned memory "
+                             "(points (N, 4) float32 + (1440, 1920, 3) RGB label image); timed: clear, pinned "
+                             "multi-buffered H2D of every frame, fused kernels, filter + render, D2H of the rendered map",
+                             rgb_frames)
+        ids_leg, rgb_b = api_leg("same call, label image handed over as the network's (1440, 1920) uint8 class-id plane",
+                                 ids_frames)
+        ids_leg["same_render_as_rgb"] = bool(np.array_equal(rgb_a, rgb_b))
+        e2e["class_ids"] = ids_leg
+        ref_leg, rgb_c = api_leg("same call, cloud in the reference's own record layout: pcd (4, N) float64 "
+                                 "(src/mapping.py:309-312), converted to the float4 layout on the device "
+                                 "(smap_cloud_to_f32x4)", pcd_frames)
+        ref_leg["same_render_as_float32"] = bool(np.array_equal(rgb_a, rgb_c))
+        e2e["reference_record_format"] = ref_leg
+        # what the link itself does: one large pinned H2D copy, timed alone
+        big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        dbig = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        dbig.copy_(big, non_blocking=True)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * e2e_steps * n_pts / float(tt.item()), "unit": "points/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8, "steps": e2e_steps,
-               "note": "smap_integrate_host: pinned host cloud (float32 x,y,z,i) + RGB label image copied per step"}
-        # the same loop fed with the network's class-id plane instead of the painted RGB image (SMAP_IMG_CLASS_IDS:
-        # 1 byte per pixel over PCIe, same grid bit for bit -- tests/test_gpu_label_ids.py)
-        grid_rgb = dm.map.clone()
-        dm.clear()
-        e2e_loop(2, ring_pinned_ids)
-        barrier()
-        dm.clear()
-        e2e_loop(2, ring_pinned)   # same 2 warm-up frames as the RGB loop above saw before its timed region
         t0 = time.perf_counter()
-        e2e_loop(e2e_steps, ring_pinned_ids)
+        for _ in range(4):
+            dbig.copy_(big, non_blocking=True)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e["class_ids"] = {"value": world * e2e_steps * n_pts / float(tt.item()), "unit": "points/s",
-                            "h2d_bytes_per_step": int(ring_pinned_ids[0][1].numel() * 4 + ring_pinned_ids[0][2].numel()),
-                            "d2h_bytes_per_step": 8, "steps": e2e_steps,
-                            "same_grid_as_rgb": bool(torch.equal(grid_rgb, dm.map)),
-                            "note": "label image handed over as the network's (1440, 1920) uint8 class-id plane"}
+        e2e["pinned_h2d_peak_gbs"] = 4 * big.numel() / (time.perf_counter() - t0) / 1e9
+        e2e["frac_of_pinned_h2d_peak"] = e2e["pcie_gbs"] / e2e["pinned_h2d_peak_gbs"]
+        del big, dbig, sm, keep
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        run = cpu_frame_fn(args)
-        run(*ring_host[0])  # warm-up
-        t0 = time.perf_counter()
-        pts = 0
-        for i in range(args.cpu_frames):
-            pts += run(*ring_host[(1 + i) % len(ring_host)])
-        dt = time.perf_counter() - t0
-        cpu = {"value": pts / dt, "unit": "points/s", "cores": blas_threads(), "kind": "port",
-               "sample": "%d full frames of the same workload through oracle/numpy_port.py (numpy restatement of the "
-                         "reference's project_pcd+update_map); %d host cores, BLAS threads only in the two dgemms"
-                         % (args.cpu_frames, os.cpu_count() or 1)}
+        run, cpu_render, kind = cpu_frame_fn(args)
+        ncores = os.cpu_count() or 1
+        set_blas_threads(ncores)
+        v_all = time_cpu(run, ring_host, args.cpu_frames)
+        cores = blas_threads()
+        set_blas_threads(1)
+        v_one = time_cpu(run, ring_host, max(2, args.cpu_frames // 2))
+        set_blas_threads(ncores)
+        cpu = {"value": v_all, "unit": "points/s", "cores": cores, "kind": kind, "single_thread_value": v_one,
+               "sample": "%d full frames of the same workload through %s project_pcd + update_map; %d host cores, BLAS "
+                         "threads pinned to %d (only the two dgemms are threaded); single_thread_value: BLAS pinned to 1"
+                         % (args.cpu_frames, "the reference's own src/mapping_replay.py (oracle/_ref, byte-compiled from "
+                            "/root/reference)" if kind == "reference" else "oracle/numpy_port.py (numpy restatement of)",
+                            ncores, cores)}
+        if render is not None and cpu_render is not None:
+            crop = None if MAP_H * MAP_W <= 4000000 else 2000
+            sec = cpu_render(crop)
+            scale = 1.0 if crop is None else (MAP_H * MAP_W) / float(crop * crop)
+            render["cpu_ms"] = 1e3 * sec * scale
+            render["cpu_note"] = ("the reference's apply_filter + render_bev_map (src/renderer.py:32-59,175-189) on the host"
+                                  + ("" if crop is None else ", timed on a %d x %d crop and scaled by area" % (crop, crop)))
 
     if rank == 0:
         line = {
             "metric": "points_fused_per_sec", "value": value, "unit": "points/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "repeats": repeats, "ms_per_step": ms / total_steps,
+            "block_ms_per_step": {"median": float(np.median(block_ms)) / args.steps, "min": float(block_ms.min()) / args.steps,
+                                  "max": float(block_ms.max()) / args.steps},
+            "timed_region_ms": ms, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "cfg4" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "frames_per_sec": value / n_pts,
             "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": ("k_fuse<masks> (project+cull+lookup+RED.OR into the frame's cell masks, one frame per "
                                     "launch); the ordered k_apply replay is apply_kernel_ms_per_frame"
-                                    if (args.workload == "cfg3" or args.ordered) else
+                                    if (log_update(args) or args.ordered) else
                                     "k_fuse<count> (register-prefetched cloud, float32 certified project+cull+lookup+update, "
                                     "one frame per launch)"),
-                         "kernel_ms": kernel_ms, "apply_kernel_ms_per_frame": apply_ms,
-                         "step_frac": bytes_per_frame / (ms / args.steps * 1e-3) / 1e9 / peak,
+                         "kernel_ms": kernel_ms,
+                         "kernel_ms_shape": "per frame in the launch shape of the timed region: batches of %d frames, one "
+                                            "half-grid launch per frame, two side by side (events around each batch)" % bsz,
+                         "kernel_alone_ms": kernel_alone_ms, "frac_alone": bytes_per_frame / (kernel_alone_ms * 1e-3) / 1e9 / peak,
+                         "apply_kernel_ms_per_frame": apply_ms,
+                         "step_frac": bytes_per_frame / (ms / total_steps * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_frame": bytes_per_frame,
                          "N": n_pts, "M": M, "K_cells": Kc, "U_elements": U},
+            "render": render, "collective": collective,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), file=args.out, flush=True)

@@ -32,7 +32,7 @@ extern "C" {
 #define SMAP_API
 #endif
 
-#define SMAP_ABI_VERSION 3
+#define SMAP_ABI_VERSION 4
 #define SMAP_MAX_CLASSES 31 /* C class bits + 1 intensity-boost bit in a 32-bit cell mask */
 #define SMAP_MAX_CAMERAS 8
 
@@ -269,6 +269,21 @@ SMAP_API int smap_allreduce(smap_handle *h, void *stream);
  * tile then sees real neighbours across the seams and BORDER_REFLECT_101 only at true map edges. */
 SMAP_API int smap_reduce_scatter_rows(smap_handle *h, double *tile_dev, int64_t tile_rows_cap, int32_t *r0, int32_t *r1,
                                       int32_t *top, int32_t *bottom, void *stream);
+/* Streaming exchange -- the same sum, but overlapped with the integration of the next frames (a replay that is
+ * summed every few hundred microseconds cannot afford to stop for the collective).  smap_comm_streaming(h, 1) makes the
+ * update kernels accumulate into one of two internal buffers of LOCAL increments instead of the grid.
+ * smap_exchange_async (collective, same call sequence on every rank) closes the current buffer, starts the ranks'
+ * agreement on its window behind the work queued on `stream` so far, and queues the DATA phase of the PREVIOUS call's
+ * buffer -- pack + zero, NCCL all-reduce, add to the grid -- on an internal high-priority stream: it runs while the
+ * frames integrated after the call fill the other buffer.  The host blocks only until that previous agreement (8
+ * ints) has arrived; `stream` never waits for a collective.  smap_exchange_flush queues the last data phase and makes
+ * `stream` wait for it: afterwards the grid of every rank holds the sum of everything handed to
+ * smap_exchange_async (frames integrated after the last smap_exchange_async are still local).  The grid is written
+ * by the exchanges only; smap_map_ptr / download / render see exchanged increments only.  Counts stay exact
+ * (integer sums); log-likelihood grids are summed in exchange order (<= 1e-5 relative by north_star). */
+SMAP_API int smap_comm_streaming(smap_handle *h, int on, void *stream);
+SMAP_API int smap_exchange_async(smap_handle *h, void *stream);
+SMAP_API int smap_exchange_flush(smap_handle *h, void *stream);
 SMAP_API int smap_comm_get_info(smap_handle *h, smap_comm_info *out);
 
 /* ---- grid access ------------------------------------------------------------------------------- */

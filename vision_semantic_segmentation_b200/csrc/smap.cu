@@ -95,6 +95,27 @@ struct smap_handle {
     FrameBox* ubox = nullptr;
     bool ubox_full = false;
     int64_t value_bound = 0;              // no grid element exceeds this while integer_grid holds (3 per frame)
+    // Where the update kernels accumulate: the grid itself, or -- streaming exchange (smap_comm_streaming) -- the
+    // current one of two buffers of LOCAL increments that smap_exchange_async hands to the other ranks while the next
+    // frames are integrated into the other buffer; abox = the union window of what `acc` holds.
+    double* acc = nullptr;
+    FrameBox* abox = nullptr;
+    bool streaming = false;
+    double* delta[2] = {};
+    FrameBox* dbox[2] = {};
+    bool d_integer[2] = {true, true};     // the buffer holds integer-valued counts
+    int64_t d_bound[2] = {0, 0};          // no element of the buffer exceeds this
+    int cur = 0;
+    cudaStream_t comm_stream = nullptr;   // agreement, pack, NCCL, unpack of the streaming exchange
+    cudaEvent_t ev_chunk = nullptr;       // the caller's stream has finished the chunk being exchanged
+    cudaEvent_t ev_agreed[2] = {};        // the ranks' agreement on buffer b has reached the host
+    cudaEvent_t ev_packed[2] = {};        // buffer b has been packed and zeroed: free for new increments
+    bool packed_recorded[2] = {false, false};
+    cudaEvent_t ev_exchanged = nullptr;   // the last queued exchange has been added to the grid
+    bool pend_active = false;             // an agreement is in flight (its data phase is queued by the next call)
+    int pend_buf = 0;
+    int* xch_dev2[2] = {};                // agreement words of the streaming exchange, per buffer
+    int* xch_host2[2] = {};
     // multi-GPU exchange (smap_comm_* / smap_allreduce / smap_reduce_scatter_rows)
     ncclComm_t comm = nullptr;
     bool own_comm = false;
@@ -153,6 +174,10 @@ struct smap_handle {
 };
 
 namespace {
+
+// properties of the accumulation target (the grid, or the current buffer of the streaming exchange)
+inline bool& acc_integer(smap_handle* h) { return h->streaming ? h->d_integer[h->cur] : h->integer_grid; }
+inline int64_t& acc_bound(smap_handle* h) { return h->streaming ? h->d_bound[h->cur] : h->value_bound; }
 
 int fill_frame_params(const smap_handle* h, const smap_frame* f, FrameParams& fp) {
     if (!f) return fail(SMAP_ERR_INVALID, "frame is NULL");
@@ -444,7 +469,7 @@ int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st)
     unsigned long long* ntt = h->touched + (h->parity ^ 1);
     const unsigned grid = (unsigned)h->sm_count * 8;
     const int lane = h->cfg.lane_index, mw = h->cfg.map_width;
-#define SMAP_LAUNCH_APPLY(NJ) k_apply<NJ><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->ubox, h->cm_dev, c, lane, mw)
+#define SMAP_LAUNCH_APPLY(NJ) k_apply<NJ><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->abox, h->cm_dev, c, lane, mw)
     if (c <= 8) SMAP_LAUNCH_APPLY(1);
     else if (c <= 16) SMAP_LAUNCH_APPLY(2);
     else if (c <= 24) SMAP_LAUNCH_APPLY(3);
@@ -465,7 +490,7 @@ int launch_clear(smap_handle* h, int n_slots_used, cudaStream_t st) {
     const dim3 grid((unsigned)h->sm_count, kMaxBatch);
     k_clear_masks<<<grid, kThreads, 0, st>>>(ap, h->boxes + (size_t)h->parity * kMaxBatch,
                                              h->boxes + (size_t)(h->parity ^ 1) * kMaxBatch, h->touched + (h->parity ^ 1),
-                                             h->ubox, h->cfg.map_width);
+                                             h->abox, h->cfg.map_width);
     CK(cudaGetLastError());
     h->parity ^= 1;
     h->stats.kernel_launches += 1;
@@ -711,11 +736,11 @@ int launch_fuse(smap_handle* h, const smap_frame* frames, const FrameParams* fps
         fb->tags = count_atomics ? h->tags + plane_words * (size_t)lane_stream : nullptr;
         fb->id_lut = h->id_lut_dev;
         // mode 1: the union window itself; otherwise the frame's own box (folded into the window by k_apply / k_clear_masks)
-        FrameBox* boxes = mode == 1 ? h->ubox : h->boxes + (size_t)h->parity * kMaxBatch + used;
+        FrameBox* boxes = mode == 1 ? h->abox : h->boxes + (size_t)h->parity * kMaxBatch + used;
         const bool ids = frames[i].image_format == SMAP_IMG_CLASS_IDS;
-        if (mode == 1) ids ? launch_k_fuse<1, 1>(*fb, h->gp, boxes, h->map, gx, ls) : launch_k_fuse<1, 0>(*fb, h->gp, boxes, h->map, gx, ls);
-        else if (mode == 2) ids ? launch_k_fuse<2, 1>(*fb, h->gp, boxes, h->map, gx, ls) : launch_k_fuse<2, 0>(*fb, h->gp, boxes, h->map, gx, ls);
-        else ids ? launch_k_fuse<0, 1>(*fb, h->gp, boxes, h->map, gx, ls) : launch_k_fuse<0, 0>(*fb, h->gp, boxes, h->map, gx, ls);
+        if (mode == 1) ids ? launch_k_fuse<1, 1>(*fb, h->gp, boxes, h->acc, gx, ls) : launch_k_fuse<1, 0>(*fb, h->gp, boxes, h->acc, gx, ls);
+        else if (mode == 2) ids ? launch_k_fuse<2, 1>(*fb, h->gp, boxes, h->acc, gx, ls) : launch_k_fuse<2, 0>(*fb, h->gp, boxes, h->acc, gx, ls);
+        else ids ? launch_k_fuse<0, 1>(*fb, h->gp, boxes, h->acc, gx, ls) : launch_k_fuse<0, 0>(*fb, h->gp, boxes, h->acc, gx, ls);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { rc = fail(SMAP_ERR_CUDA, "k_fuse launch: %s", cudaGetErrorString(e)); break; }
         h->stats.kernel_launches += 1;
@@ -828,17 +853,19 @@ inline dim3 window_grid(int units, int rows) {
 
 // rows [row0, row0 + rows) of the packed buffer <- grid rows of the same index, columns [y0, y0 + cols);
 // grid rows outside [wx0, wx1] are written as zeros
-int launch_pack(const smap_handle* h, int pack, int row0, int rows, int wx0, int wx1, int y0, int cols, void* out,
-                cudaStream_t st) {
+int launch_pack(const smap_handle* h, double* src, bool clear, int pack, int row0, int rows, int wx0, int wx1, int y0,
+                int cols, void* out, cudaStream_t st) {
     const int c = h->cfg.num_classes, run = cols * c, run_words = pack == kPackU16 ? (run + 1) / 2 : run;
     const size_t row_bytes = pack == kPackF64 ? (size_t)run * 8 : (size_t)run_words * 4;
     for (int done = 0; done < rows; done += 32768) {
         const int n = rows - done < 32768 ? rows - done : 32768;
         void* o = static_cast<char*>(out) + (size_t)done * row_bytes;
         const dim3 g = window_grid(pack == kPackU16 ? run_words : run, n);
-        if (pack == kPackU16) k_pack_window<kPackU16><<<g, kThreads, 0, st>>>(h->map, wx0, wx1, h->cfg.map_width, c, row0 + done, y0, run, run_words, o);
-        else if (pack == kPackU32) k_pack_window<kPackU32><<<g, kThreads, 0, st>>>(h->map, wx0, wx1, h->cfg.map_width, c, row0 + done, y0, run, run_words, o);
-        else k_pack_window<kPackF64><<<g, kThreads, 0, st>>>(h->map, wx0, wx1, h->cfg.map_width, c, row0 + done, y0, run, run_words, o);
+#define SMAP_PACK(P, CL) k_pack_window<P, CL><<<g, kThreads, 0, st>>>(src, wx0, wx1, h->cfg.map_width, c, row0 + done, y0, run, run_words, o)
+        if (pack == kPackU16) { if (clear) SMAP_PACK(kPackU16, true); else SMAP_PACK(kPackU16, false); }
+        else if (pack == kPackU32) { if (clear) SMAP_PACK(kPackU32, true); else SMAP_PACK(kPackU32, false); }
+        else { if (clear) SMAP_PACK(kPackF64, true); else SMAP_PACK(kPackF64, false); }
+#undef SMAP_PACK
         CK(cudaGetLastError());
     }
     return SMAP_OK;
@@ -846,14 +873,16 @@ int launch_pack(const smap_handle* h, int pack, int row0, int rows, int wx0, int
 
 // rows [dst_row0, dst_row0 + rows) of a (*, dst_mw, C) float64 array <- rows [src_row0, ...) of the packed buffer
 int launch_unpack(const smap_handle* h, int pack, double* dst, int dst_mw, int dst_row0, int rows, int y0, int cols,
-                  const void* in, int src_row0, cudaStream_t st) {
+                  const void* in, int src_row0, cudaStream_t st, bool add = false) {
     const int c = h->cfg.num_classes, run = cols * c, run_words = pack == kPackU16 ? (run + 1) / 2 : run;
     for (int done = 0; done < rows; done += 32768) {
         const int n = rows - done < 32768 ? rows - done : 32768;
         const dim3 g = window_grid(pack == kPackU16 ? run_words : run, n);
-        if (pack == kPackU16) k_unpack_window<kPackU16><<<g, kThreads, 0, st>>>(dst, dst_mw, c, dst_row0 + done, y0, run, run_words, in, src_row0 + done);
-        else if (pack == kPackU32) k_unpack_window<kPackU32><<<g, kThreads, 0, st>>>(dst, dst_mw, c, dst_row0 + done, y0, run, run_words, in, src_row0 + done);
-        else k_unpack_window<kPackF64><<<g, kThreads, 0, st>>>(dst, dst_mw, c, dst_row0 + done, y0, run, run_words, in, src_row0 + done);
+#define SMAP_UNPACK(P, AD) k_unpack_window<P, AD><<<g, kThreads, 0, st>>>(dst, dst_mw, c, dst_row0 + done, y0, run, run_words, in, src_row0 + done)
+        if (pack == kPackU16) { if (add) SMAP_UNPACK(kPackU16, true); else SMAP_UNPACK(kPackU16, false); }
+        else if (pack == kPackU32) { if (add) SMAP_UNPACK(kPackU32, true); else SMAP_UNPACK(kPackU32, false); }
+        else { if (add) SMAP_UNPACK(kPackF64, true); else SMAP_UNPACK(kPackF64, false); }
+#undef SMAP_UNPACK
         CK(cudaGetLastError());
     }
     return SMAP_OK;
@@ -933,16 +962,20 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
         if (e == cudaSuccess) { h->own_map = true; e = cudaMemset(h->map, 0, map_bytes); }
         h->integer_grid = true;
     }
+    h->acc = h->map;
     h->slot_words = (h->cells + 3) / 4 * 4;
     if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->slot_words);
     if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->slot_words);
     if (e == cudaSuccess) h->n_slots = 1;
-    if (e == cudaSuccess) e = cudaMalloc(&h->boxes, sizeof(FrameBox) * (2 * kMaxBatch + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&h->boxes, sizeof(FrameBox) * (2 * kMaxBatch + 3));
     if (e == cudaSuccess) {
-        FrameBox init[2 * kMaxBatch + 1];
-        for (int i = 0; i < 2 * kMaxBatch + 1; ++i) { init[i].x0 = 0x7fffffff; init[i].x1 = -1; init[i].y0 = 0x7fffffff; init[i].y1 = -1; }
+        FrameBox init[2 * kMaxBatch + 3];
+        for (int i = 0; i < 2 * kMaxBatch + 3; ++i) { init[i].x0 = 0x7fffffff; init[i].x1 = -1; init[i].y0 = 0x7fffffff; init[i].y1 = -1; }
         e = cudaMemcpy(h->boxes, init, sizeof init, cudaMemcpyHostToDevice);
         h->ubox = h->boxes + 2 * kMaxBatch;
+        h->dbox[0] = h->ubox + 1;
+        h->dbox[1] = h->ubox + 2;
+        h->abox = h->ubox;
     }
     // a caller-owned grid that is not declared zero may hold anything anywhere
     h->ubox_full = cfg->map_dev && !cfg->map_is_zero;
@@ -973,6 +1006,15 @@ int smap_destroy(smap_handle* h) {
     if (h->comm && h->own_comm && nccl_api().lib) nccl_api().CommDestroy(h->comm);
     cudaFree(h->xbuf); cudaFree(h->xbuf2); cudaFree(h->xch_dev);
     if (h->xch_host) cudaFreeHost(h->xch_host);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(h->delta[b]); cudaFree(h->xch_dev2[b]);
+        if (h->xch_host2[b]) cudaFreeHost(h->xch_host2[b]);
+        if (h->ev_agreed[b]) cudaEventDestroy(h->ev_agreed[b]);
+        if (h->ev_packed[b]) cudaEventDestroy(h->ev_packed[b]);
+    }
+    if (h->ev_chunk) cudaEventDestroy(h->ev_chunk);
+    if (h->ev_exchanged) cudaEventDestroy(h->ev_exchanged);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     cudaFree(h->keep); cudaFree(h->iu); cudaFree(h->iv); cudaFree(h->blk_count); cudaFree(h->blk_offset);
     if (h->ev_fork) {
         cudaEventDestroy(h->ev_fork);
@@ -1083,12 +1125,17 @@ int smap_update(smap_handle* h, double* map_dev, const double* pcd, int64_t ld, 
     CK(cudaGetLastError());
     h->stats.kernel_launches += 1;
     h->last_stream = st;
-    if (!map_dev || map_dev == h->map) {
+    double* target = map_dev ? map_dev : h->acc;
+    if (target == h->acc) {
+        acc_integer(h) = acc_integer(h) && h->identity_cm;
+        acc_bound(h) += 3;
+    } else if (target == h->map) {   // streaming: the caller named the grid itself
         h->integer_grid = h->integer_grid && h->identity_cm;
         h->value_bound += 3;
+        h->ubox_full = true;          // k_apply folds the frame's box into the accumulation window, not the grid's
     }
     h->last_update_counted = true;
-    return launch_apply(h, map_dev ? map_dev : h->map, 1, st);
+    return launch_apply(h, target, 1, st);
 }
 
 int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames, void* stream) {
@@ -1122,10 +1169,10 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
         // the count update on a grid of integer-valued counts may add its increments with float64 atomics (exact
         // in any order): de-duplicated with per-(cell, class) frame tags when there are few classes, through the
         // per-frame cell masks otherwise; everything else goes through the ordered apply
-        const bool count_atomics = f4 && h->identity_cm && h->integer_grid &&
+        const bool count_atomics = f4 && h->identity_cm && acc_integer(h) &&
                                    h->cells * (int64_t)(h->cfg.num_classes + 1) < ((int64_t)1 << 32);
         const int mode = !count_atomics ? 0 : (h->cfg.num_classes + 1 <= SMAP_TAG_MAX_PLANES ? 1 : 2);
-        if (!h->identity_cm) h->integer_grid = false;
+        if (!h->identity_cm) acc_integer(h) = false;
         int rc = mode == 1 ? SMAP_OK : ensure_slots(h, chunk);
         if (rc) return rc;
         int used = 0;
@@ -1144,7 +1191,7 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
         // also after a failed launch: the frames queued so far are applied / their slots cleared, so that the slots are
         // all zero and the boxes reset when the call returns (the error is still reported)
         int rc2 = SMAP_OK;
-        if (used > 0 && mode == 0) rc2 = launch_apply(h, h->map, used, st);
+        if (used > 0 && mode == 0) rc2 = launch_apply(h, h->acc, used, st);
         if (used > 0 && mode == 2) rc2 = launch_clear(h, used, st);
         h->last_update_counted = mode == 0;
         if (pr) cudaEventRecord(pr->e[2], st);
@@ -1152,7 +1199,7 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
             h->stats.frames += 1;
             h->stats.points += frames[begin + i].n_points;
         }
-        h->value_bound += 3 * (int64_t)used;
+        acc_bound(h) += 3 * (int64_t)used;
         if (rc) return rc;
         if (rc2) return rc2;
         begin += chunk;
@@ -1312,6 +1359,18 @@ int smap_map_ptr(smap_handle* h, double** map_dev, int64_t* n_elements) {
 int smap_clear(smap_handle* h, void* stream) {
     if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
     DeviceGuard guard(h->cfg.device);
+    if (h->streaming) {
+        // exchanges still in flight add to the grid on the communication stream: let them land first; increments
+        // not yet handed to smap_exchange_async are dropped with the rest
+        int rc = smap_exchange_flush(h, stream);
+        if (rc) return rc;
+        if (h->d_bound[h->cur] != 0 || !h->d_integer[h->cur]) {
+            CK(cudaMemsetAsync(h->delta[h->cur], 0, sizeof(double) * (size_t)h->cells * h->cfg.num_classes, static_cast<cudaStream_t>(stream)));
+            k_box_set<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->dbox[h->cur], 0x7fffffff, -1, 0x7fffffff, -1);
+            h->d_bound[h->cur] = 0;
+            h->d_integer[h->cur] = true;
+        }
+    }
     CK(cudaMemsetAsync(h->map, 0, sizeof(double) * (size_t)h->cells * h->cfg.num_classes, static_cast<cudaStream_t>(stream)));
     k_box_set<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->ubox, 0x7fffffff, -1, 0x7fffffff, -1);
     CK(cudaGetLastError());
@@ -1521,6 +1580,7 @@ int smap_comm_get_info(smap_handle* h, smap_comm_info* out) {
 int smap_allreduce(smap_handle* h, void* stream) {
     if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
     if (!h->comm) return fail(SMAP_ERR_STATE, "no communicator (smap_comm_init / smap_comm_attach)");
+    if (h->streaming) return fail(SMAP_ERR_STATE, "streaming exchange active: smap_comm_streaming(h, 0) first");
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     h->last_stream = st;
@@ -1546,7 +1606,7 @@ int smap_allreduce(smap_handle* h, void* stream) {
     const size_t bytes = count * (pack == kPackF64 ? 8 : 4);
     rc = ensure_bytes(&h->xbuf, &h->xbuf_cap, bytes);
     if (rc) return rc;
-    rc = launch_pack(h, pack, x0, rows, x0, x1, y0, cols, h->xbuf, st);
+    rc = launch_pack(h, h->map, false, pack, x0, rows, x0, x1, y0, cols, h->xbuf, st);
     if (rc) return rc;
     NCCLCK(N.AllReduce(h->xbuf, h->xbuf, count, pack == kPackF64 ? ncclFloat64 : ncclUint32, ncclSum, h->comm, st));
     rc = launch_unpack(h, pack, h->map, h->cfg.map_width, x0, rows, y0, cols, h->xbuf, 0, st);
@@ -1564,6 +1624,8 @@ int smap_reduce_scatter_rows(smap_handle* h, double* tile_dev, int64_t tile_rows
                              int32_t* top_out, int32_t* bottom_out, void* stream) {
     if (!h || !tile_dev || !r0_out || !r1_out || !top_out || !bottom_out) return fail(SMAP_ERR_INVALID, "NULL argument");
     if (!h->comm) return fail(SMAP_ERR_STATE, "no communicator (smap_comm_init / smap_comm_attach)");
+    if (h->streaming)   // every rank's grid already holds the global sum: take the rows from it
+        return fail(SMAP_ERR_STATE, "streaming exchange active: smap_comm_streaming(h, 0) first");
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     h->last_stream = st;
@@ -1602,7 +1664,7 @@ int smap_reduce_scatter_rows(smap_handle* h, double* tile_dev, int64_t tile_rows
     if (rc) return rc;
     rc = ensure_bytes(&h->xbuf2, &h->xbuf2_cap, (size_t)(per + 2) * row_count * esize);
     if (rc) return rc;
-    rc = launch_pack(h, pack, 0, per * n, x0, x1, y0, cols, h->xbuf, st);
+    rc = launch_pack(h, h->map, false, pack, 0, per * n, x0, x1, y0, cols, h->xbuf, st);
     if (rc) return rc;
     NCCLCK(N.ReduceScatter(h->xbuf, h->xbuf2, (size_t)per * row_count, dt, ncclSum, h->comm, st));
     // halo exchange: everybody publishes the first and the last row of its tile (rows of an empty tile: whatever)
@@ -1626,6 +1688,150 @@ int smap_reduce_scatter_rows(smap_handle* h, double* tile_dev, int64_t tile_rows
     }
     h->comm_last.bytes = (int64_t)((size_t)per * n * row_count * esize);
     h->stats.kernel_launches += 4;
+    return SMAP_OK;
+}
+
+// ---- streaming exchange: the ranks' increments are summed into every rank's grid while integration goes on ---------
+namespace {
+
+// Data phase of the exchange whose agreement is in flight: pack + zero the buffer's window, all-reduce, add to the
+// grid -- all on the internal communication stream.  Blocks the HOST until the agreement has arrived (it was queued
+// one call earlier, behind a chunk that has normally long finished), never the caller's stream.
+int finish_pending(smap_handle* h) {
+    if (!h->pend_active) return SMAP_OK;
+    NcclApi& N = nccl_api();
+    const int b = h->pend_buf;
+    cudaStream_t cs = h->comm_stream;
+    CK(cudaEventSynchronize(h->ev_agreed[b]));
+    h->pend_active = false;
+    const int* ag = h->xch_host2[b];
+    const int x0 = -ag[0], x1 = ag[1], y0 = -ag[2], y1 = ag[3];
+    int64_t bound_total = 0;
+    const int pack = pick_pack(h, ag, &bound_total);
+    h->comm_last.window[0] = x0; h->comm_last.window[1] = x1; h->comm_last.window[2] = y0; h->comm_last.window[3] = y1;
+    h->comm_last.pack = pack;
+    h->comm_last.bytes = 0;
+    h->comm_last.exchanges += 1;
+    if (ag[5]) h->integer_grid = false;
+    h->value_bound += bound_total;
+    h->d_integer[b] = true;      // zeroed below
+    h->d_bound[b] = 0;
+    if (x1 >= x0 && y1 >= y0) {
+        const int rows = x1 - x0 + 1, cols = y1 - y0 + 1, c = h->cfg.num_classes;
+        const int64_t run = (int64_t)cols * c;
+        if (run >= ((int64_t)1 << 31)) return fail(SMAP_ERR_INVALID, "grid row too long for the packed exchange");
+        const int64_t run_words = pack == kPackU16 ? (run + 1) / 2 : run;
+        const size_t count = (size_t)rows * (size_t)(pack == kPackF64 ? run : run_words);
+        const size_t bytes = count * (pack == kPackF64 ? 8 : 4);
+        int rc = ensure_bytes(&h->xbuf, &h->xbuf_cap, bytes);
+        if (rc) return rc;
+        rc = launch_pack(h, h->delta[b], true, pack, x0, rows, x0, x1, y0, cols, h->xbuf, cs);
+        if (rc) return rc;
+        k_box_set<<<1, 32, 0, cs>>>(h->dbox[b], 0x7fffffff, -1, 0x7fffffff, -1);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev_packed[b], cs));
+        h->packed_recorded[b] = true;
+        NCCLCK(N.AllReduce(h->xbuf, h->xbuf, count, pack == kPackF64 ? ncclFloat64 : ncclUint32, ncclSum, h->comm, cs));
+        rc = launch_unpack(h, pack, h->map, h->cfg.map_width, x0, rows, y0, cols, h->xbuf, 0, cs, true);
+        if (rc) return rc;
+        k_box_fold<<<1, 32, 0, cs>>>(h->ubox, x0, x1, y0, y1);
+        CK(cudaGetLastError());
+        h->comm_last.bytes = (int64_t)bytes;
+        h->stats.kernel_launches += 4;
+    } else {
+        CK(cudaEventRecord(h->ev_packed[b], cs));
+        h->packed_recorded[b] = true;
+    }
+    CK(cudaEventRecord(h->ev_exchanged, cs));
+    return SMAP_OK;
+}
+
+}  // namespace
+
+int smap_comm_streaming(smap_handle* h, int on, void* stream) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!on) {
+        if (!h->streaming) return SMAP_OK;
+        int rc = smap_exchange_flush(h, stream);
+        if (rc) return rc;
+        if (h->d_bound[h->cur] != 0) return fail(SMAP_ERR_STATE, "frames integrated since the last smap_exchange_async would be lost");
+        h->streaming = false;
+        h->acc = h->map;
+        h->abox = h->ubox;
+        return SMAP_OK;
+    }
+    if (h->streaming) return SMAP_OK;
+    if (!h->comm) return fail(SMAP_ERR_STATE, "no communicator (smap_comm_init / smap_comm_attach)");
+    const size_t map_bytes = sizeof(double) * (size_t)h->cells * h->cfg.num_classes;
+    if (!h->delta[0]) {
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, greatest));
+        CK(cudaEventCreateWithFlags(&h->ev_chunk, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_exchanged, cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaEventCreateWithFlags(&h->ev_agreed[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_packed[b], cudaEventDisableTiming));
+            CK(cudaMalloc(&h->xch_dev2[b], sizeof(int) * kCommWords));
+            CK(cudaHostAlloc(&h->xch_host2[b], sizeof(int) * kCommWords, cudaHostAllocDefault));
+            CK(cudaMalloc(&h->delta[b], map_bytes));
+            CK(cudaMemset(h->delta[b], 0, map_bytes));   // device-synchronous: done before anything queued later
+        }
+    }
+    // the buffers are zero and their boxes empty between streaming sessions (every exchange leaves them so)
+    h->cur = 0;
+    h->d_integer[0] = h->d_integer[1] = true;
+    h->d_bound[0] = h->d_bound[1] = 0;
+    h->packed_recorded[0] = h->packed_recorded[1] = false;
+    h->streaming = true;
+    h->acc = h->delta[0];
+    h->abox = h->dbox[0];
+    h->last_stream = st;
+    return SMAP_OK;
+}
+
+int smap_exchange_async(smap_handle* h, void* stream) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    if (!h->streaming) return fail(SMAP_ERR_STATE, "smap_comm_streaming(h, 1) first");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream), cs = h->comm_stream;
+    h->last_stream = st;
+    NcclApi& N = nccl_api();
+    // 1. the previous exchange's data phase (its agreement has normally arrived long ago)
+    int rc = finish_pending(h);
+    if (rc) return rc;
+    // 2. this exchange's agreement, behind the chunk the caller has queued so far
+    const int b = h->cur;
+    CK(cudaEventRecord(h->ev_chunk, st));
+    CK(cudaStreamWaitEvent(cs, h->ev_chunk, 0));
+    const int vb = h->d_bound[b] > 0x7fffffffll ? 0x7fffffff : (int)h->d_bound[b];
+    k_comm_prep<<<1, 32, 0, cs>>>(h->dbox[b], 0, h->cfg.map_height, h->cfg.map_width, vb, h->d_integer[b] ? 0 : 1, h->xch_dev2[b]);
+    CK(cudaGetLastError());
+    NCCLCK(N.AllReduce(h->xch_dev2[b], h->xch_dev2[b], kCommWords, ncclInt32, ncclMax, h->comm, cs));
+    CK(cudaMemcpyAsync(h->xch_host2[b], h->xch_dev2[b], sizeof(int) * kCommWords, cudaMemcpyDeviceToHost, cs));
+    CK(cudaEventRecord(h->ev_agreed[b], cs));
+    h->pend_active = true;
+    h->pend_buf = b;
+    // 3. the next frames go to the other buffer -- once its previous content has been packed and zeroed
+    h->cur ^= 1;
+    h->acc = h->delta[h->cur];
+    h->abox = h->dbox[h->cur];
+    if (h->packed_recorded[h->cur]) CK(cudaStreamWaitEvent(st, h->ev_packed[h->cur], 0));
+    return SMAP_OK;
+}
+
+int smap_exchange_flush(smap_handle* h, void* stream) {
+    if (!h) return fail(SMAP_ERR_INVALID, "NULL handle");
+    if (!h->streaming) return SMAP_OK;
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    h->last_stream = st;
+    const bool had = h->pend_active;
+    int rc = finish_pending(h);
+    if (rc) return rc;
+    if (had || h->comm_last.exchanges > 0) CK(cudaStreamWaitEvent(st, h->ev_exchanged, 0));
     return SMAP_OK;
 }
 

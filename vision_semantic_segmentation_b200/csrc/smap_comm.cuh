@@ -87,21 +87,27 @@ enum { kPackU16 = 0, kPackU32 = 1, kPackF64 = 2 };
 // elements, each padded to `run_words` 32-bit words (kPackU16: 2 elements per word, kPackU32: 1; kPackF64: run doubles).
 // Rows outside the touched rows [wx0, wx1] (untouched on every rank, or the padding rows of the row-tiled exchange
 // beyond the grid) are written as zeros without reading the grid.
-template <int PACK>
+// CLEAR: the window is zeroed behind the read (streaming exchange: the packed grid is a buffer of local increments
+// that starts over after every exchange).
+template <int PACK, bool CLEAR = false>
 __global__ void __launch_bounds__(kThreads)
-k_pack_window(const double* __restrict__ map, int wx0, int wx1, int mw, int c, int x0, int y0, int run, int run_words,
+k_pack_window(double* __restrict__ map, int wx0, int wx1, int mw, int c, int x0, int y0, int run, int run_words,
               void* __restrict__ out) {
     const int row = x0 + (int)blockIdx.y;
     const bool real = row >= wx0 && row <= wx1;
-    const double* src = map + ((size_t)row * mw + y0) * c;
+    double* src = map + ((size_t)row * mw + y0) * c;
     if (PACK == kPackF64) {
         double* dst = reinterpret_cast<double*>(out) + (size_t)blockIdx.y * run;
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < run; e += gridDim.x * blockDim.x)
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < run; e += gridDim.x * blockDim.x) {
             dst[e] = real ? src[e] : 0.0;
+            if (CLEAR && real) src[e] = 0.0;
+        }
     } else if (PACK == kPackU32) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(out) + (size_t)blockIdx.y * run_words;
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < run; e += gridDim.x * blockDim.x)
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < run; e += gridDim.x * blockDim.x) {
             dst[e] = real ? (uint32_t)__double2uint_rn(src[e]) : 0u;
+            if (CLEAR && real) src[e] = 0.0;
+        }
     } else {
         uint32_t* dst = reinterpret_cast<uint32_t*>(out) + (size_t)blockIdx.y * run_words;
         for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < run_words; w += gridDim.x * blockDim.x) {
@@ -109,17 +115,31 @@ k_pack_window(const double* __restrict__ map, int wx0, int wx1, int mw, int c, i
             uint32_t lo = 0u, hi = 0u;
             if (real) {
                 lo = (uint32_t)__double2uint_rn(src[e]);
-                if (e + 1 < run) hi = (uint32_t)__double2uint_rn(src[e + 1]);
+                if (CLEAR) src[e] = 0.0;
+                if (e + 1 < run) {
+                    hi = (uint32_t)__double2uint_rn(src[e + 1]);
+                    if (CLEAR) src[e + 1] = 0.0;
+                }
             }
             dst[w] = lo | (hi << 16);
         }
     }
 }
 
+// box <- box UNION [x0, x1] x [y0, y1]
+__global__ void k_box_fold(FrameBox* __restrict__ box, int x0, int x1, int y0, int y1) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && x1 >= x0 && y1 >= y0) {
+        box->x0 = min(box->x0, x0); box->x1 = max(box->x1, x1);
+        box->y0 = min(box->y0, y0); box->y1 = max(box->y1, y1);
+    }
+}
+
 // The reduced buffer -> the grid: dst rows [dst_x0, dst_x0 + gridDim.y) of a (*, dst_mw, C) float64 array receive the
 // buffer rows [src_row0, ...), columns [y0, y0 + cols).  Used with dst = the handle's grid (all-reduce) and with
 // dst = the caller's row tile (reduce-scatter; dst_x0 = tile row of the first received row).
-template <int PACK>
+// ADD: the window receives grid + buffer instead of the buffer (streaming exchange: the buffer holds the ranks' summed
+// increments since the previous exchange).
+template <int PACK, bool ADD = false>
 __global__ void __launch_bounds__(kThreads)
 k_unpack_window(double* __restrict__ dst, int dst_mw, int c, int dst_x0, int y0, int run, int run_words,
                 const void* __restrict__ in, int src_row0) {
@@ -127,18 +147,19 @@ k_unpack_window(double* __restrict__ dst, int dst_mw, int c, int dst_x0, int y0,
     double* out = dst + ((size_t)(dst_x0 + (int)blockIdx.y) * dst_mw + y0) * c;
     if (PACK == kPackF64) {
         const double* src = reinterpret_cast<const double*>(in) + srow * run;
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < run; e += gridDim.x * blockDim.x) out[e] = src[e];
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < run; e += gridDim.x * blockDim.x)
+            out[e] = ADD ? __dadd_rn(out[e], src[e]) : src[e];
     } else if (PACK == kPackU32) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(in) + srow * run_words;
         for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < run; e += gridDim.x * blockDim.x)
-            out[e] = (double)src[e];
+            out[e] = ADD ? __dadd_rn(out[e], (double)src[e]) : (double)src[e];
     } else {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(in) + srow * run_words;
         for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < run_words; w += gridDim.x * blockDim.x) {
             const uint32_t v = src[w];
             const int e = 2 * w;
-            out[e] = (double)(v & 0xffffu);
-            if (e + 1 < run) out[e + 1] = (double)(v >> 16);
+            out[e] = ADD ? __dadd_rn(out[e], (double)(v & 0xffffu)) : (double)(v & 0xffffu);
+            if (e + 1 < run) out[e + 1] = ADD ? __dadd_rn(out[e + 1], (double)(v >> 16)) : (double)(v >> 16);
         }
     }
 }

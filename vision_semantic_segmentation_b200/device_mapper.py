@@ -240,6 +240,20 @@ class DeviceMapper(object):
         rows = r1.value - r0.value + top.value + bottom.value
         return tile[:rows], r0.value, r1.value, top.value, bottom.value
 
+    def set_streaming(self, on=True):
+        """``smap_comm_streaming``: integrate into buffers of local increments that ``exchange_async`` sums into every
+        rank's grid while the next frames are integrated (``include/smap.h``)."""
+        _native.check(self._lib.smap_comm_streaming(self._h, int(bool(on)), self._stream()))
+
+    def exchange_async(self):
+        """Collective (same call sequence on every rank): hand the increments integrated since the previous call to
+        the other ranks; returns without waiting for the collective (``smap_exchange_async``)."""
+        _native.check(self._lib.smap_exchange_async(self._h, self._stream()))
+
+    def exchange_flush(self):
+        """The current stream waits until every exchange queued so far has been added to the grid."""
+        _native.check(self._lib.smap_exchange_flush(self._h, self._stream()))
+
     def comm_info(self):
         info = _native.SmapCommInfo()
         _native.check(self._lib.smap_comm_get_info(self._h, ctypes.byref(info)))

@@ -18,7 +18,18 @@ tile plus a one-row halo from each neighbour -- ``render_row_tile`` filters and 
 """
 
 __all__ = ["rank_and_world", "shard_range", "sum_grids", "init_from_env", "row_tile", "sum_grid_row_tile",
-           "render_row_tile", "gather_rgb_rows"]
+           "render_row_tile", "gather_rgb_rows", "backend_is_nccl"]
+
+
+def backend_is_nccl(group=None):
+    """True when torch.distributed runs over NCCL: the grids are then summed by the library's own exchange under the
+    C ABI (``smap_exchange_async`` / ``smap_allreduce``: touched window only, counts packed); other backends (gloo in the
+    CPU tests) go through ``sum_grids`` / ``sum_grid_row_tile`` below."""
+    try:
+        import torch.distributed as dist
+    except ImportError:  # pragma: no cover
+        return False
+    return dist.is_available() and dist.is_initialized() and "nccl" in str(dist.get_backend(group))
 
 
 def rank_and_world():

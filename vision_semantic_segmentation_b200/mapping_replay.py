@@ -254,11 +254,13 @@ class SemanticMapping(object):
         map[...] = tmp.cpu().numpy()
         return map
 
-    def integrate_frame(self, frame_input_dict):
-        """Fused project_pcd + update_map of one recorded frame into the device grid."""
+    def _feed_item(self, frame_input_dict):
+        """One recorded frame (``src/mapping.py:309-312``; optional ``points`` / ``camera_id`` / ``semantic_ids`` /
+        ``image_size`` keys, see the module docstring) as a ``replay_feed.FeedItem``; None when it has no cloud."""
+        from .replay_feed import FeedItem
         pcd = frame_input_dict["points"] if "points" in frame_input_dict else frame_input_dict["pcd"]
         if pcd is None:
-            return
+            return None
         cam = self.cam1
         if frame_input_dict.get("camera_id", 1) == 6:
             cam = self.cam6
@@ -271,33 +273,82 @@ class SemanticMapping(object):
                 size = (int(cam.imSize[1]), int(cam.imSize[0]))
         else:
             image, size = frame_input_dict["semantic_image"], None
-        frame, keep = self._frame_for(pcd, frame_input_dict["pcd_frame_id"], image, frame_input_dict["pose"], cam,
-                                      image_size=size)
-        self.device_mapper.integrate(frame)
+        T = self.world_to_velodyne(frame_input_dict["pose"]) if frame_input_dict["pcd_frame_id"] != "velodyne" else None
+        return FeedItem(pcd, image, T, cam, size)
+
+    def integrate_frame(self, frame_input_dict):
+        """Fused project_pcd + update_map of one recorded frame into the device grid."""
+        self.integrate_frames([frame_input_dict])
+
+    def integrate_frames(self, frame_input_dicts, after_batch=None):
+        """Fused project_pcd + update_map of a sequence of recorded frames, in order: streamed to the GPU through the
+        pinned, multi-buffered feed of ``replay_feed`` and integrated ``FEED_BATCH`` frames per ``smap_integrate_batch``
+        call.  Returns the number of frames integrated."""
+        from .replay_feed import FrameFeeder
+        dm = self.device_mapper
+        if self._feeder is None:
+            self._feeder = FrameFeeder(dm, batch=self.FEED_BATCH, depth=self.FEED_DEPTH)
+        items = (it for it in (self._feed_item(fr) for fr in frame_input_dicts) if it is not None)
+        return self._feeder.run(items, after_batch=after_batch)
+
+    FEED_BATCH = 8     # frames per smap_integrate_batch call of the host-fed replay (PCIe-bound: larger buys nothing)
+    FEED_DEPTH = 3     # slot sets: one being integrated, two with copies queued
+    EXCHANGE_EVERY = 64   # multi-GPU: frames a rank integrates between two exchanges of the streaming sum
+    _feeder = None
 
     def mapping_replay(self, input_list, file_name, write_image=True, row_tiles=False):
         """Map all frames of ``input_list`` into a fresh grid, smooth, render, save
         ``global_map_<file_name>.png`` (``src/mapping_replay.py:175-211``).  Returns the colour map.
-        Under torch.distributed the frames are sharded over the ranks.  ``row_tiles=False``: the grids are all-reduced
-        and every rank filters and renders the whole map (``self.map`` = the filtered map, as in the reference).
-        ``row_tiles=True`` (large maps): the grids are reduce-scattered by rows, every rank filters and renders its own
-        tile (one-row halos from the neighbours), the image is all-gathered; ``self.map`` then holds the filtered rows
-        of this rank's tile only, zeros elsewhere."""
+        Under torch.distributed the frames are sharded over the ranks.  With NCCL the per-rank
+        increments are summed into every rank's grid by the library's streaming exchange (``smap_exchange_async``:
+        touched window only, counts packed, overlapped with the integration of the next frames); other backends
+        (gloo in CPU tests) all-reduce the grids through torch.distributed at the end.
+        ``row_tiles=False``: every rank filters and renders the whole map (``self.map`` = the filtered map, as in the
+        reference).  ``row_tiles=True`` (large maps): every rank filters and renders its own row tile (one-row halos
+        from the neighbouring tiles), the image is all-gathered; ``self.map`` then holds the filtered rows of this
+        rank's tile only, zeros elsewhere."""
         from . import frame_sharding
         dm = self.device_mapper
+        rank, world = frame_sharding.rank_and_world()
+        native_comm = world > 1 and frame_sharding.backend_is_nccl()
+        if native_comm:
+            dm.init_comm()
+            dm.set_streaming(True)
         dm.clear()
         self._map_valid = True
-        rank, world = frame_sharding.rank_and_world()
-        for idx in frame_sharding.shard_range(len(input_list), rank, world):
-            self.integrate_frame(input_list[idx])
+        shard = frame_sharding.shard_range(len(input_list), rank, world)
+        if native_comm:
+            # the same number of exchanges on every rank: one per EXCHANGE_EVERY frames of the longest shard
+            longest = -(-len(input_list) // world)
+            n_exchanges = max(1, -(-longest // self.EXCHANGE_EVERY))
+            state = {"done": 0}
+
+            def after_batch(n_frames):
+                while state["done"] < n_exchanges - 1 and n_frames >= (state["done"] + 1) * self.EXCHANGE_EVERY:
+                    dm.exchange_async()
+                    state["done"] += 1
+            self.integrate_frames((input_list[idx] for idx in shard), after_batch=after_batch)
+            while state["done"] < n_exchanges:
+                dm.exchange_async()
+                state["done"] += 1
+            dm.exchange_flush()
+            dm.set_streaming(False)
+        else:
+            self.integrate_frames(input_list[idx] for idx in shard)
         if world > 1 and row_tiles:
-            tile, r0, r1, top, bottom = frame_sharding.sum_grid_row_tile(dm.map)
+            if native_comm:     # every rank holds the summed grid: its tile and the halo rows are slices of it
+                r0, r1 = frame_sharding.row_tile(dm.map.shape[0], rank, world)
+                top, bottom = (1 if r0 > 0 and r1 > r0 else 0), (1 if r1 < dm.map.shape[0] and r1 > r0 else 0)
+                tile = dm.map[r0 - top:r1 + bottom]
+            else:
+                tile, r0, r1, top, bottom = frame_sharding.sum_grid_row_tile(dm.map)
             rgb_tile, filtered = frame_sharding.render_row_tile(tile, top, bottom, self.label_colors, return_filtered=True)
             color_map = frame_sharding.gather_rgb_rows(rgb_tile, dm.map.shape[0])
+            filtered = filtered.clone()
             dm.map.zero_()
             dm.map[r0:r1].copy_(filtered)
         else:
-            if world > 1:
+            if world > 1 and not native_comm:
                 frame_sharding.sum_grids(dm.map)
             color_map, filtered = filter_and_render(dm.map, self.label_colors, return_filtered=True)
             dm.map.copy_(filtered)  # self.map = apply_filter(self.map)
