@@ -15,9 +15,9 @@ Timed region: R blocks of exactly K steps, back to back, R chosen so that the re
 0.3 ms); barrier + synchronize on both sides, CUDA events, max over ranks.  `ms_per_step` = region / (R K); the per-block
 figures (median / min / max) are printed next to it.
 N > 1: one process per GPU (torchrun), frames sharded by rank (weak scaling: every rank integrates K frames per block).
-Every block ends with one exchange of the ranks' increments (smap_exchange_async: touched window only, counts packed as
-uint16 pairs, NCCL all-reduce on an internal stream, overlapped with the next block's frames); the region ends when the
-last exchange has been added to every rank's grid.  After the timed region the exchanged grid is compared with a plain
+Every --exchange-every (256) frames the ranks' increments are summed (smap_exchange_async: touched window only, counts
+packed as uint16 pairs, NCCL all-reduce on an internal stream, overlapped with the next frames); the region ends when the
+last exchange -- behind the last frame -- has been added to every rank's grid.  After the timed region the exchanged grid is compared with a plain
 torch.distributed all-reduce of the per-rank grids (bit for bit in count mode).
 Workloads: cfg2 (default), cfg3 (log-likelihood update, 10^4 x 10^4 grid), cfg4 (8000 frames in total, sharded: strong
 scaling), cfg5 (cam1 + cam6 frames into a 10^4 x 10^4 grid, row-tiled filter + render + image gather inside the region).
@@ -97,6 +97,9 @@ def parse_args():
     ap.add_argument("--repeats", type=int, default=0,
                     help="blocks of --steps steps in the timed region (0: as many as make the region last >= 50 ms)")
     ap.add_argument("--min-region-ms", type=float, default=50.0)
+    ap.add_argument("--exchange-every", type=int, default=256,
+                    help="N > 1: frames a rank integrates between two exchanges of the streaming sum (as "
+                         "SemanticMapping.EXCHANGE_EVERY); the last exchange ends the timed region")
     ap.add_argument("--frames", type=int, default=8000, help="cfg4: frames of the whole job, sharded over the ranks")
     ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=48, help="frames of the end-to-end legs")
@@ -371,8 +374,9 @@ def workload_config(args, world):
             "grid": [MAP_H, MAP_W, args.classes], "update": "log-likelihood" if log_update(args) else "count",
             "frames_per_rank_per_block": args.steps,
             "parallelism": ("single GPU" if world == 1 else
-                            "frames sharded over %d ranks; one exchange of the increments per block (touched window, packed "
-                            "counts, NCCL all-reduce on an internal stream, overlapped with the next block)" % world),
+                            "frames sharded over %d ranks; the ranks' increments are summed every %d frames per rank (touched "
+                            "window, packed counts, NCCL all-reduce on an internal stream, overlapped with the next frames)"
+                            % (world, getattr(args, "exchange_every", 256))),
             "l2_policy": "inputs larger than L2: ring of %d distinct frames (%.0f MB) resident in HBM"
                          % (args.ring, args.ring * (args.points * 16 + 1440 * 1920 * (1 if ids else 3)) / 1e6)}
 
@@ -475,7 +479,7 @@ def run_b200(args):
     block(max(args.warmup, 3))
     if world > 1:
         for _ in range(3):
-            block(min(args.steps, 32))
+            block(min(args.exchange_every, 64))
             dm.exchange_async()
         dm.exchange_flush()
     if args.workload == "cfg5":
@@ -505,13 +509,20 @@ def run_b200(args):
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(repeats + 1)]
     e_end = torch.cuda.Event(enable_timing=True)
     barrier()
+    since, n_exchanges = 0, 0
     for r in range(repeats):
         marks[r].record()
         block(args.steps)
-        if world > 1:
+        since += args.steps
+        while world > 1 and since >= args.exchange_every:
             dm.exchange_async()
+            since -= args.exchange_every
+            n_exchanges += 1
     marks[repeats].record()
     if world > 1:
+        if since > 0 or n_exchanges == 0:
+            dm.exchange_async()
+            n_exchanges += 1
         dm.exchange_flush()
     if args.workload == "cfg5":
         rgb_full = render_tiles()
@@ -535,9 +546,10 @@ def run_b200(args):
     if world > 1:
         info = dm.comm_info()
         # one block, then the exchange alone (nothing to overlap with): agreement + pack + all-reduce + unpack, host included
+        n_x = min(args.exchange_every, max(args.steps, 16))   # frames behind the exchange that is timed and checked
         dm.clear()
         pos[0] = 0
-        block(args.steps)
+        block(n_x)
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
@@ -546,10 +558,11 @@ def run_b200(args):
         torch.cuda.synchronize()
         exch_ms = 1e3 * (time.perf_counter() - t0)
         got = dm.map.clone()
+        phases = dm.comm_info()
         dm.set_streaming(False)
         dm.clear()
         pos[0] = 0
-        block(args.steps)
+        block(n_x)
         want = dm.map.clone()
         dist.all_reduce(want, op=dist.ReduceOp.SUM)
         if log_update(args):
@@ -561,7 +574,9 @@ def run_b200(args):
         tt = torch.tensor([exch_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         collective = {"exchange_alone_ms": float(tt.item()), "bytes_per_exchange": info["bytes"], "grid_bytes": info["grid_bytes"],
-                      "window": info["window"], "pack": info["pack"], "exchanges_in_region": repeats,
+                      "window": info["window"], "pack": info["pack"], "exchanges_in_region": n_exchanges,
+                      "frames_per_rank_between_exchanges": args.exchange_every, "frames_behind_the_timed_exchange": n_x,
+                      "pack_ms": phases["pack_ms"], "reduce_ms": phases["reduce_ms"], "add_ms": phases["add_ms"],
                       "parity_vs_torch_all_reduce": parity,
                       "note": "exchange_alone_ms: one exchange with nothing to overlap (agreement + pack + NCCL all-reduce + "
                               "unpack-add, host time included); inside the region the exchanges run on an internal stream "

@@ -251,6 +251,9 @@ typedef struct smap_comm_info {
     int64_t bytes;       /* last exchange: payload bytes this rank handed to NCCL */
     int64_t grid_bytes;  /* size of the whole float64 grid, for comparison */
     int64_t exchanges;   /* exchanges so far */
+    /* streaming exchange, last data phase (CUDA events on the internal stream; smap_comm_get_info waits for them): */
+    double pack_ms, reduce_ms, add_ms;
+    double host_wait_ms; /* host time the last smap_exchange_async spent waiting for the ranks' agreement */
 } smap_comm_info;
 /* rank 0: a fresh NCCL unique id, to be distributed to all ranks by the caller (MPI, torch.distributed, a file...). */
 SMAP_API int smap_comm_unique_id(uint8_t id_out[SMAP_COMM_ID_BYTES]);

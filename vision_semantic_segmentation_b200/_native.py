@@ -59,7 +59,8 @@ class SmapStats(ctypes.Structure):
 class SmapCommInfo(ctypes.Structure):
     _fields_ = [("n_ranks", ctypes.c_int32), ("rank", ctypes.c_int32), ("window", ctypes.c_int32 * 4),
                 ("pack", ctypes.c_int32), ("reserved", ctypes.c_int32), ("bytes", ctypes.c_int64),
-                ("grid_bytes", ctypes.c_int64), ("exchanges", ctypes.c_int64)]
+                ("grid_bytes", ctypes.c_int64), ("exchanges", ctypes.c_int64), ("pack_ms", ctypes.c_double),
+                ("reduce_ms", ctypes.c_double), ("add_ms", ctypes.c_double), ("host_wait_ms", ctypes.c_double)]
 
 
 class SmapError(RuntimeError):

@@ -115,6 +115,9 @@ struct smap_handle {
     bool pend_active = false;             // an agreement is in flight (its data phase is queued by the next call)
     int pend_buf = 0;
     int* xch_dev2[2] = {};                // agreement words of the streaming exchange, per buffer
+    cudaEvent_t ev_phase[4] = {};         // timing of the last data phase: start, packed, reduced, added
+    bool phase_recorded = false;
+    double host_wait_ms = 0.0;            // host time the last smap_exchange_async spent waiting for the agreement
     int* xch_host2[2] = {};
     // multi-GPU exchange (smap_comm_* / smap_allreduce / smap_reduce_scatter_rows)
     ncclComm_t comm = nullptr;
@@ -860,8 +863,8 @@ int launch_pack(const smap_handle* h, double* src, bool clear, int pack, int row
     for (int done = 0; done < rows; done += 32768) {
         const int n = rows - done < 32768 ? rows - done : 32768;
         void* o = static_cast<char*>(out) + (size_t)done * row_bytes;
-        const dim3 g = window_grid(pack == kPackU16 ? run_words : run, n);
-#define SMAP_PACK(P, CL) k_pack_window<P, CL><<<g, kThreads, 0, st>>>(src, wx0, wx1, h->cfg.map_width, c, row0 + done, y0, run, run_words, o)
+        const dim3 g = window_grid(pack == kPackU16 ? 2 * run_words : run, n);
+#define SMAP_PACK(P, CL) k_pack_window<P, CL><<<g, kThreads, 0, st>>>(src, wx0, wx1, h->cfg.map_width, c, row0 + done, y0, run, run_words, o, 0ll)
         if (pack == kPackU16) { if (clear) SMAP_PACK(kPackU16, true); else SMAP_PACK(kPackU16, false); }
         else if (pack == kPackU32) { if (clear) SMAP_PACK(kPackU32, true); else SMAP_PACK(kPackU32, false); }
         else { if (clear) SMAP_PACK(kPackF64, true); else SMAP_PACK(kPackF64, false); }
@@ -877,7 +880,7 @@ int launch_unpack(const smap_handle* h, int pack, double* dst, int dst_mw, int d
     const int c = h->cfg.num_classes, run = cols * c, run_words = pack == kPackU16 ? (run + 1) / 2 : run;
     for (int done = 0; done < rows; done += 32768) {
         const int n = rows - done < 32768 ? rows - done : 32768;
-        const dim3 g = window_grid(pack == kPackU16 ? run_words : run, n);
+        const dim3 g = window_grid(run, n);
 #define SMAP_UNPACK(P, AD) k_unpack_window<P, AD><<<g, kThreads, 0, st>>>(dst, dst_mw, c, dst_row0 + done, y0, run, run_words, in, src_row0 + done)
         if (pack == kPackU16) { if (add) SMAP_UNPACK(kPackU16, true); else SMAP_UNPACK(kPackU16, false); }
         else if (pack == kPackU32) { if (add) SMAP_UNPACK(kPackU32, true); else SMAP_UNPACK(kPackU32, false); }
@@ -1012,6 +1015,8 @@ int smap_destroy(smap_handle* h) {
         if (h->ev_agreed[b]) cudaEventDestroy(h->ev_agreed[b]);
         if (h->ev_packed[b]) cudaEventDestroy(h->ev_packed[b]);
     }
+    for (int i = 0; i < 4; ++i)
+        if (h->ev_phase[i]) cudaEventDestroy(h->ev_phase[i]);
     if (h->ev_chunk) cudaEventDestroy(h->ev_chunk);
     if (h->ev_exchanged) cudaEventDestroy(h->ev_exchanged);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -1571,6 +1576,15 @@ int smap_comm_destroy(smap_handle* h) {
 int smap_comm_get_info(smap_handle* h, smap_comm_info* out) {
     if (!h || !out) return fail(SMAP_ERR_INVALID, "NULL argument");
     *out = h->comm_last;
+    out->host_wait_ms = h->host_wait_ms;
+    out->pack_ms = out->reduce_ms = out->add_ms = 0.0;
+    if (h->phase_recorded && cudaEventSynchronize(h->ev_phase[3]) == cudaSuccess) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        cudaEventElapsedTime(&a, h->ev_phase[0], h->ev_phase[1]);
+        cudaEventElapsedTime(&b, h->ev_phase[1], h->ev_phase[2]);
+        cudaEventElapsedTime(&c, h->ev_phase[2], h->ev_phase[3]);
+        out->pack_ms = a; out->reduce_ms = b; out->add_ms = c;
+    }
     out->n_ranks = h->n_ranks;
     out->rank = h->rank;
     out->grid_bytes = (int64_t)sizeof(double) * h->cells * h->cfg.num_classes;
@@ -1702,7 +1716,13 @@ int finish_pending(smap_handle* h) {
     NcclApi& N = nccl_api();
     const int b = h->pend_buf;
     cudaStream_t cs = h->comm_stream;
-    CK(cudaEventSynchronize(h->ev_agreed[b]));
+    {
+        timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        CK(cudaEventSynchronize(h->ev_agreed[b]));
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        h->host_wait_ms = 1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec);
+    }
     h->pend_active = false;
     const int* ag = h->xch_host2[b];
     const int x0 = -ag[0], x1 = ag[1], y0 = -ag[2], y1 = ag[3];
@@ -1725,17 +1745,22 @@ int finish_pending(smap_handle* h) {
         const size_t bytes = count * (pack == kPackF64 ? 8 : 4);
         int rc = ensure_bytes(&h->xbuf, &h->xbuf_cap, bytes);
         if (rc) return rc;
+        CK(cudaEventRecord(h->ev_phase[0], cs));
         rc = launch_pack(h, h->delta[b], true, pack, x0, rows, x0, x1, y0, cols, h->xbuf, cs);
         if (rc) return rc;
         k_box_set<<<1, 32, 0, cs>>>(h->dbox[b], 0x7fffffff, -1, 0x7fffffff, -1);
         CK(cudaGetLastError());
         CK(cudaEventRecord(h->ev_packed[b], cs));
         h->packed_recorded[b] = true;
+        CK(cudaEventRecord(h->ev_phase[1], cs));
         NCCLCK(N.AllReduce(h->xbuf, h->xbuf, count, pack == kPackF64 ? ncclFloat64 : ncclUint32, ncclSum, h->comm, cs));
+        CK(cudaEventRecord(h->ev_phase[2], cs));
         rc = launch_unpack(h, pack, h->map, h->cfg.map_width, x0, rows, y0, cols, h->xbuf, 0, cs, true);
         if (rc) return rc;
         k_box_fold<<<1, 32, 0, cs>>>(h->ubox, x0, x1, y0, y1);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev_phase[3], cs));
+        h->phase_recorded = true;
         h->comm_last.bytes = (int64_t)bytes;
         h->stats.kernel_launches += 4;
     } else {
@@ -1771,6 +1796,7 @@ int smap_comm_streaming(smap_handle* h, int on, void* stream) {
         CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, greatest));
         CK(cudaEventCreateWithFlags(&h->ev_chunk, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_exchanged, cudaEventDisableTiming));
+        for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&h->ev_phase[i]));
         for (int b = 0; b < 2; ++b) {
             CK(cudaEventCreateWithFlags(&h->ev_agreed[b], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->ev_packed[b], cudaEventDisableTiming));

@@ -258,7 +258,8 @@ class DeviceMapper(object):
         info = _native.SmapCommInfo()
         _native.check(self._lib.smap_comm_get_info(self._h, ctypes.byref(info)))
         return {"n_ranks": info.n_ranks, "rank": info.rank, "window": list(info.window), "pack": ("u16", "u32", "f64")[info.pack],
-                "bytes": info.bytes, "grid_bytes": info.grid_bytes, "exchanges": info.exchanges}
+                "bytes": info.bytes, "grid_bytes": info.grid_bytes, "exchanges": info.exchanges,
+                "pack_ms": info.pack_ms, "reduce_ms": info.reduce_ms, "add_ms": info.add_ms, "host_wait_ms": info.host_wait_ms}
 
     def cloud_to_f32x4(self, pcd, out, flag):
         """(4, N) float64 CUDA cloud -> (N, 4) float32 ``out``; ``flag`` (int32 CUDA tensor of one element, zeroed by

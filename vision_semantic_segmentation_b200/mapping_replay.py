@@ -293,7 +293,7 @@ class SemanticMapping(object):
 
     FEED_BATCH = 8     # frames per smap_integrate_batch call of the host-fed replay (PCIe-bound: larger buys nothing)
     FEED_DEPTH = 3     # slot sets: one being integrated, two with copies queued
-    EXCHANGE_EVERY = 64   # multi-GPU: frames a rank integrates between two exchanges of the streaming sum
+    EXCHANGE_EVERY = 256  # multi-GPU: frames a rank integrates between two exchanges of the streaming sum
     _feeder = None
 
     def mapping_replay(self, input_list, file_name, write_image=True, row_tiles=False):
