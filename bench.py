@@ -458,13 +458,21 @@ def run_b200(args):
 
     ring_frames = [f for f, _, _ in ring_dev]
     pos = [0]   # position in the ring: blocks continue where the previous one stopped
+    xch = {"since": 0, "count": 0, "on": False}   # N > 1, timed region: frames since the last exchange, exchanges so far
 
     def block(steps):
-        """exactly `steps` frames through smap_integrate_batch, in balanced batches"""
+        """exactly `steps` frames through smap_integrate_batch, in balanced batches; inside the timed region of an
+        N > 1 run the ranks' increments are handed over every --exchange-every frames"""
         for take in balanced(steps, min(args.batch, len(ring_frames))):
             start = pos[0] % len(ring_frames)
             dm.integrate_batch((ring_frames + ring_frames)[start:start + take])
             pos[0] += take
+            if xch["on"]:
+                xch["since"] += take
+                if xch["since"] >= args.exchange_every:
+                    dm.exchange_async()
+                    xch["since"] = 0
+                    xch["count"] += 1
 
     def render_tiles():
         """cfg5: filter + render of this rank's row tile (one-row halos), image all-gathered"""
@@ -509,21 +517,18 @@ def run_b200(args):
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(repeats + 1)]
     e_end = torch.cuda.Event(enable_timing=True)
     barrier()
-    since, n_exchanges = 0, 0
+    xch["on"] = world > 1
     for r in range(repeats):
         marks[r].record()
         block(args.steps)
-        since += args.steps
-        while world > 1 and since >= args.exchange_every:
-            dm.exchange_async()
-            since -= args.exchange_every
-            n_exchanges += 1
     marks[repeats].record()
     if world > 1:
-        if since > 0 or n_exchanges == 0:
+        xch["on"] = False
+        if xch["since"] > 0 or xch["count"] == 0:   # the frames behind the last regular exchange
             dm.exchange_async()
-            n_exchanges += 1
+            xch["count"] += 1
         dm.exchange_flush()
+    n_exchanges = xch["count"]
     if args.workload == "cfg5":
         rgb_full = render_tiles()
     e_end.record()
@@ -544,7 +549,6 @@ def run_b200(args):
     # ---- N > 1: the exchange on its own, and parity of the exchanged grid against torch.distributed's all-reduce
     collective = None
     if world > 1:
-        info = dm.comm_info()
         # one block, then the exchange alone (nothing to overlap with): agreement + pack + all-reduce + unpack, host included
         n_x = min(args.exchange_every, max(args.steps, 16))   # frames behind the exchange that is timed and checked
         dm.clear()
@@ -573,8 +577,8 @@ def run_b200(args):
         parity["checksum"] = float(want.sum().item())
         tt = torch.tensor([exch_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        collective = {"exchange_alone_ms": float(tt.item()), "bytes_per_exchange": info["bytes"], "grid_bytes": info["grid_bytes"],
-                      "window": info["window"], "pack": info["pack"], "exchanges_in_region": n_exchanges,
+        collective = {"exchange_alone_ms": float(tt.item()), "bytes_per_exchange": phases["bytes"], "grid_bytes": phases["grid_bytes"],
+                      "window": phases["window"], "pack": phases["pack"], "exchanges_in_region": n_exchanges,
                       "frames_per_rank_between_exchanges": args.exchange_every, "frames_behind_the_timed_exchange": n_x,
                       "pack_ms": phases["pack_ms"], "reduce_ms": phases["reduce_ms"], "add_ms": phases["add_ms"],
                       "parity_vs_torch_all_reduce": parity,

@@ -32,7 +32,7 @@ extern "C" {
 #define SMAP_API
 #endif
 
-#define SMAP_ABI_VERSION 4
+#define SMAP_ABI_VERSION 5
 #define SMAP_MAX_CLASSES 31 /* C class bits + 1 intensity-boost bit in a 32-bit cell mask */
 #define SMAP_MAX_CAMERAS 8
 
@@ -288,6 +288,13 @@ SMAP_API int smap_comm_streaming(smap_handle *h, int on, void *stream);
 SMAP_API int smap_exchange_async(smap_handle *h, void *stream);
 SMAP_API int smap_exchange_flush(smap_handle *h, void *stream);
 SMAP_API int smap_comm_get_info(smap_handle *h, smap_comm_info *out);
+
+/* ---- the planar update (cfg.MAPPING.DEPTH_METHOD other than points_map / points_raw) ------------------------------
+ * src/mapping.py:446-488 warps the label image onto the map plane and then compares the warped uint8 image with the
+ * label NAMES (:474): never equal, so no cell is ever incremented; what does run is map_local[map_local < 0] = 0
+ * (:481).  That is the whole observable behaviour, and this is it (any float64 grid; -0.0 and NaN are left alone, as
+ * numpy's mask leaves them). */
+SMAP_API int smap_clamp_negative(double *map_dev, int64_t n_elements, int device, void *stream);
 
 /* ---- grid access ------------------------------------------------------------------------------- */
 SMAP_API int smap_map_ptr(smap_handle *h, double **map_dev, int64_t *n_elements);

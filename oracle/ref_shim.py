@@ -36,7 +36,8 @@ import types
 
 import numpy as np
 
-_BUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py: sourceless .pyc tree
+# oracle/build_ref.py: the reference's modules byte-compiled into one archive (imported with zipimport)
+_BUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_bytecode.zip")
 
 
 def _pick_reference():
@@ -52,6 +53,12 @@ REF = _pick_reference()
 
 
 def reference_available():
+    if REF.endswith(".zip"):
+        if not os.path.isfile(REF):
+            return False
+        import zipfile
+        with zipfile.ZipFile(REF) as z:
+            return "src/mapping_replay.pyc" in z.namelist()
     return any(os.path.isfile(os.path.join(REF, "src", "mapping_replay" + ext)) for ext in (".py", ".pyc"))
 
 

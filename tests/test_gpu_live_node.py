@@ -73,3 +73,27 @@ def test_live_node_reproduces_reference_golden(tmp_path, variant):
     if variant == "class_ids":
         again.set_label_palette(syn.COLORS_19)
     assert np.array_equal(again.mapping_replay(back, "again", write_image=False), case.arrays["rgb"])
+
+
+def test_planar_update_is_the_references_clamp(tmp_path):
+    """cfg.MAPPING.DEPTH_METHOD other than points_map / points_raw: the reference's update_map_planar
+    (src/mapping.py:446-488) compares the warped uint8 image with label NAMES, so -- probed on the unmodified reference,
+    SURVEY.md 8a A7 -- no cell is ever incremented and the only effect is map_local[map_local < 0] = 0."""
+    case = Case("cfg1_c5_count")
+    sm = SemanticMapping(make_cfg(tmp_path, case, False))
+    rng = np.random.default_rng(4)
+    grid = rng.normal(size=(sm.map_height, sm.map_width, sm.map_depth))
+    grid[0, 0, 0], grid[0, 0, 1], grid[0, 1, 0] = -0.0, np.nan, -np.inf
+    want = grid.copy()
+    want[want < 0] = 0                                   # the statement of the reference, on the same array
+    image = syn.synthetic_frame(1, 0, 10)["semantic_image"]
+    got = grid.copy()
+    ret = sm.update_map_planar(got, image, sm.cam1)
+    assert ret is got and np.array_equal(got, want, equal_nan=True) and np.signbit(got[0, 0, 0])
+    dev = torch.from_numpy(grid).cuda()
+    assert sm.update_map_planar(dev, image, sm.cam1) is dev
+    assert np.array_equal(dev.cpu().numpy(), want, equal_nan=True)
+    # the live entry point: a planar frame changes nothing in a fresh map and is not recorded
+    sm.depth_method = "planar"
+    sm.mapping(image, syn.synthetic_pose(0), sm.cam1)
+    assert sm.input_list == [] and not np.any(sm.map)

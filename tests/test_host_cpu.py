@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = _native.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.smap_abi_version() == _native.ABI_VERSION == 4
+    assert lib.smap_abi_version() == _native.ABI_VERSION == 5
     # struct layouts agree with the header (sizes as computed by the C compiler)
     probe = r'''
     #include <stdio.h>

@@ -127,9 +127,14 @@ def test_image_callback_synchronises_records_and_integrates():
 
 
 def test_planar_method_and_extrinsics():
-    sm = bare_node(depth_method="planar")
-    with pytest.raises(NotImplementedError, match="planar"):
-        sm.mapping(np.zeros((2, 2, 3), np.uint8), None, sm.cam1)
+    # the planar method: nothing is recorded or integrated (src/mapping.py:319-320), only update_map_planar runs -- and that
+    # needs the device (no CPU fallback): tests/test_gpu_live_node.py::test_planar_update_is_the_references_clamp
+    sm = NodeOnFakeDevice.__new__(NodeOnFakeDevice)
+    sm.__dict__.update(bare_node(depth_method="planar").__dict__)
+    sm.fake, sm._map_valid, planar_calls = FakeDevice(), False, []
+    sm.update_map_planar = lambda m, image, cam: planar_calls.append((m, image.shape, cam))
+    sm.mapping(np.zeros((2, 2, 3), np.uint8), None, sm.cam1)
+    assert sm.fake.calls == ["clear"] and planar_calls == [(None, (2, 2, 3), sm.cam1)] and sm.input_list == []
     sm = bare_node()
     T_v2b = tr.euler_matrix(0.0, 0.140, 0.0)
     T_v2b[0:3, 3] = [2.64, 0, 1.98]

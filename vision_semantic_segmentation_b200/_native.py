@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMAP_LIB_PATH") or os.path.join(_HERE, "csrc", "libsmap_b200.so")  # env: kernel-variant sweeps
 
-ABI_VERSION = 4   # SMAP_ABI_VERSION of include/smap.h this binding was written against
+ABI_VERSION = 5   # SMAP_ABI_VERSION of include/smap.h this binding was written against
 SMAP_PTS_F32X4 = 0
 SMAP_PTS_F64_SOA = 1
 SMAP_IMG_RGB = 0
@@ -26,6 +26,7 @@ EXPORTS = [
     "smap_debug_nearest_map", "smap_cloud_to_f32x4",
     "smap_comm_unique_id", "smap_comm_init", "smap_comm_attach", "smap_comm_destroy", "smap_allreduce",
     "smap_reduce_scatter_rows", "smap_comm_get_info", "smap_comm_streaming", "smap_exchange_async", "smap_exchange_flush",
+    "smap_clamp_negative",
 ]
 SMAP_COMM_ID_BYTES = 128
 
@@ -167,6 +168,8 @@ def load():
     L.smap_exchange_async.argtypes = [vp, vp]
     L.smap_exchange_flush.restype = i32
     L.smap_exchange_flush.argtypes = [vp, vp]
+    L.smap_clamp_negative.restype = i32
+    L.smap_clamp_negative.argtypes = [vp, i64, i32, vp]
     L.smap_comm_get_info.restype = i32
     L.smap_comm_get_info.argtypes = [vp, ctypes.POINTER(SmapCommInfo)]
     _lib = L

@@ -794,13 +794,13 @@ int launch_render(const double* map, int mh, int mw, int c, const uint8_t* color
     const uint32_t div_c = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)c - 1) / (uint64_t)c);   // umulhi(e, div_c) = e / c, e < 2^16
     // fewer than 8 classes: strips of 4 cells, one running class sum; otherwise strips of 2 and numpy's eight partial sums
     const bool small = c < 8;
-    const int r = small ? 4 : 2;
+    const int r = small ? kRSmall : 2;
     const size_t smem = render_smem_bytes(FILTER, r, cs);
     dim3 grid((unsigned)ceil_div(mw, kRX), (unsigned)ceil_div(mh, render_tile_rows(r)));
     if (grid.y > 65535u) return fail(SMAP_ERR_INVALID, "grid has too many rows for the render kernel");
     if (small) {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_render<FILTER, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_render<FILTER, 4, 1><<<grid, kRThreads, smem, st>>>(map, mh, mw, c, cs, div_c, rc, rgb, filtered);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_render<FILTER, kRSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_render<FILTER, kRSmall, 1><<<grid, kRThreads, smem, st>>>(map, mh, mw, c, cs, div_c, rc, rgb, filtered);
     } else {
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_render<FILTER, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_render<FILTER, 2, 8><<<grid, kRThreads, smem, st>>>(map, mh, mw, c, cs, div_c, rc, rgb, filtered);
@@ -1350,6 +1350,29 @@ int smap_render_thresholds(const double* map, int mh, int mw, int c, const uint8
     const int64_t cells = (int64_t)mh * mw;
     k_render_thresholds<<<(unsigned)ceil_div(cells, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         map, cells, c, rcol, tp, rgb);
+    CK(cudaGetLastError());
+    return SMAP_OK;
+}
+
+// map[map < 0] = 0 -- the one observable effect of the reference's planar update (src/mapping.py:481): its per-class
+// increments never fire (the warped uint8 image is compared with label NAMES, :474), the clamp always runs.
+__global__ void __launch_bounds__(kThreads) k_clamp_negative(double* __restrict__ map, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = map[i];
+        if (v < 0.0) map[i] = 0.0;   // NaN and -0.0 stay, as numpy's boolean mask leaves them
+    }
+}
+
+int smap_clamp_negative(double* map_dev, int64_t n_elements, int device, void* stream) {
+    if (n_elements < 0 || (n_elements > 0 && !map_dev)) return fail(SMAP_ERR_INVALID, "bad grid");
+    if (n_elements == 0) return SMAP_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(SMAP_ERR_CUDA, "cudaSetDevice failed");
+    int sms = 148;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    int64_t grid = ceil_div(n_elements, kThreads);
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    k_clamp_negative<<<(unsigned)grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(map_dev, n_elements);
     CK(cudaGetLastError());
     return SMAP_OK;
 }

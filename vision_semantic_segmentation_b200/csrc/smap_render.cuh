@@ -20,9 +20,19 @@
 
 namespace smap {
 
+#ifndef SMAP_RENDER_STRIPS
+#define SMAP_RENDER_STRIPS 8
+#endif
+#ifndef SMAP_RENDER_R_SMALL
+#define SMAP_RENDER_R_SMALL 4      // rows per strip when C < 8
+#endif
+#ifndef SMAP_RENDER_MINB
+#define SMAP_RENDER_MINB 4         // resident blocks per SM the register allocation of the C < 8 kernels must allow
+#endif
 constexpr int kRX = 32;        // tile columns = lanes of a warp
-constexpr int kRStrips = 8;    // strips (= warps) per block
+constexpr int kRStrips = SMAP_RENDER_STRIPS;    // strips (= warps) per block
 constexpr int kRThreads = kRX * kRStrips;
+constexpr int kRSmall = SMAP_RENDER_R_SMALL;
 
 struct RenderColors {
     uint8_t rgb[32 * 3];
@@ -52,8 +62,11 @@ inline size_t render_smem_bytes(bool filter, int r, int cs) {
     return sizeof(double) * (size_t)(render_tile_rows(r) + 2 * h) * (kRX + 2 * h) * cs + (size_t)render_tile_rows(r) * kRX * 3 + 8;
 }
 
+// Occupancy: the filtered C < 8 kernel wants 96 registers (two blocks = 16 warps per SM, 130 us for the 2000 x 2000 x 5
+// grid); capped at 64 (four blocks, 8 bytes of spill) it takes 92 us.  The C >= 8 kernels keep their registers: with
+// the same cap they spill inside the class loop (290 -> 383 us at C = 19).  gpurun_out/r2f_render_variants.log
 template <bool FILTER, int R, int NPS>
-__global__ void __launch_bounds__(kRThreads)
+__global__ void __launch_bounds__(kRThreads, NPS == 1 ? SMAP_RENDER_MINB : 1)
 k_render(const double* __restrict__ map, int mh, int mw, int c, int cs, uint32_t div_c, const __grid_constant__ RenderColors colors,
          uint8_t* __restrict__ rgb, double* __restrict__ filtered) {
     extern __shared__ __align__(16) unsigned char s_raw[];

@@ -24,9 +24,10 @@ instead of a good fraction of a second.  What is ROS in the reference is a plain
 * the recorded drive is written with ``replay_io`` (``input_list.npz``; hickle is not part of the target image);
 * ``main()`` wires the callbacks to rospy subscribers when rospy is importable and says so when it is not.
 
-Not carried over: ``update_map_planar`` (``:446-488``; in the reference it compares a uint8 image with label *names*,
-never matches, and so never updates a cell -- SURVEY.md 8a A7) raises ``NotImplementedError`` with that explanation;
-``add_car_to_map`` (``:490-526``, "not tested, may have bug", no caller).
+``update_map_planar`` (``:446-488``) does what the reference's does to the map: in the reference the warped uint8 image is
+compared with label *names*, never matches, and so never updates a cell; only the clamp
+``map[map < 0] = 0`` runs, and that is what runs here.  Not carried over: ``add_car_to_map`` (``:490-526``, "not
+tested, may have bug", no caller).
 """
 import os
 import os.path as osp
@@ -133,12 +134,15 @@ class SemanticMapping(mapping_replay.SemanticMapping):
         """Integrate the current cloud (``self.pcd`` / ``self.pcd_frame_id``) seen through ``semantic_image`` at ``pose``
         into the map; when ``save_map_to_file`` is set, also finish the drive: dump the recorded inputs, smooth, render,
         write ``global_map.png``, evaluate, hand the image to ``on_semantic_local_map`` and set ``done``."""
-        if self.depth_method not in _POINTS_METHODS:
-            self.update_map_planar(None, semantic_image, camera_calibration)
         dm = self.device_mapper
         if not self._map_valid:               # self.map = np.zeros(...) on the first frame
             dm.clear()
             self._map_valid = True
+        if self.depth_method not in _POINTS_METHODS:
+            # src/mapping.py:319-320: nothing is recorded, nothing is projected; see update_map_planar
+            self.update_map_planar(None, semantic_image, camera_calibration)
+            self._finish_frame(dm)
+            return
         ids = getattr(semantic_image, "ndim", 3) == 2 or (hasattr(semantic_image, "dim") and semantic_image.dim() == 2)
         if self.record_inputs:
             # the reference's record (:309-312); a float4 cloud goes under "points", the key replay gives that layout
@@ -162,6 +166,10 @@ class SemanticMapping(mapping_replay.SemanticMapping):
                                           image_size=size)
             dm.integrate(frame)
 
+        self._finish_frame(dm)
+
+    def _finish_frame(self, dm):
+        """``src/mapping.py:322-355``: when ``save_map_to_file`` is set, finish the drive."""
         if self.save_map_to_file:
             if self.record_inputs:
                 os.makedirs(self.input_dir, exist_ok=True)
@@ -184,10 +192,35 @@ class SemanticMapping(mapping_replay.SemanticMapping):
             self.done = True
 
     def update_map_planar(self, map_local, image, cam):
-        raise NotImplementedError(
-            "DEPTH_METHOD %r selects the planar homography update (src/mapping.py:446-488), which in the reference never "
-            "updates a cell (it compares the warped uint8 image with label names) and needs a live TF tree; use "
-            "'points_map' or 'points_raw'" % (self.depth_method,))
+        """The planar (homography) update of the reference (``src/mapping.py:446-488``), i.e. what it does to the map:
+        it warps ``image`` onto the map plane (``generate_homography``, needs a live TF tree) and then tests
+        ``image_on_map[:, :, 0] == self.label_names[i]`` -- a uint8 array against a *string*, which numpy evaluates to
+        ``False`` -- so no cell is ever incremented (probed on the unmodified reference); the one
+        statement with an effect is ``map_local[map_local < 0] = 0`` (``:481``).  Exactly that runs here
+        (``smap_clamp_negative``); the warp, whose result the reference discards, is not computed.
+        ``map_local``: numpy array (clamped in place and returned, as the reference does), CUDA tensor, or None for
+        the device grid."""
+        import ctypes
+        from . import _native
+        torch = _native.require_cuda()
+        lib = _native.load()
+        if map_local is None:
+            dm = self.device_mapper
+            target = dm.map
+        elif isinstance(map_local, np.ndarray):
+            target = torch.from_numpy(np.ascontiguousarray(map_local, dtype=np.float64)).to(self.device_mapper.device)
+        else:
+            target = map_local
+            if not target.is_cuda or target.dtype != torch.float64 or not target.is_contiguous():
+                raise ValueError("map must be a contiguous float64 CUDA tensor or a numpy array")
+        with torch.cuda.device(target.device):
+            _native.check(lib.smap_clamp_negative(ctypes.c_void_p(target.data_ptr()), target.numel(), target.device.index,
+                                                  _native.current_stream_ptr(target.device)))
+        if map_local is None:
+            return None     # the device grid keeps only zeros and counts >= 0 or log-probabilities <= 0: bookkeeping unchanged
+        if isinstance(map_local, np.ndarray):
+            map_local[...] = target.cpu().numpy()
+        return map_local
 
     def get_extrinsics(self, pose, camera_id):
         """World -> camera 3x4 extrinsics for ``camera1`` / ``camera6`` at ``pose`` (``:528-541``)."""
