@@ -93,7 +93,7 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=5, choices=[5, 19],
                     help="mapped classes: the reference's default 5 (LABELS=[2,1,8,10,3]) or all 19")
     ap.add_argument("--ring", type=int, default=16, help="distinct frames resident in HBM")
-    ap.add_argument("--batch", type=int, default=16, help="frames handed to smap_integrate_batch per call (at most)")
+    ap.add_argument("--batch", type=int, default=32, help="frames handed to smap_integrate_batch per call (at most)")
     ap.add_argument("--repeats", type=int, default=0,
                     help="blocks of --steps steps in the timed region (0: as many as make the region last >= 50 ms)")
     ap.add_argument("--min-region-ms", type=float, default=50.0)
@@ -463,9 +463,9 @@ def run_b200(args):
     def block(steps):
         """exactly `steps` frames through smap_integrate_batch, in balanced batches; inside the timed region of an
         N > 1 run the ranks' increments are handed over every --exchange-every frames"""
-        for take in balanced(steps, min(args.batch, len(ring_frames))):
+        for take in balanced(steps, args.batch):
             start = pos[0] % len(ring_frames)
-            dm.integrate_batch((ring_frames + ring_frames)[start:start + take])
+            dm.integrate_batch([ring_frames[(start + j) % len(ring_frames)] for j in range(take)])
             pos[0] += take
             if xch["on"]:
                 xch["since"] += take
@@ -598,8 +598,8 @@ def run_b200(args):
     pos[0] = 0
     block(16)
     torch.cuda.synchronize()
-    n_b = max(4, min(64, total_steps // max(1, min(args.batch, len(ring_frames)))))
-    bsz = min(args.batch, len(ring_frames))
+    bsz = balanced(args.steps, args.batch)[0]     # the batch size of the timed region
+    n_b = max(4, min(64, total_steps // bsz))
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_b + 1)]
     for b in range(n_b):
         evs[b].record()

@@ -182,9 +182,11 @@ SMAP_API int smap_update(smap_handle *h, double *map_dev, const double *pcd_dev,
  * returns RGB labels and therefore takes RGB images only. */
 SMAP_API int smap_integrate(smap_handle *h, const smap_frame *frame, void *stream);
 
-/* Same rule for n_frames frames IN ORDER.  Up to 16 frames are queued together (one fused launch per frame on
- * alternating internal streams, joined back into `stream`): each frame scatters into its own mask slot and the
- * apply kernel replays the slots in frame order per cell, so the result is bit-identical to n_frames calls of
+/* Same rule for n_frames frames IN ORDER.  Frames are queued together in chunks (one fused launch per frame on
+ * alternating internal streams, forked from and joined back into `stream` once per chunk).  Ordered update and count
+ * update through the cell masks: chunks of up to 16 frames, each frame scatters into its own mask slot and the apply
+ * kernel replays the slots in frame order per cell.  Tagged count update (identity matrix, C + 1 <= 8, grid of counts):
+ * no per-frame state, chunks of up to 64 frames.  Either way the result is bit-identical to n_frames calls of
  * smap_integrate.  Frames of one call must share a point layout. */
 SMAP_API int smap_integrate_batch(smap_handle *h, const smap_frame *frames_host, int n_frames, void *stream);
 

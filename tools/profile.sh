@@ -10,7 +10,7 @@ set -u
 tag=${1:-run}
 out=gpurun_out
 mkdir -p $out
-short="--steps 32 --warmup 16 --no-cpu-baseline --no-e2e ${BENCH_ARGS:-}"
+short="--steps 32 --warmup 16 --repeats 2 --no-cpu-baseline --no-e2e --no-render ${BENCH_ARGS:-}"
 if [ -z "${SKIP_TESTS:-}" ]; then
   python -m pytest tests -m gpu -x -q -n 3 2>&1 | tail -15 > $out/${tag}_gpu_tests.log
   tail -3 $out/${tag}_gpu_tests.log

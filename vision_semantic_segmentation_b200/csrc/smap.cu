@@ -1150,11 +1150,22 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     h->last_stream = st;
-    FrameParams fps[kMaxBatch];
+    // The tagged count update keeps no per-frame state (no mask slot, no box), so its chunks -- one fork / join of the
+    // internal streams each -- may be longer than the kMaxBatch frames the mask paths apply in one pass.
+    constexpr int kTagChunk = 4 * kMaxBatch;
+    std::vector<FrameParams> fps_store((size_t)(n_frames < kTagChunk ? (n_frames > 0 ? n_frames : 1) : kTagChunk));
+    FrameParams* const fps = fps_store.data();
+    const bool tags_possible = h->identity_cm && h->cfg.num_classes + 1 <= SMAP_TAG_MAX_PLANES &&
+                               h->cells * (int64_t)(h->cfg.num_classes + 1) < ((int64_t)1 << 32);
     for (int begin = 0; begin < n_frames;) {
-        const int chunk = (n_frames - begin < kMaxBatch) ? n_frames - begin : kMaxBatch;
+        // the first non-empty frame decides the kernel (empty frames carry no layout that matters)
+        int first_ne = begin;
+        while (first_ne < n_frames && frames[first_ne].n_points <= 0) ++first_ne;
+        const bool f4_ahead = first_ne >= n_frames || frames[first_ne].layout == SMAP_PTS_F32X4;
+        const int cap = (tags_possible && f4_ahead && acc_integer(h)) ? kTagChunk : kMaxBatch;
+        const int chunk = (n_frames - begin < cap) ? n_frames - begin : cap;
         // ---- validate the whole chunk before anything is launched: a bad frame must not leave half a batch behind
-        int first = -1;   // the first non-empty frame decides the kernel (empty frames carry no layout that matters)
+        int first = -1;
         for (int i = 0; i < chunk; ++i) {
             int rc = fill_frame_params(h, frames + begin + i, fps[i]);
             if (rc) return rc;
