@@ -120,6 +120,35 @@ def test_render_kernels_follow_numpy_order_on_general_data(c):
         assert np.array_equal(rgb.cpu().numpy(), c_oracle.render_bev_map(want, colors))
 
 
+@pytest.mark.parametrize("shape", [(5, 2, 5), (40, 34, 5), (70, 100, 5), (33, 64, 19), (67, 130, 7), (35, 96, 31),
+                                   (130, 66, 19), (3, 32, 1)])
+def test_render_bulk_staged_tiles(shape):
+    """Grids the bulk-copy staged render kernel takes (odd number of classes, even number of columns): several tiles
+    in both directions, right-edge tiles of 2 / 4 / 32 columns, bottom tiles of a few rows, NaN / inf / signed zeros."""
+    rng = np.random.default_rng(sum(shape))
+    c = shape[2]
+    m = rng.normal(0, 1e3, shape) * rng.choice([1.0, 1e-9, 1e9, 0.0], shape)
+    m[rng.random(shape) < 0.02] = -0.0
+    m[0, 0, :] = 0.0
+    m[shape[0] // 2, shape[1] // 2, c // 2] = np.nan
+    m[shape[0] - 1, shape[1] - 1, c - 1] = np.inf
+    m[0, shape[1] - 1, 0] = -np.inf
+    colors = rng.integers(0, 256, (c, 3))
+    with np.errstate(all="ignore"):
+        want = c_oracle.apply_filter(m)
+        rgb, filt = renderer.filter_and_render(dev(m), colors, return_filtered=True)
+        assert np.array_equal(filt.cpu().numpy(), want, equal_nan=True)
+        assert np.array_equal(np.signbit(filt.cpu().numpy()), np.signbit(want))
+        assert np.array_equal(rgb.cpu().numpy(), c_oracle.render_bev_map(want, colors))
+        assert np.array_equal(renderer.filter_and_render(dev(m), colors).cpu().numpy(), c_oracle.render_bev_map(want, colors))
+        assert np.array_equal(renderer.render_bev_map(dev(m), colors).cpu().numpy(), c_oracle.render_bev_map(m, colors))
+        # a view that starts 8 bytes into an allocation: not 16-byte aligned, the register-staged kernel takes it
+        flat = torch.empty(m.size + 1, dtype=torch.float64, device="cuda")
+        view = flat[1:].view(shape)
+        view.copy_(dev(m))
+        assert np.array_equal(renderer.filter_and_render(view, colors).cpu().numpy(), c_oracle.render_bev_map(want, colors))
+
+
 @pytest.mark.parametrize("shape", [(1, 1, 3), (1, 7, 2), (6, 1, 4), (2, 2, 2), (8, 32, 5), (9, 33, 5), (64, 100, 19)])
 def test_filter_borders(shape):
     rng = np.random.default_rng(7)

@@ -17,6 +17,9 @@
 #define SMAP_AUX_STREAMS 4      // internal streams the per-frame k_fuse launches of a batch alternate over
 #endif
 #ifndef SMAP_TAG_MAX_PLANES
+#ifndef SMAP_RENDER_BULK
+#define SMAP_RENDER_BULK 1   // 0: dev switch, every grid through the register-staged render kernel
+#endif
 #define SMAP_TAG_MAX_PLANES 8   // count update: per-(cell, class) tags up to this many tags per cell (C + 1), masks beyond
 #endif
 #ifndef SMAP_FUSE_GRID_DIV
@@ -795,9 +798,23 @@ int launch_render(const double* map, int mh, int mw, int c, const uint8_t* color
     // fewer than 8 classes: strips of 4 cells, one running class sum; otherwise strips of 2 and numpy's eight partial sums
     const bool small = c < 8;
     const int r = small ? kRSmall : 2;
-    const size_t smem = render_smem_bytes(FILTER, r, cs);
     dim3 grid((unsigned)ceil_div(mw, kRX), (unsigned)ceil_div(mh, render_tile_rows(r)));
     if (grid.y > 65535u) return fail(SMAP_ERR_INVALID, "grid has too many rows for the render kernel");
+    // tile rows staged by bulk copies: cells of an odd number of doubles, even number of columns, 16-byte aligned grid
+    // (smap_render.cuh, k_render_bulk); every other grid goes through the register-staged kernel
+    const size_t bulk_smem = render_bulk_smem_bytes(FILTER, r, c);
+    if (SMAP_RENDER_BULK && (c & 1) && !(mw & 1) && (reinterpret_cast<uintptr_t>(map) & 15u) == 0 && bulk_smem <= 200 * 1024) {
+        if (small) {
+            CK(cudaFuncSetAttribute(k_render_bulk<FILTER, kRSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+            k_render_bulk<FILTER, kRSmall, 1><<<grid, kRThreads, bulk_smem, st>>>(map, mh, mw, c, rc, rgb, filtered);
+        } else {
+            CK(cudaFuncSetAttribute(k_render_bulk<FILTER, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+            k_render_bulk<FILTER, 2, 8><<<grid, kRThreads, bulk_smem, st>>>(map, mh, mw, c, rc, rgb, filtered);
+        }
+        CK(cudaGetLastError());
+        return SMAP_OK;
+    }
+    const size_t smem = render_smem_bytes(FILTER, r, cs);
     if (small) {
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_render<FILTER, kRSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_render<FILTER, kRSmall, 1><<<grid, kRThreads, smem, st>>>(map, mh, mw, c, cs, div_c, rc, rgb, filtered);

@@ -510,19 +510,39 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
         }
     };
 
+    // SMAP_ABL (dev builds only, results are WRONG): the stages after the cull switched off one by one, to see what each
+    // costs in the real launch shape -- 1: no tag / grid update, 2: no label lookup either, 3: no decisions either
+    // (stream + cull + compaction only).  profiles/r2g_ablation.md
     auto drain = [&](uint32_t count) {
+#if defined(SMAP_ABL) && SMAP_ABL >= 3
+        qn -= count;
+        if (queue[qn + lane].x == 1.2345e-30f) fbx0 = 0.f;
+        return;
+#endif
         decide32(count);
         __syncwarp();
         if (dn >= 32u) {
             decide64(32u);
             __syncwarp();
         }
+#if defined(SMAP_ABL) && SMAP_ABL >= 2
+        if (rn >= 32u * kFGather) {
+            rn -= 32u * kFGather;
+            if (recs[rn + lane].x == 0xfffffff0u) fbx0 = 0.f;
+        }
+        return;
+#endif
         if (rn >= 32u * kFGather) {
             lookup(32u * kFGather);
             __syncwarp();
             if (MODE == 1) {
                 while (un >= 32u * kFUpdate) {
+#if defined(SMAP_ABL) && SMAP_ABL >= 1
+                    un -= 32u * kFUpdate;
+                    if (upds[un + lane].x == 0xfffffff0u) fbx0 = 0.f;
+#else
                     update(32u * kFUpdate);
+#endif
                     __syncwarp();
                 }
             }

@@ -207,4 +207,187 @@ k_render(const double* __restrict__ map, int mh, int mw, int c, int cs, uint32_t
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_render_bulk: the same computation with the tile staged by the TMA engine (round 2).
+//
+// k_render above reaches 29 % (filter + render) / 40 % (render only) of the HBM peak on the 2000 x 2000 x 5 grid: its
+// staging loop keeps at most a few 256-byte requests per warp in flight, and only the warps that happen to be staging
+// have any, so an SM never holds the ~44 KB in flight that 6.5 TB/s over 148 SMs at ~1 us of loaded latency asks for.
+// Here a tile row -- one contiguous run of the C-contiguous grid -- is ONE bulk copy (cp.async.bulk.shared::cluster.global,
+// completion counted in bytes on an mbarrier): the lanes of warp 0 issue the TY + 2 rows of the tile back to back, the
+// whole 26 - 98 KB tile is in flight at once and no register or issue slot is spent on it.  Shared memory holds the
+// rows exactly as they lie in HBM (no padding), so this path takes the grids whose cells are an ODD number of doubles
+// (5 and 19 classes: 32 adjacent cells then fall on 32 distinct bank pairs) with an even number of columns and a
+// 16-byte aligned base (every row run then starts and ends on a 16-byte boundary); everything else goes through
+// k_render.  kf * p is formed when a value enters the 3 x 3 register window (three products per output instead of
+// one per staged element: FP64 issue is not what bounds the kernel on B200).
+//
+// Slots of a staged row: slot s = column x0 - OFF + s, OFF = 2 when filtering (the halo column x0 - 1 is slot 1; the
+// run starts one column further left so that it starts on an even column), 0 otherwise.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__host__ __device__ constexpr int render_bulk_slots(bool filter) { return filter ? kRX + 4 : kRX; }
+inline size_t render_bulk_smem_bytes(bool filter, int r, int c) {
+    const int h = filter ? 1 : 0;
+    return sizeof(double) * (size_t)(render_tile_rows(r) + 2 * h) * render_bulk_slots(filter) * c + (size_t)render_tile_rows(r) * kRX * 3 + 8;
+}
+
+template <bool FILTER, int R, int NPS>
+__global__ void __launch_bounds__(kRThreads, NPS == 1 ? SMAP_RENDER_MINB : 1)
+k_render_bulk(const double* __restrict__ map, int mh, int mw, int c, const __grid_constant__ RenderColors colors,
+              uint8_t* __restrict__ rgb, double* __restrict__ filtered) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    constexpr int H = FILTER ? 1 : 0;
+    constexpr int OFF = FILTER ? 2 : 0;
+    constexpr int SL = render_bulk_slots(FILTER);
+    constexpr int TY = kRStrips * R;
+    double* const tile = reinterpret_cast<double*>(s_raw);
+    const int pitch = SL * c;   // doubles per staged row (even: SL is)
+    uint8_t* const s_rgb = s_raw + sizeof(double) * (size_t)(TY + 2 * H) * pitch;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * kRX, y0 = blockIdx.y * TY;
+    const double kf = (double)(1.0f / 9.0f);
+
+    // ---- stage: one bulk copy per tile row, all issued by warp 0
+    const int xa = max(x0 - OFF, 0), xb = min(x0 - OFF + SL, mw);   // columns of the run (even .. even)
+    const uint32_t row_bytes = (uint32_t)(xb - xa) * (uint32_t)c * 8u;
+    int rows = TY + 2 * H;
+    if (y0 - H + rows - 1 > mh - 1 + H) rows = mh + H - (y0 - H);   // rows below the bottom halo are never read
+    const uint32_t bar = smem_addr32(&s_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)rows) : "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        for (int r = lane; r < rows; r += 32) {
+            const int ys = reflect101(y0 - H + r, mh);
+            const double* src = map + ((size_t)ys * mw + xa) * c;
+            const uint32_t dst = smem_addr32(tile + (size_t)r * pitch + (xa - (x0 - OFF)) * c);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
+        }
+    }
+    __syncthreads();   // the barrier is initialised for every waiter
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        }
+    }
+    if (FILTER && (x0 == 0 || x0 + kRX >= mw)) {
+        // the reflected halo columns (BORDER_REFLECT_101): column -1 = column 1, column mw = column mw - 2
+        for (int i = threadIdx.x; i < rows * c; i += kRThreads) {
+            const int r = i / c, k = i - r * c;
+            double* row = tile + (size_t)r * pitch;
+            if (x0 == 0) row[1 * c + k] = row[(reflect101(-1, mw) + OFF) * c + k];
+            if (x0 + kRX >= mw) row[(mw - x0 + OFF) * c + k] = row[(reflect101(mw, mw) - x0 + OFF) * c + k];
+        }
+        __syncthreads();
+    }
+
+    // ---- compute: lane = column, warp = strip of R rows; classes stream through a sliding 3x3 register window
+    const int x = x0 + lane;
+    const int ys0 = y0 + warp * R;
+    if (x < mw && ys0 < mh) {
+        CellAcc<NPS> acc[R];
+        double res[R];
+        const double* base = tile + (size_t)(warp * R) * pitch + (lane + OFF - H) * c;
+        auto one_class = [&](int ch, auto&& consume) {
+            const double* p = base + ch;
+            if (FILTER) {
+                double a0 = __dmul_rn(kf, p[0]), a1 = __dmul_rn(kf, p[c]), a2 = __dmul_rn(kf, p[2 * c]);
+                double b0 = __dmul_rn(kf, p[pitch]), b1 = __dmul_rn(kf, p[pitch + c]), b2 = __dmul_rn(kf, p[pitch + 2 * c]);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    if (ys0 + i < mh) {
+                        const double* q = p + (size_t)(i + 2) * pitch;
+                        const double c0 = __dmul_rn(kf, q[0]), c1 = __dmul_rn(kf, q[c]), c2 = __dmul_rn(kf, q[2 * c]);
+                        double v = __dadd_rn(0.0, a0);
+                        v = __dadd_rn(v, a1); v = __dadd_rn(v, a2);
+                        v = __dadd_rn(v, b0); v = __dadd_rn(v, b1); v = __dadd_rn(v, b2);
+                        v = __dadd_rn(v, c0); v = __dadd_rn(v, c1); v = __dadd_rn(v, c2);
+                        if (filtered) filtered[((size_t)(ys0 + i) * mw + x) * c + ch] = v;
+                        consume(i, v);
+                        a0 = b0; a1 = b1; a2 = b2;
+                        b0 = c0; b1 = c1; b2 = c2;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (ys0 + i < mh) consume(i, p[(size_t)i * pitch]);
+            }
+        };
+        if (NPS == 1) {
+            for (int ch = 0; ch < c; ++ch)
+                one_class(ch, [&](int i, double v) {
+                    acc[i].track(ch, v);
+                    acc[i].r[0] = (ch == 0) ? __dadd_rn(0.0, v) : __dadd_rn(acc[i].r[0], v);
+                });
+#pragma unroll
+            for (int i = 0; i < R; ++i) res[i] = acc[i].r[0];
+        } else {
+            const int main = c - (c % 8);
+            for (int c8 = 0; c8 < main; c8 += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    one_class(c8 + j, [&](int i, double v) {
+                        acc[i].track(c8 + j, v);
+                        acc[i].r[j % NPS] = (c8 == 0) ? v : __dadd_rn(acc[i].r[j % NPS], v);
+                    });
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                res[i] = __dadd_rn(__dadd_rn(__dadd_rn(acc[i].r[0], acc[i].r[1 % NPS]), __dadd_rn(acc[i].r[2 % NPS], acc[i].r[3 % NPS])),
+                                   __dadd_rn(__dadd_rn(acc[i].r[4 % NPS], acc[i].r[5 % NPS]), __dadd_rn(acc[i].r[6 % NPS], acc[i].r[7 % NPS])));
+            for (int ch = main; ch < c; ++ch)
+                one_class(ch, [&](int i, double v) {
+                    acc[i].track(ch, v);
+                    res[i] = __dadd_rn(res[i], v);
+                });
+        }
+        if (rgb) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                if (ys0 + i < mh) {
+                    uint8_t* o = s_rgb + ((warp * R + i) * kRX + lane) * 3;
+                    const bool black = res[i] == 0.0;
+                    o[0] = black ? 0 : colors.rgb[3 * acc[i].best];
+                    o[1] = black ? 0 : colors.rgb[3 * acc[i].best + 1];
+                    o[2] = black ? 0 : colors.rgb[3 * acc[i].best + 2];
+                }
+            }
+        }
+    }
+    if (!rgb) return;
+    __syncthreads();
+    // ---- colours out: warp w writes tile rows w, w + 8, ...: bytes up to the first 4-byte boundary, words, bytes
+    const int nb = min(kRX, mw - x0) * 3;
+    for (int r = warp; r < TY; r += kRStrips) {
+        const int y = y0 + r;
+        if (y >= mh) break;
+        uint8_t* g = rgb + ((size_t)y * mw + x0) * 3;
+        const uint8_t* s = s_rgb + r * kRX * 3;
+        int head = (int)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u)) & 3u);
+        head = min(head, nb);
+        if (lane < head) g[lane] = s[lane];
+        const int nwords = (nb - head) >> 2;
+        if (lane < nwords) {
+            const int off = head + 4 * lane;
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(s) + (off >> 2);
+            const uint32_t word = __funnelshift_r(sw[0], sw[1], (off & 3) * 8);
+            *reinterpret_cast<uint32_t*>(g + off) = word;
+        }
+        const int t0 = head + 4 * nwords;
+        if (lane < nb - t0) g[t0 + lane] = s[t0 + lane];
+    }
+}
+
 }  // namespace smap
