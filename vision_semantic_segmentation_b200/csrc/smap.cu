@@ -804,13 +804,22 @@ int launch_render(const double* map, int mh, int mw, int c, const uint8_t* color
     // (smap_render.cuh, k_render_bulk); every other grid goes through the register-staged kernel
     const size_t bulk_smem = render_bulk_smem_bytes(FILTER, r, c);
     if (SMAP_RENDER_BULK && (c & 1) && !(mw & 1) && (reinterpret_cast<uintptr_t>(map) & 15u) == 0 && bulk_smem <= 200 * 1024) {
-        if (small) {
-            CK(cudaFuncSetAttribute(k_render_bulk<FILTER, kRSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
-            k_render_bulk<FILTER, kRSmall, 1><<<grid, kRThreads, bulk_smem, st>>>(map, mh, mw, c, rc, rgb, filtered);
-        } else {
-            CK(cudaFuncSetAttribute(k_render_bulk<FILTER, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
-            k_render_bulk<FILTER, 2, 8><<<grid, kRThreads, bulk_smem, st>>>(map, mh, mw, c, rc, rgb, filtered);
-        }
+#define SMAP_LAUNCH_RENDER_BULK(RR, NPS, CT)                                                                               \
+    do {                                                                                                                  \
+        if (FILTER && filtered) {                                                                                         \
+            CK(cudaFuncSetAttribute(k_render_bulk<FILTER, FILTER, RR, NPS, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem)); \
+            k_render_bulk<FILTER, FILTER, RR, NPS, CT><<<grid, kRThreads, bulk_smem, st>>>(map, mh, mw, c, rc, rgb, filtered); \
+        } else {                                                                                                          \
+            CK(cudaFuncSetAttribute(k_render_bulk<FILTER, false, RR, NPS, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem)); \
+            k_render_bulk<FILTER, false, RR, NPS, CT><<<grid, kRThreads, bulk_smem, st>>>(map, mh, mw, c, rc, rgb, filtered); \
+        }                                                                                                                 \
+    } while (0)
+        // the reference's two class counts (cfg.LABELS: 5 by default, 19 in full) as compile-time constants
+        if (c == 5) SMAP_LAUNCH_RENDER_BULK(kRSmall, 1, 5);
+        else if (c == 19) SMAP_LAUNCH_RENDER_BULK(2, 8, 19);
+        else if (small) SMAP_LAUNCH_RENDER_BULK(kRSmall, 1, 0);
+        else SMAP_LAUNCH_RENDER_BULK(2, 8, 0);
+#undef SMAP_LAUNCH_RENDER_BULK
         CK(cudaGetLastError());
         return SMAP_OK;
     }

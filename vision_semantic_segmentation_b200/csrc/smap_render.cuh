@@ -234,10 +234,15 @@ inline size_t render_bulk_smem_bytes(bool filter, int r, int c) {
     return sizeof(double) * (size_t)(render_tile_rows(r) + 2 * h) * render_bulk_slots(filter) * c + (size_t)render_tile_rows(r) * kRX * 3 + 8;
 }
 
-template <bool FILTER, int R, int NPS>
+// CT: the number of classes as a compile-time constant (5 and 19: the reference's two configurations), 0 = run-time.
+// With a run-time class count two thirds of the kernel's instructions were index arithmetic (ncu, r2i: 53.5 M warp
+// instructions for 20 M outputs, 21 % IMAD, 74 % issue-active); with CT every shared-memory address is an immediate.
+// WF: the filtered grid is written as well (a template parameter, not a pointer test inside the unrolled loops).
+template <bool FILTER, bool WF, int R, int NPS, int CT>
 __global__ void __launch_bounds__(kRThreads, NPS == 1 ? SMAP_RENDER_MINB : 1)
-k_render_bulk(const double* __restrict__ map, int mh, int mw, int c, const __grid_constant__ RenderColors colors,
+k_render_bulk(const double* __restrict__ map, int mh, int mw, int c_arg, const __grid_constant__ RenderColors colors,
               uint8_t* __restrict__ rgb, double* __restrict__ filtered) {
+    const int c = CT ? CT : c_arg;
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ __align__(8) unsigned long long s_bar;
     constexpr int H = FILTER ? 1 : 0;
@@ -292,13 +297,24 @@ k_render_bulk(const double* __restrict__ map, int mh, int mw, int c, const __gri
         __syncthreads();
     }
 
-    // ---- compute: lane = column, warp = strip of R rows; classes stream through a sliding 3x3 register window
+    // ---- compute: lane = column, warp = strip of R rows; classes stream through a sliding 3x3 register window.
+    // Straight-line code: every lane of a strip that has at least one row inside the map computes all R rows (rows and
+    // columns beyond the map read staged bytes nobody wrote -- inside the tile's allocation -- and are dropped at the
+    // stores), the argmax / sum state is updated with selects.  With the bottom-row, filtered-pointer and argmax
+    // branches inside the unrolled loops half of the executed instructions were moves and branches (ncu, r2k).
     const int x = x0 + lane;
     const int ys0 = y0 + warp * R;
-    if (x < mw && ys0 < mh) {
-        CellAcc<NPS> acc[R];
-        double res[R];
-        const double* base = tile + (size_t)(warp * R) * pitch + (lane + OFF - H) * c;
+    if (ys0 < mh) {
+        double mp[R], rs[R][NPS], res[R];
+        int best[R];
+        const bool col_ok = x < mw;
+        const double* base = tile + (warp * R) * pitch + (lane + OFF - H) * c;
+        // np.argmax: the first maximum wins, and so does the first NaN (mp != mp from then on)
+        auto track = [&](int i, int ch, double v) {
+            const bool take = (ch == 0) | (!(v <= mp[i]) & (mp[i] == mp[i]));
+            mp[i] = take ? v : mp[i];
+            best[i] = take ? ch : best[i];
+        };
         auto one_class = [&](int ch, auto&& consume) {
             const double* p = base + ch;
             if (FILTER) {
@@ -306,63 +322,62 @@ k_render_bulk(const double* __restrict__ map, int mh, int mw, int c, const __gri
                 double b0 = __dmul_rn(kf, p[pitch]), b1 = __dmul_rn(kf, p[pitch + c]), b2 = __dmul_rn(kf, p[pitch + 2 * c]);
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
-                    if (ys0 + i < mh) {
-                        const double* q = p + (size_t)(i + 2) * pitch;
-                        const double c0 = __dmul_rn(kf, q[0]), c1 = __dmul_rn(kf, q[c]), c2 = __dmul_rn(kf, q[2 * c]);
-                        double v = __dadd_rn(0.0, a0);
-                        v = __dadd_rn(v, a1); v = __dadd_rn(v, a2);
-                        v = __dadd_rn(v, b0); v = __dadd_rn(v, b1); v = __dadd_rn(v, b2);
-                        v = __dadd_rn(v, c0); v = __dadd_rn(v, c1); v = __dadd_rn(v, c2);
-                        if (filtered) filtered[((size_t)(ys0 + i) * mw + x) * c + ch] = v;
-                        consume(i, v);
-                        a0 = b0; a1 = b1; a2 = b2;
-                        b0 = c0; b1 = c1; b2 = c2;
+                    const double* q = p + (i + 2) * pitch;
+                    const double c0 = __dmul_rn(kf, q[0]), c1 = __dmul_rn(kf, q[c]), c2 = __dmul_rn(kf, q[2 * c]);
+                    double v = __dadd_rn(0.0, a0);
+                    v = __dadd_rn(v, a1); v = __dadd_rn(v, a2);
+                    v = __dadd_rn(v, b0); v = __dadd_rn(v, b1); v = __dadd_rn(v, b2);
+                    v = __dadd_rn(v, c0); v = __dadd_rn(v, c1); v = __dadd_rn(v, c2);
+                    if (WF) {
+                        if (col_ok && ys0 + i < mh) filtered[((size_t)(ys0 + i) * mw + x) * c + ch] = v;
                     }
+                    consume(i, v);
+                    a0 = b0; a1 = b1; a2 = b2;
+                    b0 = c0; b1 = c1; b2 = c2;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < R; ++i)
-                    if (ys0 + i < mh) consume(i, p[(size_t)i * pitch]);
+                for (int i = 0; i < R; ++i) consume(i, p[i * pitch]);
             }
         };
         if (NPS == 1) {
+#pragma unroll(CT ? CT : 1)
             for (int ch = 0; ch < c; ++ch)
                 one_class(ch, [&](int i, double v) {
-                    acc[i].track(ch, v);
-                    acc[i].r[0] = (ch == 0) ? __dadd_rn(0.0, v) : __dadd_rn(acc[i].r[0], v);
+                    track(i, ch, v);
+                    rs[i][0] = __dadd_rn(ch == 0 ? 0.0 : rs[i][0], v);
                 });
 #pragma unroll
-            for (int i = 0; i < R; ++i) res[i] = acc[i].r[0];
+            for (int i = 0; i < R; ++i) res[i] = rs[i][0];
         } else {
             const int main = c - (c % 8);
             for (int c8 = 0; c8 < main; c8 += 8) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     one_class(c8 + j, [&](int i, double v) {
-                        acc[i].track(c8 + j, v);
-                        acc[i].r[j % NPS] = (c8 == 0) ? v : __dadd_rn(acc[i].r[j % NPS], v);
+                        track(i, c8 + j, v);
+                        rs[i][j % NPS] = (c8 == 0) ? v : __dadd_rn(rs[i][j % NPS], v);
                     });
             }
 #pragma unroll
             for (int i = 0; i < R; ++i)
-                res[i] = __dadd_rn(__dadd_rn(__dadd_rn(acc[i].r[0], acc[i].r[1 % NPS]), __dadd_rn(acc[i].r[2 % NPS], acc[i].r[3 % NPS])),
-                                   __dadd_rn(__dadd_rn(acc[i].r[4 % NPS], acc[i].r[5 % NPS]), __dadd_rn(acc[i].r[6 % NPS], acc[i].r[7 % NPS])));
+                res[i] = __dadd_rn(__dadd_rn(__dadd_rn(rs[i][0], rs[i][1 % NPS]), __dadd_rn(rs[i][2 % NPS], rs[i][3 % NPS])),
+                                   __dadd_rn(__dadd_rn(rs[i][4 % NPS], rs[i][5 % NPS]), __dadd_rn(rs[i][6 % NPS], rs[i][7 % NPS])));
+#pragma unroll(CT ? (CT % 8 ? CT % 8 : 1) : 1)
             for (int ch = main; ch < c; ++ch)
                 one_class(ch, [&](int i, double v) {
-                    acc[i].track(ch, v);
+                    track(i, ch, v);
                     res[i] = __dadd_rn(res[i], v);
                 });
         }
         if (rgb) {
 #pragma unroll
             for (int i = 0; i < R; ++i) {
-                if (ys0 + i < mh) {
-                    uint8_t* o = s_rgb + ((warp * R + i) * kRX + lane) * 3;
-                    const bool black = res[i] == 0.0;
-                    o[0] = black ? 0 : colors.rgb[3 * acc[i].best];
-                    o[1] = black ? 0 : colors.rgb[3 * acc[i].best + 1];
-                    o[2] = black ? 0 : colors.rgb[3 * acc[i].best + 2];
-                }
+                uint8_t* o = s_rgb + ((warp * R + i) * kRX + lane) * 3;   // rows / columns beyond the map: never copied out
+                const bool black = res[i] == 0.0;
+                o[0] = black ? 0 : colors.rgb[3 * best[i]];
+                o[1] = black ? 0 : colors.rgb[3 * best[i] + 1];
+                o[2] = black ? 0 : colors.rgb[3 * best[i] + 2];
             }
         }
     }
