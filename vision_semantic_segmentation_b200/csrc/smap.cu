@@ -83,6 +83,13 @@ struct smap_handle {
     FrameBox* boxes = nullptr;                // [2][kMaxBatch]
     unsigned long long* touched = nullptr;    // [2]
     int parity = 0;
+    // Two sets of mask slots (set = parity): while k_apply / k_clear_masks of chunk k runs on apply_stream over set p,
+    // the k_fuse launches of chunk k + 1 scatter into set p ^ 1 (one smap_integrate_batch call of several chunks).
+    cudaStream_t apply_stream = nullptr;
+    cudaEvent_t ev_fused = nullptr;           // the chunk's scatter launches have joined the caller's stream
+    cudaEvent_t ev_applied[2] = {};           // the apply / clear over set p has finished
+    bool applied_pending[2] = {false, false};
+    bool applied_writes_grid[2] = {false, false};   // the pending kernel is a k_apply (k_clear_masks only touches masks)
     int sm_count = 148;
     bool identity_cm = false;   // update matrix is exactly np.eye(C): the count update
     bool integer_grid = false;  // the grid is known to hold integer-valued counts (zeroed by us, then only count updates)
@@ -445,62 +452,124 @@ int ensure_scratch(smap_handle* h, int64_t n) {
 }
 
 // Make room for `want` mask slots (slot 0 always exists).  New memory is zero = "never written".
+// slot i of the current set (set = parity)
+inline uint32_t* mask_slot(const smap_handle* h, int i) {
+    return h->mask + ((size_t)h->parity * (size_t)h->n_slots + (size_t)i) * (size_t)h->slot_words;
+}
+
+// n_slots = slots per set; two sets.  Every slot is all zero between chunks, so growing needs no copy.
 int ensure_slots(smap_handle* h, int want) {
     if (want <= h->n_slots) return SMAP_OK;
     uint32_t* fresh = nullptr;
     const size_t slot_bytes = sizeof(uint32_t) * (size_t)h->slot_words;
     CK(cudaDeviceSynchronize());
-    CK(cudaMalloc(&fresh, slot_bytes * want));
-    CK(cudaMemset(fresh, 0, slot_bytes * want));
-    if (h->mask) {
-        CK(cudaMemcpy(fresh, h->mask, slot_bytes * h->n_slots, cudaMemcpyDeviceToDevice));
-        CK(cudaFree(h->mask));
-    }
+    CK(cudaMalloc(&fresh, slot_bytes * 2 * want));
+    CK(cudaMemset(fresh, 0, slot_bytes * 2 * want));
+    if (h->mask) CK(cudaFree(h->mask));
     h->mask = fresh;
     h->n_slots = want;
     return SMAP_OK;
 }
 
-// K3b launch: ordered apply of the `n_slots_used` mask slots whose boxes are boxes[parity]; flips parity.
-int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st) {
+int ensure_apply_stream(smap_handle* h) {
+    if (h->apply_stream) return SMAP_OK;
+    CK(cudaStreamCreateWithFlags(&h->apply_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fused, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->ev_applied[i], cudaEventDisableTiming));
+    return SMAP_OK;
+}
+
+// Before anything scatters into the current slot set: the apply / clear that last used the set has finished (its masks
+// are zero again), the set's boxes are empty and its touched-cell counter is zero.
+int begin_chunk(smap_handle* h, cudaStream_t st) {
+    if (h->applied_pending[h->parity]) {
+        CK(cudaStreamWaitEvent(st, h->ev_applied[h->parity], 0));
+        h->applied_pending[h->parity] = false;
+    }
+    k_reset_slot_state<<<1, 32, 0, st>>>(h->boxes + (size_t)h->parity * kMaxBatch, h->touched + h->parity);
+    CK(cudaGetLastError());
+    return SMAP_OK;
+}
+
+// The caller's stream waits for every apply / clear still running on apply_stream (end of an API call: the
+// stream-ordered contract -- whatever follows on `st` sees the updated grid).
+int join_applies(smap_handle* h, cudaStream_t st) {
+    for (int p = 0; p < 2; ++p) {
+        if (!h->applied_pending[p]) continue;
+        CK(cudaStreamWaitEvent(st, h->ev_applied[p], 0));
+        h->applied_pending[p] = false;
+    }
+    return SMAP_OK;
+}
+
+// Stream the apply / clear of the current set runs on: apply_stream behind the chunk's scatter launches when `overlap`
+// (more chunks follow), the caller's stream -- behind the previous chunk's apply, the grid updates are ordered --
+// otherwise.
+int apply_stream_for(smap_handle* h, cudaStream_t st, bool overlap, cudaStream_t* out) {
+    if (overlap) {
+        int rc = ensure_apply_stream(h);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_fused, st));
+        CK(cudaStreamWaitEvent(h->apply_stream, h->ev_fused, 0));
+        *out = h->apply_stream;
+    } else {
+        int rc = join_applies(h, st);
+        if (rc) return rc;
+        *out = st;
+    }
+    return SMAP_OK;
+}
+
+int applied(smap_handle* h, cudaStream_t as, bool overlap, bool writes_grid) {
+    if (overlap) {
+        CK(cudaEventRecord(h->ev_applied[h->parity], as));
+        h->applied_pending[h->parity] = true;
+        h->applied_writes_grid[h->parity] = writes_grid;
+    }
+    h->parity ^= 1;
+    h->stats.kernel_launches += 1;
+    return SMAP_OK;
+}
+
+// K3b launch: ordered apply of the `n_slots_used` mask slots of the current set (boxes[parity]); flips parity.
+int launch_apply(smap_handle* h, double* map, int n_slots_used, cudaStream_t st, bool overlap = false) {
     const int c = h->cfg.num_classes;
     ApplyParams ap;
     memset(&ap, 0, sizeof ap);
     ap.n_frames = n_slots_used;
-    for (int i = 0; i < n_slots_used; ++i) ap.mask[i] = h->mask + (size_t)i * h->slot_words;
+    for (int i = 0; i < n_slots_used; ++i) ap.mask[i] = mask_slot(h, i);
     const size_t smem = sizeof(double) * c * c;
     FrameBox* boxes = h->boxes + (size_t)h->parity * kMaxBatch;
-    FrameBox* next_boxes = h->boxes + (size_t)(h->parity ^ 1) * kMaxBatch;
     unsigned long long* tt = h->touched + h->parity;
-    unsigned long long* ntt = h->touched + (h->parity ^ 1);
     const unsigned grid = (unsigned)h->sm_count * 8;
     const int lane = h->cfg.lane_index, mw = h->cfg.map_width;
-#define SMAP_LAUNCH_APPLY(NJ) k_apply<NJ><<<grid, kThreads, smem, st>>>(map, ap, boxes, next_boxes, tt, ntt, h->abox, h->cm_dev, c, lane, mw)
+    cudaStream_t as = st;
+    int rc = apply_stream_for(h, st, overlap, &as);
+    if (rc) return rc;
+#define SMAP_LAUNCH_APPLY(NJ) k_apply<NJ><<<grid, kThreads, smem, as>>>(map, ap, boxes, nullptr, tt, nullptr, h->abox, h->cm_dev, c, lane, mw)
     if (c <= 8) SMAP_LAUNCH_APPLY(1);
     else if (c <= 16) SMAP_LAUNCH_APPLY(2);
     else if (c <= 24) SMAP_LAUNCH_APPLY(3);
     else SMAP_LAUNCH_APPLY(4);
 #undef SMAP_LAUNCH_APPLY
     CK(cudaGetLastError());
-    h->parity ^= 1;
-    h->stats.kernel_launches += 1;
-    return SMAP_OK;
+    return applied(h, as, overlap, true);
 }
 
 // After a count update through the masks (k_fuse MODE 2): zero the slots inside the frames' boxes; flips parity.
-int launch_clear(smap_handle* h, int n_slots_used, cudaStream_t st) {
+int launch_clear(smap_handle* h, int n_slots_used, cudaStream_t st, bool overlap = false) {
     ApplyParams ap;
     memset(&ap, 0, sizeof ap);
     ap.n_frames = n_slots_used;
-    for (int i = 0; i < n_slots_used; ++i) ap.mask[i] = h->mask + (size_t)i * h->slot_words;
+    for (int i = 0; i < n_slots_used; ++i) ap.mask[i] = mask_slot(h, i);
     const dim3 grid((unsigned)h->sm_count, kMaxBatch);
-    k_clear_masks<<<grid, kThreads, 0, st>>>(ap, h->boxes + (size_t)h->parity * kMaxBatch,
-                                             h->boxes + (size_t)(h->parity ^ 1) * kMaxBatch, h->touched + (h->parity ^ 1),
-                                             h->abox, h->cfg.map_width);
+    cudaStream_t as = st;
+    int rc = apply_stream_for(h, st, overlap, &as);
+    if (rc) return rc;
+    k_clear_masks<<<grid, kThreads, 0, as>>>(ap, h->boxes + (size_t)h->parity * kMaxBatch, nullptr, nullptr, h->abox,
+                                             h->cfg.map_width);
     CK(cudaGetLastError());
-    h->parity ^= 1;
-    h->stats.kernel_launches += 1;
-    return SMAP_OK;
+    return applied(h, as, overlap, false);
 }
 
 // Queue one k_stream_soa launch per non-empty (4, N) float64 frame; frame i of the non-empty ones scatters into
@@ -515,7 +584,7 @@ int launch_stream(smap_handle* h, const smap_frame* frames, const FrameParams* f
         sp.fp = fps[i];
         sp.pts = frames[i].points_dev;
         sp.image = frames[i].image_dev;
-        sp.mask = h->mask + (size_t)used * h->slot_words;
+        sp.mask = mask_slot(h, used);
         sp.n = frames[i].n_points;
         sp.ld = frames[i].ld;
         // persistent grid: as many blocks as stay resident, never more than the cloud has rounds
@@ -654,7 +723,7 @@ int fill_fuse_frame(smap_handle* h, const smap_frame* fr, const FrameParams& fp,
     fill_fast32(h, fr, fp, f.fk);
     f.pts = static_cast<const float4*>(fr->points_dev);
     f.image = fr->image_dev;
-    f.mask = mode == 1 ? nullptr : h->mask + (size_t)slot * h->slot_words;
+    f.mask = mode == 1 ? nullptr : mask_slot(h, slot);
     f.fk.tag = ++h->frame_tag;   // larger than every tag written to this frame's plane before
     f.n = fr->n_points;
     f.img64 = ((reinterpret_cast<uintptr_t>(fr->image_dev) & 7u) == 0u &&
@@ -993,8 +1062,8 @@ int smap_create(const smap_config* cfg, smap_handle** out) {
     }
     h->acc = h->map;
     h->slot_words = (h->cells + 3) / 4 * 4;
-    if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->slot_words);
-    if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->slot_words);
+    if (e == cudaSuccess) e = cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)h->slot_words * 2);   // two sets of one slot
+    if (e == cudaSuccess) e = cudaMemset(h->mask, 0, sizeof(uint32_t) * (size_t)h->slot_words * 2);
     if (e == cudaSuccess) h->n_slots = 1;
     if (e == cudaSuccess) e = cudaMalloc(&h->boxes, sizeof(FrameBox) * (2 * kMaxBatch + 3));
     if (e == cudaSuccess) {
@@ -1030,6 +1099,9 @@ int smap_destroy(smap_handle* h) {
     cudaDeviceSynchronize();
     harvest_profile(h);
     if (h->own_map) cudaFree(h->map);
+    if (h->apply_stream) cudaStreamDestroy(h->apply_stream);
+    if (h->ev_fused) cudaEventDestroy(h->ev_fused);
+    for (int i = 0; i < 2; ++i) if (h->ev_applied[i]) cudaEventDestroy(h->ev_applied[i]);
     cudaFree(h->mask); cudaFree(h->tags); cudaFree(h->boxes); cudaFree(h->touched); cudaFree(h->cm_dev); cudaFree(h->total_dev);
     cudaFree(h->id_lut_dev); cudaFree(h->nn.tab_dev);
     if (h->comm && h->own_comm && nccl_api().lib) nccl_api().CommDestroy(h->comm);
@@ -1151,7 +1223,11 @@ int smap_update(smap_handle* h, double* map_dev, const double* pcd, int64_t ld, 
     if (m == 0) return SMAP_OK;
     int64_t grid = ceil_div(m, kThreads);
     if (grid > (int64_t)h->sm_count * 16) grid = (int64_t)h->sm_count * 16;
-    k_update_scatter<<<(unsigned)grid, kThreads, 0, st>>>(pcd, ld, label, ldl, m, h->gp, h->mask,
+    {
+        int rc = begin_chunk(h, st);
+        if (rc) return rc;
+    }
+    k_update_scatter<<<(unsigned)grid, kThreads, 0, st>>>(pcd, ld, label, ldl, m, h->gp, mask_slot(h, 0),
                                                          h->boxes + (size_t)h->parity * kMaxBatch);
     CK(cudaGetLastError());
     h->stats.kernel_launches += 1;
@@ -1217,6 +1293,17 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
         if (!h->identity_cm) acc_integer(h) = false;
         int rc = mode == 1 ? SMAP_OK : ensure_slots(h, chunk);
         if (rc) return rc;
+        if (mode != 0 && ((h->applied_pending[0] && h->applied_writes_grid[0]) || (h->applied_pending[1] && h->applied_writes_grid[1]))) {
+            // the count update's scatter kernels add to the grid themselves: not beside a k_apply that rewrites its rows
+            rc = join_applies(h, st);
+            if (rc) return rc;
+        }
+        if (mode != 1) {
+            rc = begin_chunk(h, st);
+            if (rc) { join_applies(h, st); return rc; }
+        }
+        // mask paths: the apply / clear of this chunk runs beside the scatter launches of the next one (second slot set)
+        const bool overlap = mode != 1 && begin + chunk < n_frames && !h->profiling;
         int used = 0;
         smap_handle::ProfRec* pr = nullptr;
         if (h->profiling) {
@@ -1233,8 +1320,8 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
         // also after a failed launch: the frames queued so far are applied / their slots cleared, so that the slots are
         // all zero and the boxes reset when the call returns (the error is still reported)
         int rc2 = SMAP_OK;
-        if (used > 0 && mode == 0) rc2 = launch_apply(h, h->acc, used, st);
-        if (used > 0 && mode == 2) rc2 = launch_clear(h, used, st);
+        if (used > 0 && mode == 0) rc2 = launch_apply(h, h->acc, used, st, overlap && !rc);
+        if (used > 0 && mode == 2) rc2 = launch_clear(h, used, st, overlap && !rc);
         h->last_update_counted = mode == 0;
         if (pr) cudaEventRecord(pr->e[2], st);
         for (int i = 0; i < chunk; ++i) {
@@ -1242,11 +1329,13 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
             h->stats.points += frames[begin + i].n_points;
         }
         acc_bound(h) += 3 * (int64_t)used;
-        if (rc) return rc;
-        if (rc2) return rc2;
+        if (rc || rc2) {
+            join_applies(h, st);
+            return rc ? rc : rc2;
+        }
         begin += chunk;
     }
-    return SMAP_OK;
+    return join_applies(h, st);
 }
 
 int smap_integrate(smap_handle* h, const smap_frame* frame, void* stream) {

@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(kThreads)
 k_clear_masks(const __grid_constant__ ApplyParams ap, const FrameBox* __restrict__ boxes, FrameBox* __restrict__ next_boxes,
               unsigned long long* __restrict__ next_touched_total, FrameBox* __restrict__ ubox, int mw) {
     const int f = blockIdx.y;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (next_boxes && blockIdx.x == 0 && threadIdx.x == 0) {
         box_reset(&next_boxes[f].x0);
         if (f == 0) *next_touched_total = 0ull;
     }

@@ -236,6 +236,12 @@ template <> __device__ __forceinline__ void mask_vec_load<2>(const uint32_t* p, 
 }
 template <> __device__ __forceinline__ void mask_vec_load<1>(const uint32_t* p, uint32_t (&w)[1]) { w[0] = *p; }
 
+// Before a slot set is (re)used by a chunk: its boxes empty, its touched-cell counter zero.
+__global__ void k_reset_slot_state(FrameBox* __restrict__ boxes, unsigned long long* __restrict__ touched_total) {
+    if (threadIdx.x < kMaxBatch) box_reset(&boxes[threadIdx.x].x0);
+    if (threadIdx.x == 0) *touched_total = 0ull;
+}
+
 template <int NJ>
 __global__ void __launch_bounds__(kThreads)
 k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameBox* __restrict__ boxes,
@@ -254,8 +260,9 @@ k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameB
         s_boxes[threadIdx.x] = b;
     }
     if (threadIdx.x == 0) s_count = 0;
-    if (blockIdx.x == 0 && threadIdx.x < kMaxBatch) box_reset(&next_boxes[threadIdx.x].x0);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *next_touched_total = 0ull;
+    // (next_boxes == nullptr: the host resets a slot set's boxes itself before it reuses the set, k_reset_slot_state)
+    if (next_boxes && blockIdx.x == 0 && threadIdx.x < kMaxBatch) box_reset(&next_boxes[threadIdx.x].x0);
+    if (next_touched_total && blockIdx.x == 0 && threadIdx.x == 0) *next_touched_total = 0ull;
     __syncthreads();
     int x0 = 0x7fffffff, x1 = -1, y0 = 0x7fffffff, y1 = -1;
     for (int f = 0; f < ap.n_frames; ++f) {

@@ -243,15 +243,15 @@ __global__ void __launch_bounds__(kRThreads, NPS == 1 ? SMAP_RENDER_MINB : 1)
 k_render_bulk(const double* __restrict__ map, int mh, int mw, int c_arg, const __grid_constant__ RenderColors colors,
               uint8_t* __restrict__ rgb, double* __restrict__ filtered) {
     const int c = CT ? CT : c_arg;
-    extern __shared__ __align__(128) unsigned char s_raw[];
+    extern __shared__ __align__(128) unsigned char s_bulk[];
     __shared__ __align__(8) unsigned long long s_bar;
     constexpr int H = FILTER ? 1 : 0;
     constexpr int OFF = FILTER ? 2 : 0;
     constexpr int SL = render_bulk_slots(FILTER);
     constexpr int TY = kRStrips * R;
-    double* const tile = reinterpret_cast<double*>(s_raw);
+    double* const tile = reinterpret_cast<double*>(s_bulk);
     const int pitch = SL * c;   // doubles per staged row (even: SL is)
-    uint8_t* const s_rgb = s_raw + sizeof(double) * (size_t)(TY + 2 * H) * pitch;
+    uint8_t* const s_rgb = s_bulk + sizeof(double) * (size_t)(TY + 2 * H) * pitch;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * kRX, y0 = blockIdx.y * TY;
@@ -307,6 +307,8 @@ k_render_bulk(const double* __restrict__ map, int mh, int mw, int c_arg, const _
     if (ys0 < mh) {
         double mp[R], rs[R][NPS], res[R];
         int best[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { mp[i] = 0.0; best[i] = 0; }
         const bool col_ok = x < mw;
         const double* base = tile + (warp * R) * pitch + (lane + OFF - H) * c;
         // np.argmax: the first maximum wins, and so does the first NaN (mp != mp from then on)
