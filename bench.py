@@ -160,7 +160,8 @@ class ClockSampler(object):
             except Exception:
                 pass
 
-    def start(self):
+    def start(self, thread=True):
+        """thread=False (ranks > 0): no polling thread, only the samples sample_now() takes"""
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -175,8 +176,9 @@ class ClockSampler(object):
                 h = nv.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             self._nvml = (nv, h)
-            self._thread = threading.Thread(target=self._poll, daemon=True)
-            self._thread.start()
+            if thread:
+                self._thread = threading.Thread(target=self._poll, daemon=True)
+                self._thread.start()
             return
         except Exception:
             self._nvml = None
@@ -195,7 +197,8 @@ class ClockSampler(object):
     def stop(self):
         if self._nvml is not None:
             self._stop.set()
-            self._thread.join(timeout=1.0)
+            if self._thread is not None:
+                self._thread.join(timeout=1.0)
             nv = self._nvml[0]
             names = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
                      ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
@@ -512,16 +515,19 @@ def run_b200(args):
     # ---- device-resident throughput (`value`)
     launches_before = dm.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.start(thread=(rank == 0))
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(repeats + 1)]
     e_end = torch.cuda.Event(enable_timing=True)
     barrier()
     xch["on"] = world > 1
+    t_host0 = time.perf_counter()
     for r in range(repeats):
         marks[r].record()
         block(args.steps)
+        if rank != 0 and r == repeats // 2:
+            sampler.sample_now()
     marks[repeats].record()
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0)
     if world > 1:
         xch["on"] = False
         if xch["since"] > 0 or xch["count"] == 0:   # the frames behind the last regular exchange
@@ -532,15 +538,24 @@ def run_b200(args):
     if args.workload == "cfg5":
         rgb_full = render_tiles()
     e_end.record()
-    if rank == 0:
-        sampler.sample_now()
+    sampler.sample_now()
     barrier()
     ms = marks[0].elapsed_time(e_end)
     block_ms = np.array([marks[r].elapsed_time(marks[r + 1]) for r in range(repeats)])
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     launches = dm.stats()["kernel_launches"] - launches_before
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # every rank's own view of the region (the line's ms_per_step is the MAX): its time, its median block, how long
+        # its host took to queue the region, its SM clock under load and throttle reasons
+        mine = torch.tensor([ms, float(np.median(block_ms)), host_enqueue_ms, clocks.get("sm_mhz") or 0.0,
+                             float(sampler.reason_bits)], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": i, "region_ms": float(v[0]), "median_block_ms_per_step": float(v[1]) / args.steps,
+                     "host_enqueue_ms": float(v[2]), "sm_mhz": float(v[3]), "clock_event_reason_bits": int(v[4])}
+                    for i, v in enumerate(x.cpu().numpy() for x in allr)]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     total_steps = repeats * args.steps
@@ -758,7 +773,7 @@ def run_b200(args):
                          "step_frac": bytes_per_frame / (ms / total_steps * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_frame": bytes_per_frame,
                          "N": n_pts, "M": M, "K_cells": Kc, "U_elements": U},
-            "render": render, "collective": collective,
+            "render": render, "collective": collective, "per_rank": per_rank, "host_enqueue_ms": host_enqueue_ms,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), file=args.out, flush=True)

@@ -298,6 +298,13 @@ SMAP_API int smap_comm_get_info(smap_handle *h, smap_comm_info *out);
  * numpy's mask leaves them). */
 SMAP_API int smap_clamp_negative(double *map_dev, int64_t n_elements, int device, void *stream);
 
+/* The warp itself: cv2.warpPerspective(image, h, (dst_w, dst_h)) as generate_homography calls it
+ * (src/homography.py:53-55: default flags -- INTER_LINEAR, BORDER_CONSTANT 0) for an 8-bit image of 1..4 interleaved
+ * channels, bit for bit (OpenCV's fixed-point arithmetic, restated in oracle/warp_port.py).  h_host: the 3 x 3 homography
+ * source -> destination, row-major, as cv2.findHomography returns it.  src_dev and dst_dev must not overlap. */
+SMAP_API int smap_warp_perspective(const uint8_t *src_dev, int src_h, int src_w, int channels, const double h_host[9],
+                                   uint8_t *dst_dev, int dst_h, int dst_w, int device, void *stream);
+
 /* ---- grid access ------------------------------------------------------------------------------- */
 SMAP_API int smap_map_ptr(smap_handle *h, double **map_dev, int64_t *n_elements);
 SMAP_API int smap_clear(smap_handle *h, void *stream);            /* self.map = np.zeros(...)  src/mapping_replay.py:181 */

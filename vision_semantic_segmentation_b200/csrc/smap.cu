@@ -12,11 +12,15 @@
 #include "smap_kernels.cuh"
 #include "smap_fuse.cuh"
 #include "smap_comm.cuh"
+#include "smap_warp.cuh"
 
 #ifndef SMAP_AUX_STREAMS
 #define SMAP_AUX_STREAMS 4      // internal streams the per-frame k_fuse launches of a batch alternate over
 #endif
 #ifndef SMAP_TAG_MAX_PLANES
+#ifndef SMAP_APPLY_OVERLAP
+#define SMAP_APPLY_OVERLAP 1   // 0: dev switch, k_apply / k_clear_masks on the caller's stream, nothing beside them
+#endif
 #ifndef SMAP_RENDER_BULK
 #define SMAP_RENDER_BULK 1   // 0: dev switch, every grid through the register-staged render kernel
 #endif
@@ -1303,7 +1307,7 @@ int smap_integrate_batch(smap_handle* h, const smap_frame* frames, int n_frames,
             if (rc) { join_applies(h, st); return rc; }
         }
         // mask paths: the apply / clear of this chunk runs beside the scatter launches of the next one (second slot set)
-        const bool overlap = mode != 1 && begin + chunk < n_frames && !h->profiling;
+        const bool overlap = SMAP_APPLY_OVERLAP && mode != 1 && begin + chunk < n_frames && !h->profiling;
         int used = 0;
         smap_handle::ProfRec* pr = nullptr;
         if (h->profiling) {
@@ -1487,6 +1491,47 @@ __global__ void __launch_bounds__(kThreads) k_clamp_negative(double* __restrict_
         const double v = map[i];
         if (v < 0.0) map[i] = 0.0;   // NaN and -0.0 stay, as numpy's boolean mask leaves them
     }
+}
+
+int smap_warp_perspective(const uint8_t* src_dev, int src_h, int src_w, int channels, const double h_host[9],
+                          uint8_t* dst_dev, int dst_h, int dst_w, int device, void* stream) {
+    if (!src_dev || !dst_dev || !h_host) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0) return fail(SMAP_ERR_INVALID, "empty image");
+    if (channels < 1 || channels > 4) return fail(SMAP_ERR_INVALID, "1 to 4 channels");
+    if (src_h >= 32768 || src_w >= 32768 || dst_h > 65535) return fail(SMAP_ERR_INVALID, "image too large (OpenCV keeps source coordinates in int16)");
+    DeviceGuard guard(device);
+    WarpParams p;
+    // cv::invert of a 3 x 3 double matrix: the closed adjugate formula
+    const double* s = h_host;
+    double d = s[0] * (s[4] * s[8] - s[5] * s[7]) - s[1] * (s[3] * s[8] - s[5] * s[6]) + s[2] * (s[3] * s[7] - s[4] * s[6]);
+    if (d == 0.0) {
+        for (int i = 0; i < 9; ++i) p.m[i] = 0.0;
+    } else {
+        d = 1.0 / d;
+        p.m[0] = (s[4] * s[8] - s[5] * s[7]) * d;
+        p.m[1] = (s[2] * s[7] - s[1] * s[8]) * d;
+        p.m[2] = (s[1] * s[5] - s[2] * s[4]) * d;
+        p.m[3] = (s[5] * s[6] - s[3] * s[8]) * d;
+        p.m[4] = (s[0] * s[8] - s[2] * s[6]) * d;
+        p.m[5] = (s[2] * s[3] - s[0] * s[5]) * d;
+        p.m[6] = (s[3] * s[7] - s[4] * s[6]) * d;
+        p.m[7] = (s[1] * s[6] - s[0] * s[7]) * d;
+        p.m[8] = (s[0] * s[4] - s[1] * s[3]) * d;
+    }
+    p.src_h = src_h; p.src_w = src_w; p.cn = channels; p.dst_h = dst_h; p.dst_w = dst_w;
+    // WarpPerspectiveInvoker's block width: BLOCK_SZ = 32, bh0 = min(16, h), bw0 = min(1024 / bh0, w)
+    const int bh0 = dst_h < 16 ? dst_h : 16;
+    p.bw0 = (1024 / bh0 < dst_w) ? 1024 / bh0 : dst_w;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid((unsigned)ceil_div(dst_w, 256), (unsigned)dst_h);
+    switch (channels) {
+        case 1: k_warp_perspective<1><<<grid, 256, 0, st>>>(p, src_dev, dst_dev); break;
+        case 2: k_warp_perspective<2><<<grid, 256, 0, st>>>(p, src_dev, dst_dev); break;
+        case 3: k_warp_perspective<3><<<grid, 256, 0, st>>>(p, src_dev, dst_dev); break;
+        default: k_warp_perspective<4><<<grid, 256, 0, st>>>(p, src_dev, dst_dev); break;
+    }
+    CK(cudaGetLastError());
+    return SMAP_OK;
 }
 
 int smap_clamp_negative(double* map_dev, int64_t n_elements, int device, void* stream) {

@@ -279,6 +279,9 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
     uint32_t qn = 0, dn = 0, rn = 0, un = 0;   // entries on the survivor / deferred / record / update stacks (warp-uniform)
     // bounding box of what this warp touched: magic-shifted floats (monotone in the cell coordinates)
     float fbx0 = 3.0e38f, fbx1 = -3.0e38f, fby0 = 3.0e38f, fby1 = -3.0e38f;
+    // (the uniform-register box in MODE 1 / 2 as well: measured, no gain -- 13.01 vs 12.89 us, profiles/r2s_*)
+    constexpr bool kBoxInRegs = MODE != 0;
+    int ubx0 = 0x7fffffff, ubx1 = -1, uby0 = 0x7fffffff, uby1 = -1;   // MODE 0: the warp's box, warp-uniform
 
     // a decided point -> record stack: {pixel index, cell index | intensity flag << 31}
     auto push_record = [&](bool have, uint32_t pix, uint32_t cell, float it) {
@@ -297,6 +300,7 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
         bool defer_me = false, have = false;
         uint32_t pix = 0, cell = 0;
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 tcb = make_float2(0.f, 0.f);   // the magic-shifted cell coordinates (MODE 0: for the box below)
         if ((uint32_t)lane < count) {
             w = queue[first + lane];
             const float2 lxy = __fadd2_rn(make_float2(w.x, w.y), fk.n_ctr_xy);
@@ -342,10 +346,22 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
                 pix = label_index<1>(F, __float_as_uint(tp.x) - kMagicBits, __float_as_uint(tp.y) - kMagicBits);
             }
             cell = __float_as_uint(tc.x) * (uint32_t)gp.mw + __float_as_uint(tc.y) + fk.cell_k;
-            if (have) {
+            tcb = tc;
+            if (kBoxInRegs && have) {
                 fbx0 = fminf(fbx0, tc.x); fbx1 = fmaxf(fbx1, tc.x);
                 fby0 = fminf(fby0, tc.y); fby1 = fmaxf(fby1, tc.y);
             }
+        }
+        if (!kBoxInRegs) {
+            // MODE 0: the four running extremes do not fit next to the prefetched round (ptxas spilled a float4 of the
+            // prefetch at the top of every round and waited for it right there): the batch's box is reduced over the
+            // warp right here and kept in four warp-uniform integers (uniform registers)
+            const uint32_t ox = __float_as_uint(fk.clamp_c.x), oy = __float_as_uint(fk.clamp_c.y);
+            const int vx = (int)(__float_as_uint(tcb.x) - ox), vy = (int)(__float_as_uint(tcb.y) - oy);
+            ubx0 = min(ubx0, __reduce_min_sync(0xffffffffu, have ? vx : 0x7fffffff));
+            ubx1 = max(ubx1, __reduce_max_sync(0xffffffffu, have ? vx : -1));
+            uby0 = min(uby0, __reduce_min_sync(0xffffffffu, have ? vy : 0x7fffffff));
+            uby1 = max(uby1, __reduce_max_sync(0xffffffffu, have ? vy : -1));
         }
         push_record(have, pix, cell, w.w);
         const unsigned dballot = __ballot_sync(0xffffffffu, defer_me);
@@ -465,8 +481,15 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
         for (int k = 0; k < kFGather; ++k) {
             if (FMT == 0) bits[k] = (cellf[k] != kNone) ? (s_tab_r[lr[k]] & s_tab_g[lg[k]]) : 0u;
             else bits[k] = (cellf[k] != kNone) ? s_tab_r[lr[k]] : 0u;
+            if constexpr (MODE == 0) {
+                // ordered update: fire-and-forget RED.OR into the frame's slot, nothing comes back
+                if (!bits[k]) continue;
+                const bool boost = (bits[k] & lane_bit) && (cellf[k] >> 31);
+                atomicOr(F.mask + (cellf[k] & 0x7fffffffu), boost ? (bits[k] | (1u << gp.c)) : bits[k]);
+            }
         }
-        if constexpr (MODE == 1) {
+        if constexpr (MODE == 0) {
+        } else if constexpr (MODE == 1) {
             // third compaction: only the records of mapped classes go on
 #pragma unroll
             for (int k = 0; k < kFGather; ++k) {
@@ -483,14 +506,10 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
                 const uint32_t cell = cellf[k] & 0x7fffffffu;
                 const bool boost = (bits[k] & lane_bit) && (cellf[k] >> 31);
                 want[k] = boost ? (bits[k] | (1u << gp.c)) : bits[k];          // the bits this point wants set
-                if (MODE == 0) {
-                    atomicOr(F.mask + cell, want[k]);                          // result unused: RED.OR
-                } else {
-                    old[k] = atomicOr(F.mask + cell, want[k]);                 // what the frame had set before
-                    cellf[k] = cell;
-                }
+                old[k] = atomicOr(F.mask + cell, want[k]);                     // what the frame had set before
+                cellf[k] = cell;
             }
-            if (MODE == 2) {
+            {
 #pragma unroll
                 for (int k = 0; k < kFGather; ++k) {
                     uint32_t fresh = want[k] & ~old[k];   // inactive slots: want == 0
@@ -590,7 +609,12 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
     }
 
     // ---- bounding box: lane -> warp -> block (shared atomics) -> global
-    if (__any_sync(0xffffffffu, fbx1 >= fbx0)) {
+    if (!kBoxInRegs) {
+        if (lane == 0 && ubx1 >= ubx0) {
+            atomicMin(&s_box[0], ubx0); atomicMax(&s_box[1], ubx1);
+            atomicMin(&s_box[2], uby0); atomicMax(&s_box[3], uby1);
+        }
+    } else if (__any_sync(0xffffffffu, fbx1 >= fbx0)) {
         // magic-shifted float -> cell coordinate: bits - (bits(magic) - I0); clamp_c = magic - I0
         const int ox = (int)__float_as_uint(fk.clamp_c.x), oy = (int)__float_as_uint(fk.clamp_c.y);
         const bool any = fbx1 >= fbx0;
