@@ -305,6 +305,20 @@ SMAP_API int smap_clamp_negative(double *map_dev, int64_t n_elements, int device
 SMAP_API int smap_warp_perspective(const uint8_t *src_dev, int src_h, int src_w, int channels, const double h_host[9],
                                    uint8_t *dst_dev, int dst_h, int dst_w, int device, void *stream);
 
+/* ---- generate_convex_hull (src/semantic_convex_hull.py:17-91): the per-pixel part -----------------------------------
+ * smap_hull_components: mask = (img == index), cv2.erode(mask, ones(3, 3)), 8-connected components of what is left.
+ * labels_dev[p] = pixel index of the raster-first pixel of p's component (-1 outside the mask); areas_dev[root] = pixels
+ * of the component (0 elsewhere).  img_dev: (h, w) uint8, as cv2.erode requires of the reference's input; scratch_dev:
+ * h * w bytes.  h * w < 2^31.
+ * smap_hull_row_extremes: per image row the smallest / largest column of component `root`, with the component's first
+ * pixel left out as the reference leaves it out (:70); rowmin_dev[y] = INT_MAX, rowmax_dev[y] = -1 for rows it misses.
+ * The convex hull of those <= 2 h points is the hull cv2.convexHull returns for the whole component (the host wrapper
+ * semantic_convex_hull.py finishes there). */
+SMAP_API int smap_hull_components(const uint8_t *img_dev, int h, int w, int index, uint8_t *scratch_dev, int32_t *labels_dev,
+                                  int32_t *areas_dev, int device, void *stream);
+SMAP_API int smap_hull_row_extremes(const int32_t *labels_dev, int h, int w, int root, int32_t *rowmin_dev,
+                                    int32_t *rowmax_dev, int device, void *stream);
+
 /* ---- grid access ------------------------------------------------------------------------------- */
 SMAP_API int smap_map_ptr(smap_handle *h, double **map_dev, int64_t *n_elements);
 SMAP_API int smap_clear(smap_handle *h, void *stream);            /* self.map = np.zeros(...)  src/mapping_replay.py:181 */

@@ -331,3 +331,41 @@ def load_reference_color_map():
                 sys.modules.pop(name, None)
     return types.SimpleNamespace(apply_color_map=mod.apply_color_map, get_labels=mod.get_labels,
                                  config_19=os.path.join(REF, 'config', 'config_19.json'))
+
+
+def load_reference_convex_hull():
+    """The reference's ``generate_convex_hull`` (``src/semantic_convex_hull.py:17-91``), unmodified.  Its one absent
+    dependency on the path is ``skimage.measure.label`` (scikit-image is not in this image): the stand-in below labels
+    the 8-connected components with ``scipy.ndimage.label`` -- numbered in raster order of their first pixel, as
+    scikit-image numbers them -- and the function's result does not depend on the numbering anyway unless the caller
+    names component indices itself (``index_to_vitualize``)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REF)
+    import importlib.util
+    from scipy import ndimage
+
+    def label(img, connectivity=None, **kw):
+        nd = img.ndim
+        conn = nd if connectivity is None else connectivity
+        structure = ndimage.generate_binary_structure(nd, conn)
+        out, _ = ndimage.label(img, structure=structure)
+        return out.astype(np.int64)
+
+    measure = _inert_module('skimage.measure', label=label)
+    stubs = {'skimage': _inert_module('skimage', measure=measure), 'skimage.measure': measure,
+             'matplotlib': _inert_module('matplotlib'), 'matplotlib.pyplot': _inert_module('matplotlib.pyplot'),
+             'rospy': _inert_module('rospy')}
+    saved = {name: sys.modules.get(name) for name in stubs}
+    sys.modules.update(stubs)
+    try:
+        path = os.path.join(REF, 'src', 'semantic_convex_hull.py')
+        spec = importlib.util.spec_from_file_location('_ref_semantic_convex_hull', path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for name, val in saved.items():
+            if val is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = val
+    return mod.generate_convex_hull

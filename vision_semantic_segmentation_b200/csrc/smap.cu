@@ -13,6 +13,7 @@
 #include "smap_fuse.cuh"
 #include "smap_comm.cuh"
 #include "smap_warp.cuh"
+#include "smap_hull.cuh"
 
 #ifndef SMAP_AUX_STREAMS
 #define SMAP_AUX_STREAMS 4      // internal streams the per-frame k_fuse launches of a batch alternate over
@@ -1530,6 +1531,39 @@ int smap_warp_perspective(const uint8_t* src_dev, int src_h, int src_w, int chan
         case 3: k_warp_perspective<3><<<grid, 256, 0, st>>>(p, src_dev, dst_dev); break;
         default: k_warp_perspective<4><<<grid, 256, 0, st>>>(p, src_dev, dst_dev); break;
     }
+    CK(cudaGetLastError());
+    return SMAP_OK;
+}
+
+int smap_hull_components(const uint8_t* img_dev, int h, int w, int index, uint8_t* scratch_dev, int32_t* labels_dev,
+                         int32_t* areas_dev, int device, void* stream) {
+    if (!img_dev || !scratch_dev || !labels_dev || !areas_dev) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (h <= 0 || w <= 0) return fail(SMAP_ERR_INVALID, "empty image");
+    if ((int64_t)h * w >= ((int64_t)1 << 31) || h > 65535) return fail(SMAP_ERR_INVALID, "image too large");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t n = (int64_t)h * w;
+    const dim3 grid2((unsigned)ceil_div(w, 256), (unsigned)h);
+    const unsigned grid1 = (unsigned)ceil_div(n, 256);
+    k_hull_erode<<<grid2, 256, 0, st>>>(img_dev, h, w, index, scratch_dev);
+    k_ccl_init<<<grid1, 256, 0, st>>>(scratch_dev, n, labels_dev, areas_dev);
+    k_ccl_merge<<<grid2, 256, 0, st>>>(scratch_dev, h, w, labels_dev);
+    k_ccl_flatten<<<grid1, 256, 0, st>>>(n, labels_dev, areas_dev);
+    CK(cudaGetLastError());
+    return SMAP_OK;
+}
+
+int smap_hull_row_extremes(const int32_t* labels_dev, int h, int w, int root, int32_t* rowmin_dev, int32_t* rowmax_dev,
+                           int device, void* stream) {
+    if (!labels_dev || !rowmin_dev || !rowmax_dev) return fail(SMAP_ERR_INVALID, "NULL argument");
+    if (h <= 0 || w <= 0 || h > 65535) return fail(SMAP_ERR_INVALID, "bad image size");
+    if (root < 0 || (int64_t)root >= (int64_t)h * w) return fail(SMAP_ERR_INVALID, "root outside the image");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    k_fill_i32<<<(unsigned)ceil_div(h, 256), 256, 0, st>>>(rowmin_dev, h, 0x7fffffff);
+    k_fill_i32<<<(unsigned)ceil_div(h, 256), 256, 0, st>>>(rowmax_dev, h, -1);
+    const dim3 grid2((unsigned)ceil_div(w, 256), (unsigned)h);
+    k_hull_row_extremes<<<grid2, 256, 0, st>>>(labels_dev, h, w, root, rowmin_dev, rowmax_dev);
     CK(cudaGetLastError());
     return SMAP_OK;
 }
