@@ -26,7 +26,9 @@
 // Variants measured and NOT kept (numbers in profiles/r1*_ncu_summary.md, profiles/r2_sweep*.log; the code is in the
 // history up to commit cf06422): a per-warp TMA stage ring for the cloud, one persistent launch per batch, launches
 // with blockIdx.y = frame, register-carried software pipelines of the label loads / atomics, L2 / L1 prefetch hints
-// for the label image, the cloud and the records' label bytes.
+// for the label image, the cloud and the records' label bytes; round 2 (profiles/r2_rejected_variants.md): the cull as
+// scalar FFMAs with constant-bank operands, the cull's constants read from shared memory (LDS.128), third grids on three
+// or six streams, the running box in uniform registers for the count update.
 // ------------------------------------------------------------------------------------------------
 #pragma once
 #include "smap_kernels.cuh"
