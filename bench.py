@@ -550,11 +550,12 @@ def run_b200(args):
         # every rank's own view of the region (the line's ms_per_step is the MAX): its time, its median block, how long
         # its host took to queue the region, its SM clock under load and throttle reasons
         mine = torch.tensor([ms, float(np.median(block_ms)), host_enqueue_ms, clocks.get("sm_mhz") or 0.0,
-                             float(sampler.reason_bits)], dtype=torch.float64, device=dev)
+                             float(sampler.reason_bits), float(len(os.sched_getaffinity(0)))], dtype=torch.float64, device=dev)
         allr = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        per_rank = [{"rank": i, "region_ms": float(v[0]), "median_block_ms_per_step": float(v[1]) / args.steps,
-                     "host_enqueue_ms": float(v[2]), "sm_mhz": float(v[3]), "clock_event_reason_bits": int(v[4])}
+        per_rank = [{"rank": i, "region_ms": float(v[0]), "median_block_us_per_step": 1e3 * float(v[1]) / args.steps,
+                     "host_enqueue_ms": float(v[2]), "sm_mhz": float(v[3]), "clock_event_reason_bits": int(v[4]),
+                     "cpus_bound_to": int(v[5])}
                     for i, v in enumerate(x.cpu().numpy() for x in allr)]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
