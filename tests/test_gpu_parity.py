@@ -250,6 +250,38 @@ def test_batched_launch_equals_sequential_frames(name, ordered):
     dm.close()
 
 
+@pytest.mark.parametrize("name,ordered", [("cfg1_c5_count", False), ("cfg1_c19_count", False), ("cfg1_c5_count", True)])
+def test_graph_and_plain_launches_agree(name, ordered, monkeypatch):
+    """A chunk's k_fuse launches go out as one CUDA graph launch (re-parameterised per chunk) or, with
+    SMAP_FUSE_GRAPH=0, as per-frame launches on the internal streams: same grids, chunk after chunk (the second and
+    third call reuse and update the instantiated graphs; 5 frames and 21 frames need different ones)."""
+    case = Case(name)
+    base = [case.frame(f) for f in range(3)]
+    grids = []
+    for use_graph in ("1", "0"):
+        monkeypatch.setenv("SMAP_FUSE_GRAPH", use_graph)
+        dm = make_mapper(case)
+        if ordered:
+            dm.notify_map_modified()
+        keep = []
+        got = []
+        for order in ([0, 1, 2, 1, 0], [2, 2, 1, 0, 1, 2, 0] * 3, [1, 0, 2, 2, 1]):
+            frames_dev = []
+            for i in order:
+                pcd, points, image, T = base[i]
+                dp, di = dev(points), dev(image)
+                keep.append((dp, di))
+                frames_dev.append(dm.make_frame(dp, di, T, 0))
+            dm.integrate_batch(frames_dev)
+            got.append(dm.map.cpu().numpy().copy())
+        grids.append(got)
+        dm.close()
+    want = _oracle_grid(case, [base[i] for i in [0, 1, 2, 1, 0] + [2, 2, 1, 0, 1, 2, 0] * 3 + [1, 0, 2, 2, 1]])
+    for a, b in zip(*grids):
+        assert np.array_equal(a, b)
+    assert np.array_equal(grids[0][-1], want)
+
+
 def test_many_classes_and_mask_slots_stay_clean():
     """28 classes (4 register chunks in the apply kernel, boost bit 28); 20 frames through the same mask slot:
     any word left uncleared by k_apply would leak into a later frame."""
