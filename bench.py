@@ -103,6 +103,9 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=8000, help="cfg4: frames of the whole job, sharded over the ranks")
     ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=48, help="frames of the end-to-end legs")
+    ap.add_argument("--clock-period-ms", type=float, default=1.0,
+                    help="period of the NVML clock / throttle-reason polling thread during the timed region (0: only "
+                         "the two direct samples taken while the region is queued)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-render", action="store_true")
@@ -134,8 +137,8 @@ class ClockSampler(object):
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+    def __init__(self, index, period_s=0.001):
+        self.index, self.lines, self.proc, self.period_s = index, [], None, period_s
         self.samples, self.reason_bits, self.max_mhz = [], 0, None
         self._stop, self._thread, self._nvml = threading.Event(), None, None
 
@@ -147,7 +150,7 @@ class ClockSampler(object):
                 self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(self.period_s)
 
     def sample_now(self):
         """One sample from the calling thread (called right after the timed loop has been queued, while the GPU is
@@ -233,8 +236,11 @@ def make_ring(args, rank, n=None):
     pose, T (4,4) f64 world -> velodyne, camera slot (cfg5: cam1 / cam6 alternate)"""
     frames = []
     for i in range(args.ring if n is None else n):
-        f = rank * 100000 + i
-        fr = syn.synthetic_frame(SEED, f, args.points, blocky=(i % 2 == 1), as_float64=False, with_ids=True)
+        # every rank drives the SAME stretch of road (poses of frames 0 .. ring - 1: inside the map) with its own clouds and
+        # label images, so the ranks do equal work.  (Up to round-2 commit 7b01586 rank r used frame indices 10^5 r + i,
+        # i.e. poses hundreds of kilometres off the map: ranks 1 - 3 had nothing to update and ran 13 % faster than one
+        # GPU alone, ranks 4 - 7 had coordinates beyond 2^20 m -- the exact-arithmetic path -- and ran 25 % slower.)
+        fr = syn.synthetic_frame(SEED + 7919 * rank, i, args.points, blocky=(i % 2 == 1), as_float64=False, with_ids=True)
         fr["T"] = np.linalg.inv(tr.get_transform_from_pose(fr["pose"]) @ syn.velodyne_to_baselink())
         fr["camera"] = (i % 2) if args.workload == "cfg5" else 0
         fr["camera_id"] = 6 if fr["camera"] == 1 else 1
@@ -514,8 +520,8 @@ def run_b200(args):
 
     # ---- device-resident throughput (`value`)
     launches_before = dm.stats()["kernel_launches"]
-    sampler = ClockSampler(local_rank)
-    sampler.start(thread=(rank == 0))
+    sampler = ClockSampler(local_rank, period_s=args.clock_period_ms * 1e-3)
+    sampler.start(thread=(rank == 0 and args.clock_period_ms > 0))
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(repeats + 1)]
     e_end = torch.cuda.Event(enable_timing=True)
     barrier()
