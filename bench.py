@@ -11,8 +11,8 @@ in HBM (ring >> L2), so every step streams its cloud and image from DRAM.  Frame
 (smap_integrate_batch: one fused kernel per frame; inside a batch a launch takes half of the resident block slots and
 the launches alternate over internal streams, so two frames run side by side).
 
-Timed region: R blocks of exactly K steps, back to back, R chosen so that the region lasts >= 50 ms (a 20-step block is
-0.3 ms); barrier + synchronize on both sides, CUDA events, max over ranks.  `ms_per_step` = region / (R K); the per-block
+Timed region: R blocks of exactly K steps, back to back, R chosen so that the region lasts >= 50 ms on one GPU and
+>= 300 ms on several (a 20-step block is 0.3 ms); barrier + synchronize on both sides, CUDA events, max over ranks.  `ms_per_step` = region / (R K); the per-block
 figures (median / min / max) are printed next to it.
 N > 1: one process per GPU (torchrun), frames sharded by rank (weak scaling: every rank integrates K frames per block).
 Every --exchange-every (256) frames the ranks' increments are summed (smap_exchange_async: touched window only, counts
@@ -96,7 +96,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32, help="frames handed to smap_integrate_batch per call (at most)")
     ap.add_argument("--repeats", type=int, default=0,
                     help="blocks of --steps steps in the timed region (0: as many as make the region last >= 50 ms)")
-    ap.add_argument("--min-region-ms", type=float, default=50.0)
+    ap.add_argument("--min-region-ms", type=float, default=0.0,
+                    help="length the timed region is stretched to by repeating the block of --steps steps (0: 50 ms on "
+                         "one GPU, 300 ms on several -- one late rank stalls every rank at the next exchange, and such "
+                         "hiccups of 1 - 30 ms were seen once per run on the 8-GPU boxes whatever the launch path)")
     ap.add_argument("--exchange-every", type=int, default=256,
                     help="N > 1: frames a rank integrates between two exchanges of the streaming sum (as "
                          "SemanticMapping.EXCHANGE_EVERY); the last exchange ends the timed region")
@@ -509,7 +512,8 @@ def run_b200(args):
     e1.record()
     torch.cuda.synchronize()
     est = max(e0.elapsed_time(e1), 1e-3)
-    repeats = args.repeats if args.repeats > 0 else int(min(2000, max(1, np.ceil(args.min_region_ms / est))))
+    min_region_ms = args.min_region_ms if args.min_region_ms > 0 else (50.0 if world == 1 else 300.0)
+    repeats = args.repeats if args.repeats > 0 else int(min(4000, max(1, np.ceil(min_region_ms / est))))
     if world > 1:   # every rank must run the same number of blocks
         t = torch.tensor([repeats], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -760,7 +764,8 @@ def run_b200(args):
             "metric": "points_fused_per_sec", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "repeats": repeats, "ms_per_step": ms / total_steps,
             "block_ms_per_step": {"median": float(np.median(block_ms)) / args.steps, "min": float(block_ms.min()) / args.steps,
-                                  "max": float(block_ms.max()) / args.steps},
+                                  "max": float(block_ms.max()) / args.steps, "slowest_block": int(np.argmax(block_ms)),
+                                  "blocks": int(len(block_ms))},
             "timed_region_ms": ms, "higher_is_better": True,
             "scaling": "strong" if args.workload == "cfg4" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "frames_per_sec": value / n_pts,
