@@ -529,6 +529,9 @@ def run_b200(args):
     sampler.start(thread=(rank == 0 and args.clock_period_ms > 0))
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(repeats + 1)]
     e_end = torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()          # no collector pause on any rank inside the region (one late host stalls every rank's exchange)
     barrier()
     xch["on"] = world > 1
     t_host0 = time.perf_counter()
@@ -551,6 +554,7 @@ def run_b200(args):
     e_end.record()
     sampler.sample_now()
     barrier()
+    gc.enable()
     ms = marks[0].elapsed_time(e_end)
     block_ms = np.array([marks[r].elapsed_time(marks[r + 1]) for r in range(repeats)])
     clocks = sampler.stop()
