@@ -384,10 +384,12 @@ k_render_bulk(const double* __restrict__ map, int mh, int mw, int c_arg, const _
         }
     }
     if (!rgb) return;
-    __syncthreads();
-    // ---- colours out: warp w writes tile rows w, w + 8, ...: bytes up to the first 4-byte boundary, words, bytes
+    __syncwarp();
+    // ---- colours out: every warp writes the R rows of its own strip (no block barrier: a warp that is done leaves):
+    // bytes up to the first 4-byte boundary, words, bytes
     const int nb = min(kRX, mw - x0) * 3;
-    for (int r = warp; r < TY; r += kRStrips) {
+    for (int i = 0; i < R; ++i) {
+        const int r = warp * R + i;
         const int y = y0 + r;
         if (y >= mh) break;
         uint8_t* g = rgb + ((size_t)y * mw + x0) * 3;
