@@ -319,6 +319,11 @@ SMAP_API int smap_hull_components(const uint8_t *img_dev, int h, int w, int inde
 SMAP_API int smap_hull_row_extremes(const int32_t *labels_dev, int h, int w, int root, int32_t *rowmin_dev,
                                     int32_t *rowmax_dev, int device, void *stream);
 
+/* Dev builds with -DSMAP_DEBUG_BOUNDS (tools/bounds_check.sh): out[0] = index violations the kernels counted since the
+ * library was loaded (stack pushes, label loads, mask / tag / grid updates, staged tiles), out[1] = code of the first
+ * one.  Synchronises the device.  Returns SMAP_ERR_STATE in a normal build (nothing is checked there). */
+SMAP_API int smap_debug_bounds(unsigned long long out[2]);
+
 /* ---- grid access ------------------------------------------------------------------------------- */
 SMAP_API int smap_map_ptr(smap_handle *h, double **map_dev, int64_t *n_elements);
 SMAP_API int smap_clear(smap_handle *h, void *stream);            /* self.map = np.zeros(...)  src/mapping_replay.py:181 */

@@ -26,7 +26,7 @@ EXPORTS = [
     "smap_debug_nearest_map", "smap_cloud_to_f32x4",
     "smap_comm_unique_id", "smap_comm_init", "smap_comm_attach", "smap_comm_destroy", "smap_allreduce",
     "smap_reduce_scatter_rows", "smap_comm_get_info", "smap_comm_streaming", "smap_exchange_async", "smap_exchange_flush",
-    "smap_clamp_negative", "smap_warp_perspective", "smap_hull_components", "smap_hull_row_extremes",
+    "smap_clamp_negative", "smap_warp_perspective", "smap_hull_components", "smap_hull_row_extremes", "smap_debug_bounds",
 ]
 SMAP_COMM_ID_BYTES = 128
 
@@ -174,6 +174,8 @@ def load():
     L.smap_hull_components.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp]
     L.smap_hull_row_extremes.restype = i32
     L.smap_hull_row_extremes.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
+    L.smap_debug_bounds.restype = i32
+    L.smap_debug_bounds.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
     L.smap_warp_perspective.restype = i32
     L.smap_warp_perspective.argtypes = [vp, i32, i32, i32, ctypes.POINTER(ctypes.c_double), vp, i32, i32, i32, vp]
     L.smap_comm_get_info.restype = i32

@@ -1711,6 +1711,18 @@ int smap_hull_row_extremes(const int32_t* labels_dev, int h, int w, int root, in
     return SMAP_OK;
 }
 
+int smap_debug_bounds(unsigned long long out[2]) {
+    if (!out) return fail(SMAP_ERR_INVALID, "NULL argument");
+#ifdef SMAP_DEBUG_BOUNDS
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out, g_bounds, sizeof(unsigned long long) * 2));
+    return SMAP_OK;
+#else
+    out[0] = out[1] = 0ull;
+    return fail(SMAP_ERR_STATE, "not a -DSMAP_DEBUG_BOUNDS build");
+#endif
+}
+
 int smap_clamp_negative(double* map_dev, int64_t n_elements, int device, void* stream) {
     if (n_elements < 0 || (n_elements > 0 && !map_dev)) return fail(SMAP_ERR_INVALID, "bad grid");
     if (n_elements == 0) return SMAP_OK;

@@ -12,6 +12,21 @@
 
 namespace smap {
 
+// -DSMAP_DEBUG_BOUNDS (dev build, tools/bounds_check.sh): every index the kernels form for a stack push, a label load, a
+// mask / tag / grid update or a staged tile is checked against its array; violations are counted (never trapped) and
+// read back with smap_debug_bounds.  compute-sanitizer is not available on the GPU pool; this is the stand-in.
+#ifdef SMAP_DEBUG_BOUNDS
+__device__ unsigned long long g_bounds[2];   // violations, code of the first one
+#define SMAP_BOUNDS(cond, code)                                                   \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            if (atomicAdd(&g_bounds[0], 1ull) == 0ull) g_bounds[1] = (code);       \
+        }                                                                          \
+    } while (0)
+#else
+#define SMAP_BOUNDS(cond, code) do { } while (0)
+#endif
+
 constexpr int kMaxBatch = 16;  // frames per launch (one cell-mask slot each)
 
 // Per-frame projection constants (kernel parameter -> copied to shared memory once per block and frame).

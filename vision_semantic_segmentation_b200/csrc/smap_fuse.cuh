@@ -290,6 +290,7 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
         const unsigned ballot = __ballot_sync(0xffffffffu, have);
         if (have) {
             const uint32_t extreme = (it < 2.0f || it > 14.0f) ? 0x80000000u : 0u;   // src/mapping_replay.py:290
+            SMAP_BOUNDS(rn + __popc(ballot & lt_mask) < (uint32_t)kFRecCap, 101);
             recs[rn + __popc(ballot & lt_mask)] = make_uint2(pix, cell | extreme);
         }
         rn += __popc(ballot);
@@ -378,6 +379,7 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
         }
 #endif
         if (dballot) {
+            SMAP_BOUNDS(!defer_me || dn + __popc(dballot & lt_mask) < (uint32_t)kFDeferCap, 102);
             if (defer_me) defer[dn + __popc(dballot & lt_mask)] = w;
             dn += __popc(dballot);
         }
@@ -417,6 +419,7 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
             if (i < count) {
                 const uint2 u = upds[first + i];
                 const uint32_t cell = u.x & 0x7fffffffu, bits = u.y;
+                SMAP_BOUNDS(cell < (uint32_t)gp.mh * (uint32_t)gp.mw && bits < (1u << gp.c), 111);
                 const bool boost = (bits & lane_bit) && (u.x >> 31);
                 // element indices fit 32 bits (checked by the host)
                 uint32_t* trow = B.tags + (size_t)(cell * c1);
@@ -461,11 +464,13 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
                 const uint32_t pix = rec.x;
                 const uint8_t* img = F.image;
                 if (FMT == 1) {
+                    SMAP_BOUNDS(pix < (uint32_t)F.src_w * 65536u, 121);   // (the plane's height is not a kernel constant)
                     lr[k] = __ldg(img + pix);   // the class id
                 } else if (F.img64) {
                     // R and G from ONE aligned 8-byte load (a second one only when R is the last byte of its 8: one
                     // pixel in eight): the L1 sees one sector request per point instead of two
                     const uint32_t a = pix * 3u;   // < 3 * 2^28
+                    SMAP_BOUNDS(pix < (uint32_t)F.fp.img_w * (uint32_t)F.fp.img_h, 122);
                     const uint2 wv = __ldg(reinterpret_cast<const uint2*>(img + (a & ~7u)));
                     const uint32_t sh = (a & 7u) * 8u;
                     const uint64_t v = (((uint64_t)wv.y << 32) | wv.x) >> sh;
@@ -487,6 +492,7 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
                 // ordered update: fire-and-forget RED.OR into the frame's slot, nothing comes back
                 if (!bits[k]) continue;
                 const bool boost = (bits[k] & lane_bit) && (cellf[k] >> 31);
+                SMAP_BOUNDS((cellf[k] & 0x7fffffffu) < (uint32_t)gp.mh * (uint32_t)gp.mw, 112);
                 atomicOr(F.mask + (cellf[k] & 0x7fffffffu), boost ? (bits[k] | (1u << gp.c)) : bits[k]);
             }
         }
@@ -496,6 +502,7 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
 #pragma unroll
             for (int k = 0; k < kFGather; ++k) {
                 const unsigned ballot = __ballot_sync(0xffffffffu, bits[k] != 0u);
+                SMAP_BOUNDS(!bits[k] || un + __popc(ballot & lt_mask) < (uint32_t)kFUpdCap, 103);
                 if (bits[k]) upds[un + __popc(ballot & lt_mask)] = make_uint2(cellf[k], bits[k]);
                 un += __popc(ballot);
             }
@@ -508,6 +515,7 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
                 const uint32_t cell = cellf[k] & 0x7fffffffu;
                 const bool boost = (bits[k] & lane_bit) && (cellf[k] >> 31);
                 want[k] = boost ? (bits[k] | (1u << gp.c)) : bits[k];          // the bits this point wants set
+                SMAP_BOUNDS(cell < (uint32_t)gp.mh * (uint32_t)gp.mw, 113);
                 old[k] = atomicOr(F.mask + cell, want[k]);                     // what the frame had set before
                 cellf[k] = cell;
             }
@@ -585,6 +593,7 @@ k_fuse(const __grid_constant__ FuseLaunch B, const __grid_constant__ GridParams 
             const float4 w = buf[j];
             const bool pass = cull32(fk, w.x, w.y, w.z) & (j * 32 + lane < pts);
             const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+            SMAP_BOUNDS(!pass || qn + __popc(ballot & lt_mask) < (uint32_t)kFQueueCap, 104);
             if (pass) queue[qn + __popc(ballot & lt_mask)] = w;
             qn += __popc(ballot);
         }

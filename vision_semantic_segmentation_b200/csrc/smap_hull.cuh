@@ -77,6 +77,7 @@ k_ccl_merge(const uint8_t* __restrict__ mask, int h, int w, int* __restrict__ la
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
     const int p = y * w + x;
+    SMAP_BOUNDS(p >= 0 && (int64_t)p < (int64_t)h * w, 401);
     if (!mask[p]) return;
     if (x > 0 && mask[p - 1]) ccl_unite(lab, p, p - 1);
     if (y > 0) {

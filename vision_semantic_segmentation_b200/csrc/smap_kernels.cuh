@@ -319,6 +319,7 @@ k_apply(double* __restrict__ map, const __grid_constant__ ApplyParams ap, FrameB
             for (int f = 0; f < kMaxBatch; ++f) anyv |= w[f][v];
             if (!anyv) continue;
             const uint32_t cell = cell0 + v;
+            SMAP_BOUNDS(cell / (uint32_t)mw <= (uint32_t)x1 && cell % (uint32_t)mw >= (uint32_t)y0 && cell % (uint32_t)mw <= (uint32_t)y1, 201);
             double* row = map + (size_t)cell * c;
             double acc[8 * NJ];
 #pragma unroll

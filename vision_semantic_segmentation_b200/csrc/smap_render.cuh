@@ -273,6 +273,9 @@ k_render_bulk(const double* __restrict__ map, int mh, int mw, int c_arg, const _
         for (int r = lane; r < rows; r += 32) {
             const int ys = reflect101(y0 - H + r, mh);
             const double* src = map + ((size_t)ys * mw + xa) * c;
+            SMAP_BOUNDS(ys >= 0 && ys < mh && xa >= 0 && xb <= mw && xb > xa && (row_bytes & 15u) == 0u &&
+                        ((reinterpret_cast<uintptr_t>(src)) & 15u) == 0u && r < TY + 2 * H &&
+                        (xa - (x0 - OFF)) >= 0 && (xa - (x0 - OFF)) + (xb - xa) <= SL, 301);
             const uint32_t dst = smem_addr32(tile + (size_t)r * pitch + (xa - (x0 - OFF)) * c);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar) : "memory");

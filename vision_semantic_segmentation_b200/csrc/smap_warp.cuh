@@ -49,6 +49,8 @@ k_warp_perspective(const __grid_constant__ WarpParams p, const uint8_t* __restri
     const uint8_t* r0 = src + ((size_t)(y0ok ? sy : 0) * p.src_w) * CN;
     const uint8_t* r1 = src + ((size_t)(y1ok ? sy + 1 : 0) * p.src_w) * CN;
     const int c0 = (x0ok ? sx : 0) * CN, c1 = (x1ok ? sx + 1 : 0) * CN;
+    SMAP_BOUNDS((!y0ok || (sy >= 0 && sy < p.src_h)) && (!y1ok || sy + 1 < p.src_h) && (!x0ok || (sx >= 0 && sx < p.src_w)) &&
+                (!x1ok || sx + 1 < p.src_w), 501);
     uint8_t* o = dst + ((size_t)y * p.dst_w + x) * CN;
 #pragma unroll
     for (int k = 0; k < CN; ++k) {
