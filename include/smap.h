@@ -182,12 +182,16 @@ SMAP_API int smap_update(smap_handle *h, double *map_dev, const double *pcd_dev,
  * returns RGB labels and therefore takes RGB images only. */
 SMAP_API int smap_integrate(smap_handle *h, const smap_frame *frame, void *stream);
 
-/* Same rule for n_frames frames IN ORDER.  Frames are queued together in chunks (one fused launch per frame on
- * alternating internal streams, forked from and joined back into `stream` once per chunk).  Ordered update and count
- * update through the cell masks: chunks of up to 16 frames, each frame scatters into its own mask slot and the apply
- * kernel replays the slots in frame order per cell.  Tagged count update (identity matrix, C + 1 <= 8, grid of counts):
- * no per-frame state, chunks of up to 64 frames.  Either way the result is bit-identical to n_frames calls of
- * smap_integrate.  Frames of one call must share a point layout. */
+/* Same rule for n_frames frames IN ORDER.  Frames are queued together in chunks: one fused kernel per frame, four
+ * frames' kernels independent of each other (kernel i follows kernel i - 4), the whole chunk handed to `stream` as ONE
+ * CUDA graph launch -- instantiated once per (update mode, label format, frames) and re-parameterised per chunk; with
+ * SMAP_FUSE_GRAPH=0 in the environment, or for chunks of fewer than four frames, as per-frame launches on four internal
+ * streams forked from and joined back into `stream`.  Ordered update and count update through the cell masks: chunks
+ * of up to 16 frames, each frame scatters into its own mask slot and the apply kernel replays the slots in frame
+ * order per cell (the apply of one chunk runs on an internal stream beside the scatter kernels of the next chunk of the
+ * same call; `stream` joins it before the call returns).  Tagged count update (identity matrix, C + 1 <= 8, grid of
+ * counts): no per-frame state, chunks of up to 64 frames.  Either way the result is bit-identical to n_frames calls of
+ * smap_integrate.  Frames of one chunk must share a point layout. */
 SMAP_API int smap_integrate_batch(smap_handle *h, const smap_frame *frames_host, int n_frames, void *stream);
 
 /* Same as smap_integrate with HOST buffers: frame->points_dev / image_dev hold HOST pointers here.  Points (layout as
